@@ -1,0 +1,257 @@
+"""Pin the oracle (oracle/mifi_oracle.c + oracle/pj_oracle.c):
+
+  * against the reference's own known-answer tests, restated from
+    /root/reference/test/testInterpolation.cc (line numbers in each test);
+  * bit-for-bit against the golden vectors in tests/golden/, which were produced by the reference's own
+    src/interpolation.c compiled unmodified (tests/golden/make_golden.py);
+  * live against that compiled reference on fresh seeded inputs, when oracle/_ref/ exists.
+
+CPU only.
+"""
+import numpy as np
+import pytest
+
+from conftest import assert_bit_equal
+from oracle.oracle import (BICUBIC, BILINEAR, LATITUDE, LONGITUDE, NEAREST_NEIGHBOR, PROJ_AXIS)
+
+EMEP = "+ellps=sphere +a=127.4 +e=0 +proj=stere +lat_0=90 +lon_0=-32 +lat_ts=60 +x_0=7 +y_0=109"
+LATLONG = "+ellps=sphere +a=6370 +e=0 +proj=latlong"
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference known answers
+# ---------------------------------------------------------------------------------------------------
+def test_points2position(oracle):
+    # test/testInterpolation.cc:49-58
+    got = oracle.points2position([-3.0, 5.0, 1.3, 2.0, 6.0], [1.0, 2, 3, 4, 5], PROJ_AXIS)
+    assert np.allclose(got, [-4.0, 4.0, 0.3, 1.0, 5.0], atol=1e-10, rtol=0)
+
+
+def test_points2position_reverse(oracle):
+    # test/testInterpolation.cc:61-70
+    got = oracle.points2position([-3.0, 5.0, 1.3, 2.0, 6.0], [5.0, 4, 3, 2, 1], PROJ_AXIS)
+    assert np.allclose(got, [8.0, 0.0, 3.7, 3.0, -1.0], atol=1e-10, rtol=0)
+
+
+def test_get_values_f(oracle):
+    # test/testInterpolation.cc:73-80
+    assert oracle.get_values(NEAREST_NEIGHBOR, [1.0, 2.0, 1.0, 2.0], 0.3, 0.3, 2, 2, 1)[0] == 1.0
+
+
+def test_get_values_bilinear_f(oracle):
+    # test/testInterpolation.cc:83-112
+    f = np.array([1.0, 2.0, 2.0, 1 + np.sqrt(np.float32(2.0))], dtype=np.float32)
+    g = lambda x, y: float(oracle.get_values(BILINEAR, f, x, y, 2, 2, 1)[0])
+    assert abs(g(0.3, 0.0) - 1.3) < 1e-6
+    assert abs(g(0.3, 0.0001) - 1.3) < 1e-4
+    assert abs(g(0.0, 0.3) - 1.3) < 1e-6
+    assert abs(g(0.0001, 0.3) - 1.3) < 1e-4
+    assert not np.isnan(g(0, 0))
+    assert not np.isnan(g(1, 1))
+    for x, y in ((1.5, 0.5), (0.5, 1.5), (0.5, -0.5), (-0.5, 0.5)):
+        assert np.isnan(g(x, y))
+
+
+def test_get_values_bicubic_f(oracle):
+    # test/testInterpolation.cc:115-155
+    f = np.array([1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1], dtype=np.float32)
+    ft = f.reshape(4, 4).T.copy().ravel()
+    g = lambda a, x, y: float(oracle.get_values(BICUBIC, a, x, y, 4, 4, 1)[0])
+    assert g(f, 1, 1) == pytest.approx(2.0, rel=1e-5)
+    assert g(f, 1, 1.99999) == pytest.approx(2.0, rel=1e-5)
+    assert g(f, 1, 1.5) == pytest.approx(2.125, rel=1e-5)
+    assert g(f, 1.5, 1) == pytest.approx(2.0, rel=1e-5)
+    assert g(ft, 1, 1) == pytest.approx(2.0, rel=1e-5)
+    assert g(ft, 1.99999, 1) == pytest.approx(2.0, rel=1e-5)
+    assert g(ft, 1.5, 1) == pytest.approx(2.125, rel=1e-5)
+    assert g(ft, 1, 1.5) == pytest.approx(2.0, rel=1e-5)
+    for x, y in ((0.5, 1), (1, 0.5), (2.5, 1), (1, 2.5)):
+        assert np.isnan(g(f, x, y))
+
+
+def test_project_axes_emep_pole(oracle):
+    # test/testInterpolation.cc:265-278: all nine points lie north of 89 degrees
+    rc, x, y = oracle.project_axes(EMEP, LATLONG, [6.0, 7, 8], [108.0, 109, 110])
+    assert rc == 1
+    assert np.all(np.degrees(y) > 89)
+    # closed form (Snyder 21-1..4, sphere): the projection origin (7,109) is the pole itself
+    assert np.degrees(y[4]) == pytest.approx(90.0, abs=1e-9)
+
+
+def test_interpolate_f_emep(oracle, golden):
+    # test/testInterpolation.cc:280-393: country map, cell (lon 9, lat 25) == 32 for NN, bilinear, bicubic
+    g = golden("emep")
+    assert g["infield"][50, 93] == 4.0  # :346
+    for name, m in (("nn", NEAREST_NEIGHBOR), ("bilinear", BILINEAR), ("bicubic", BICUBIC)):
+        rc, out = oracle.interpolate_f(m, EMEP, g["infield"], np.arange(170) + 1.0, np.arange(150) + 1.0, PROJ_AXIS, PROJ_AXIS, 1,
+                                       LATLONG, g["lon"], g["lat"], LONGITUDE, LATITUDE)
+        assert rc == 1
+        assert abs(out[0, 25, 9] - 32) < 1e-6
+        assert_bit_equal(out, g[name], f"emep {name} vs compiled reference")
+
+
+def _rotate_setup(lon0_b):
+    a = "+ellps=sphere +a=127.4 +e=0 +proj=stere +lat_0=90 +lon_0=0 +lat_ts=60"
+    b = f"+ellps=sphere +a=127.4 +e=0 +proj=stere +lat_0=90 +lon_0={lon0_b} +lat_ts=60"
+    ax = np.arange(5) - 2.0
+    u = np.arange(25, dtype=np.float32)
+    v = 25 - np.arange(25, dtype=np.float32)
+    return a, b, ax, u, v
+
+
+@pytest.mark.parametrize("lon0,tol", [(90, 1e-4), (180, 1e-5)])
+def test_vector_reproject_rotate(oracle, lon0, tol):
+    # test/testInterpolation.cc:396-453 (90 deg: u -> -v, v -> u) and :455-512 (180 deg: both negated)
+    a, b, ax, u, v = _rotate_setup(lon0)
+    _, uo = oracle.interpolate_f(NEAREST_NEIGHBOR, a, u, ax, ax, 0, 0, 1, b, ax, ax, 0, 0)
+    _, vo = oracle.interpolate_f(NEAREST_NEIGHBOR, a, v, ax, ax, 0, 0, 1, b, ax, ax, 0, 0)
+    rc, ur, vr = oracle.vector_reproject_values(a, b, uo, vo, ax, ax, 0, 0, 1)
+    assert rc == 1
+    uo, vo, ur, vr = uo.ravel(), vo.ravel(), ur.ravel(), vr.ravel()
+    if lon0 == 90:
+        assert np.all(np.abs(vo - ur) < tol)
+        assert np.all(np.abs(uo + vr) < tol)
+    else:
+        assert np.all(np.abs(vo + vr) < tol)
+        assert np.all(np.abs(uo + ur) < tol)
+
+
+def test_vector_reproject_keep_size(oracle):
+    # test/testInterpolation.cc:515-583: |(u,v)| is preserved
+    ai = np.arange(4) + 6.0
+    aj = np.arange(4) + 108.0
+    lon = np.arange(4) * 60.0
+    lat = np.arange(4) / 2.0 + 88.5
+    u = np.arange(16, dtype=np.float32)
+    v = -16 + np.arange(16, dtype=np.float32)
+    _, uo = oracle.interpolate_f(NEAREST_NEIGHBOR, EMEP, u, ai, aj, 0, 0, 1, LATLONG, lon, lat, LONGITUDE, LATITUDE)
+    _, vo = oracle.interpolate_f(NEAREST_NEIGHBOR, EMEP, v, ai, aj, 0, 0, 1, LATLONG, lon, lat, LONGITUDE, LATITUDE)
+    rc, ur, vr = oracle.vector_reproject_values(EMEP, LATLONG, uo, vo, lon, lat, LONGITUDE, LATITUDE, 1)
+    assert rc == 1
+    ur, vr = ur.ravel(), vr.ravel()
+    d = ur.astype(np.float64)**2 + vr.astype(np.float64)**2 - uo.ravel().astype(np.float64)**2 - vo.ravel().astype(np.float64)**2
+    d = d[~np.isnan(d)]
+    assert d.size > 0 and np.all(np.abs(d) < 1e-3)
+
+
+def test_vector_reproject_directions(oracle):
+    # test/testInterpolation.cc:586-654
+    a = "+ellps=sphere +a=127.4 +e=0 +proj=stere +lat_0=90 +lon_0=0 +lat_ts=60"
+    ax = (np.arange(5) - 2) * 1000.0
+    xf, yf = np.meshgrid(ax, ax)
+    rc, m = oracle.vector_matrix_field(a, LATLONG, xf.ravel(), yf.ravel(), 5, 5)
+    assert rc == 1
+    ang = oracle.vector_reproject_direction(m, np.zeros(25, dtype=np.float32), 5, 5, 1)
+    close = lambda want, got: abs(got - want) <= 0.01 * max(abs(want), abs(got))
+    assert close(315, ang[0 + 5 * 0]) and close(270, ang[0 + 5 * 2]) and close(225, ang[0 + 5 * 4])
+    for j in (0, 1):
+        o = ang[2 + 5 * j]
+        o = o - 360 if o > 300 else o
+        assert close(10, 10 + o)
+    assert close(180, ang[2 + 5 * 3]) and close(180, ang[2 + 5 * 4])
+    assert close(45, ang[4 + 5 * 0]) and close(90, ang[4 + 5 * 2]) and close(135, ang[4 + 5 * 4])
+
+
+def test_string_to_method(oracle):
+    # src/interpolation.c:66-101, incl. the forward_undef_min quirk (:97-98)
+    assert oracle.string_to_method("bilinear") == BILINEAR
+    assert oracle.string_to_method("nearestneighbor") == NEAREST_NEIGHBOR
+    assert oracle.string_to_method("forward_mean") == 6
+    assert oracle.string_to_method("forward_undef_min") == 9
+    assert oracle.string_to_method("nope") == -1
+
+
+# ---------------------------------------------------------------------------------------------------
+# golden vectors produced by the compiled reference
+# ---------------------------------------------------------------------------------------------------
+def test_golden_kernels(oracle, golden):
+    g = golden("kernels")
+    field, px, py = g["field"], g["px"], g["py"]
+    iz, iy, ix = field.shape
+    for name, m in (("nn", NEAREST_NEIGHBOR), ("bilinear", BILINEAR), ("bicubic", BICUBIC)):
+        got = np.stack([oracle.get_values(m, field, px[i], py[i], ix, iy, iz) for i in range(px.size)], axis=1)
+        assert_bit_equal(got, g[name], f"{name} kernel")
+    # the masked set is exactly the reference's out-of-bounds branch (interpolation.c:936)
+    assert g["ub"].sum() > 0
+    assert np.all(np.isnan(g["bilinear"][:, g["ub"]]))
+
+
+def test_golden_points2position(oracle, golden):
+    g = golden("points2position")
+    for k in ("asc", "desc", "lon360", "lon180", "lon_regional", "lon_desc", "lat_desc", "nonuniform", "metric"):
+        got = oracle.points2position(g[k + "_in"], g[k + "_axis"], int(g[k + "_type"]))
+        want = g[k + "_out"]
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), k
+
+
+def test_golden_vectors(oracle, golden):
+    g = golden("vectors")
+    for k in ("ll_rot", "ll_stere", "ll_lcc", "stere_ll", "rot_stere"):
+        m = g[k + "_m"]
+        u, v = g[k + "_u"], g[k + "_v"]
+        oz, oy, ox = u.shape
+        ur, vr = oracle.vector_reproject_by_matrix(m, u, v, ox, oy, oz)
+        assert_bit_equal(ur.reshape(u.shape), g[k + "_ur"], k + " u")
+        assert_bit_equal(vr.reshape(v.shape), g[k + "_vr"], k + " v")
+        assert np.allclose(m[0::4]**2 + m[1::4]**2, 1.0, atol=1e-14)
+
+
+# ---------------------------------------------------------------------------------------------------
+# live against the compiled reference (only where oracle/_ref exists)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_oracle_equals_reference_kernels(oracle, reference, seed):
+    rng = np.random.default_rng(seed)
+    ix, iy, iz = int(rng.integers(2, 40)), int(rng.integers(2, 40)), int(rng.integers(1, 5))
+    field = rng.normal(0, 100, (iz, iy, ix)).astype(np.float32)
+    field[rng.random(field.shape) < 0.05] = np.nan
+    px = rng.uniform(-2, ix + 1, 1500)
+    py = rng.uniform(-2, iy + 1, 1500)
+    px[:200] = np.round(px[:200] * 2) / 2  # integers and half-cells
+    py[100:300] = np.round(py[100:300] * 2) / 2
+    for m in (NEAREST_NEIGHBOR, BILINEAR, BICUBIC):
+        for i in range(px.size):
+            if m == BILINEAR and oracle.bilinear_is_ub(px[i], py[i], ix, iy):
+                assert np.all(np.isnan(oracle.get_values(m, field, px[i], py[i], ix, iy, iz)))
+                continue
+            a = oracle.get_values(m, field, px[i], py[i], ix, iy, iz)
+            b = reference.get_values(m, field, px[i], py[i], ix, iy, iz)
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (m, px[i], py[i])
+
+
+def test_oracle_equals_reference_matrix(oracle, reference):
+    src = "+proj=latlong +a=6371000 +e=0 +no_defs"
+    for dst, xa, ya, xt, yt in (
+        ("+proj=ob_tran +o_proj=longlat +lon_0=-40 +o_lat_p=22 +R=6.371e+06 +no_defs", np.linspace(-10, 10, 11), np.linspace(-8, 8, 9),
+         LONGITUDE, LATITUDE),
+        ("+proj=stere +lat_0=90 +lon_0=0 +lat_ts=60 +a=6371000 +e=0", np.linspace(-2e6, 2e6, 11), np.linspace(-2e6, 2e6, 9), 0, 0),
+        ("+proj=lcc +lat_0=63 +lon_0=15 +lat_1=63 +lat_2=63 +no_defs +R=6.371e+06", np.linspace(-1e6, 1e6, 11), np.linspace(-2e6, 2e6, 9), 0, 0),
+    ):
+        rc1, m1 = oracle.vector_matrix(src, dst, xa, ya, xt, yt)
+        rc2, m2 = reference.vector_matrix(src, dst, xa, ya, xt, yt)
+        assert rc1 == rc2 == 1
+        assert np.array_equal(m1.view(np.uint64), m2.view(np.uint64)), dst
+    # lat/long target: bearing branch (interpolation.c:366-368, 408-412)
+    rc1, m1 = oracle.vector_matrix("+proj=stere +lat_0=90 +lon_0=0 +lat_ts=60 +a=6371000 +e=0", src, np.linspace(-30, 40, 9),
+                                   np.linspace(50, 85, 7), LONGITUDE, LATITUDE)
+    rc2, m2 = reference.vector_matrix("+proj=stere +lat_0=90 +lon_0=0 +lat_ts=60 +a=6371000 +e=0", src, np.linspace(-30, 40, 9),
+                                      np.linspace(50, 85, 7), LONGITUDE, LATITUDE)
+    assert rc1 == rc2 == 1 and np.array_equal(m1.view(np.uint64), m2.view(np.uint64))
+    xs = np.linspace(-1e6, 1e6, 13)
+    rc1, m1 = oracle.vector_matrix_points(src, "+proj=stere +lat_0=90 +lon_0=0 +lat_ts=60 +a=6371000 +e=0", 1, xs, xs[::-1])
+    rc2, m2 = reference.vector_matrix_points(src, "+proj=stere +lat_0=90 +lon_0=0 +lat_ts=60 +a=6371000 +e=0", 1, xs, xs[::-1])
+    assert rc1 == rc2 == 1 and np.array_equal(m1.view(np.uint64), m2.view(np.uint64))
+
+
+def test_oracle_cached_loop_equals_reference_kernels(oracle, reference):
+    """orc_cached_interpolate (restated CachedInterpolation.cc:118-147) == the reference kernels point by point"""
+    rng = np.random.default_rng(7)
+    inX, inY, inZ, outX, outY = 19, 13, 4, 31, 11
+    field = rng.normal(0, 1, (inZ, inY, inX)).astype(np.float32)
+    field[rng.random(field.shape) < 0.05] = np.nan
+    px = rng.uniform(0.2, inX - 1.2, outX * outY)  # interior + some strips, none in the UB corner
+    py = rng.uniform(-0.4, inY - 0.6, outX * outY)
+    for m in (NEAREST_NEIGHBOR, BILINEAR, BICUBIC):
+        a = oracle.cached_interpolate(m, px, py, inX, inY, outX, outY, field, nthreads=3)
+        b = reference.cached_interpolate(m, px, py, inX, inY, outX, outY, field)
+        assert_bit_equal(a, b, f"cached loop method {m}")
