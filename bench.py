@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config 2 (configs[1]):
+
+    synthetic ERA5-shape 1440x721 x 137 levels x 24 times float32, bilinear to a 2.5 km rotated-pole 2000x2000 grid.
+
+One "step" = one pass of the hot path over the whole (time x level) stack of one GPU: 24*137 = 3288 levels through
+CachedInterpolation::interpolateValues = 1.3152e10 regridded output values.  Inputs and outputs are resident in
+HBM for `value`; `e2e` runs the same workload through the C ABI with HOST buffers (pinned), copies inside the
+timed region.  N > 1: one process per GPU (torchrun), each owning its own contiguous slab of 3288 levels (weak
+scaling); rank 0 computes the index tables on its GPU and broadcasts the two fp64 position tables over NCCL.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--method bilinear|nearestneighbor|bicubic]
+
+--impl reference times the reference's own CPU implementation of the path (oracle/_ref: the reference's
+interpolation.c compiled unmodified, inside the restated CachedInterpolation loop, OpenMP over all host cores) on a
+bounded sample (one time step = 137 levels per step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SRC_PROJ = "+proj=latlong +a=6371000 +e=0 +no_defs"  # the default sphere the reference writes (ProjectionImpl.cc:139-160)
+DST_PROJ = "+proj=ob_tran +o_proj=longlat +lon_0=-40 +o_lat_p=22 +R=6.371e+06 +no_defs"  # test/testInterpolator.cc:413
+NX, NY, NZ, NT = 1440, 721, 137, 24
+OUT_N = 2000
+OUT_STEP_DEG = 0.0225  # ~2.5 km on R = 6371 km
+METRIC = "regridded output values/sec"
+METHODS = {"bilinear": 1, "nearestneighbor": 0, "bicubic": 2}
+
+
+def axes():
+    lon = np.arange(NX) * 0.25
+    lat = 90.0 - np.arange(NY) * 0.25
+    out = (np.arange(OUT_N) - (OUT_N - 1) / 2.0) * OUT_STEP_DEG
+    return lon, lat, out
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region"""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                                          str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_tables(method):
+    """index tables with the CPU oracle (projection + points2position + createReducedDomain)"""
+    from oracle import oracle as orc
+    o = orc.Oracle()
+    lon, lat, out = axes()
+    rc, x, y = o.project_axes(DST_PROJ, SRC_PROJ, np.radians(out), np.radians(out))
+    assert rc == 1
+    px = o.points2position(x, np.radians(lon), orc.LONGITUDE)
+    py = o.points2position(y, np.radians(lat), orc.LATITUDE)
+    red, px, py, inX, inY, x0, y0 = o.reduced_domain(px, py, NX, NY)
+    return px, py, inX, inY, x0, y0
+
+
+def synth_field_np(nlev, inX, inY, x0, y0, t=0, seed=20261018):
+    """v = 250 + 30 sin(lat) cos(2 lon) + 0.1 z + t + 0.5 N(0,1) on the cropped footprint"""
+    lon, lat, _ = axes()
+    lo = np.radians(lon[x0:x0 + inX])[None, None, :]
+    la = np.radians(lat[y0:y0 + inY])[None, :, None]
+    z = np.arange(nlev, dtype=np.float32)[:, None, None]
+    rng = np.random.default_rng(seed + t)
+    return (250 + 30 * np.sin(la) * np.cos(2 * lo) + 0.1 * z + t + 0.5 * rng.standard_normal((nlev, inY, inX))).astype(np.float32)
+
+
+def cpu_driver():
+    from oracle import oracle as orc
+    if orc.Reference.available():
+        r = orc.Reference()
+        return r, "reference", r.max_threads(), "reference src/interpolation.c (gcc -O2 -fopenmp, unmodified) in the restated " \
+                                                 "CachedInterpolation.cc:118-147 loop"
+    o = orc.Oracle()
+    return o, "port", os.cpu_count(), "oracle/mifi_oracle.c restatement (gcc -O2 -fopenmp)"
+
+
+def run_cpu(method_id, steps, warmup, nlev=NZ):
+    drv, kind, cores, how = cpu_driver()
+    px, py, inX, inY, x0, y0 = cpu_tables(method_id)
+    field = synth_field_np(nlev, inX, inY, x0, y0)
+    out = np.empty(nlev * OUT_N * OUT_N, dtype=np.float32)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        drv.cached_interpolate(method_id, px, py, inX, inY, OUT_N, OUT_N, field, out=out)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    values = nlev * OUT_N * OUT_N
+    total = sum(times)
+    return {"value": values * len(times) / total, "ms_per_step": 1e3 * total / len(times), "cores": int(cores), "kind": kind,
+            "sample": f"{nlev} levels (one time step) of the workload per step, {len(times)} steps after {warmup} warm-up; {how}",
+            "footprint": [int(inX), int(inY)]}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    method_id = METHODS[args.method]
+    r = run_cpu(method_id, max(1, args.steps), max(0, args.warmup))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "values/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.method), "sample_levels_per_step": NZ, "footprint": r["footprint"]},
+        "cpu_baseline": {"value": r["value"], "unit": "values/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "values/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_name(method):
+    return f"ERA5-shape {NX}x{NY}x{NZ}x{NT} float32 -> {OUT_N}x{OUT_N} rotated-pole {OUT_STEP_DEG} deg (~2.5 km), {method}"
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------------------------
+def main_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import fimex_b200 as fb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path in fimex_b200)"
+    torch.cuda.set_device(local)
+    fb.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    method = args.method
+    method_id = METHODS[method]
+    lon, lat, out_ax = axes()
+
+    # ---- index tables: rank 0 builds them on its GPU, NCCL broadcasts the two fp64 tables --------------------
+    t_setup0 = time.perf_counter()
+    if rank == 0:
+        ci = fb.CachedInterpolation.fromProjection(method_id, DST_PROJ, out_ax, out_ax, True, True, SRC_PROJ, lon, lat, True)
+        ci.createReducedDomain()
+        geom = [ci.getInX(), ci.getInY(), ci.reducedDomain()[2], ci.reducedDomain()[3]]
+    else:
+        ci, geom = None, [0, 0, 0, 0]
+    if world > 1:
+        from fimex_b200 import slab
+        ci, geom = slab.broadcast_cached_interpolation(ci, geom, method_id, OUT_N, OUT_N, rank, dev)
+    inX, inY, x0, y0 = geom
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t_setup0
+
+    # ---- synthetic slab, generated on the device ---------------------------------------------------------------
+    nlev = NZ * NT
+    g = torch.Generator(device=dev).manual_seed(20261018 + rank)
+    lo = torch.deg2rad(torch.tensor(lon[x0:x0 + inX], device=dev, dtype=torch.float32))[None, None, :]
+    la = torch.deg2rad(torch.tensor(lat[y0:y0 + inY], device=dev, dtype=torch.float32))[None, :, None]
+    zz = (torch.arange(nlev, device=dev) % NZ).to(torch.float32)[:, None, None]
+    tt = (torch.arange(nlev, device=dev) // NZ).to(torch.float32)[:, None, None]
+    d_in = 250 + 30 * torch.sin(la) * torch.cos(2 * lo) + 0.1 * zz + tt
+    d_in = (d_in + 0.5 * torch.randn((nlev, inY, inX), generator=g, device=dev, dtype=torch.float32)).contiguous()
+    d_out = torch.empty(nlev * OUT_N * OUT_N, device=dev, dtype=torch.float32)
+    values_per_step = nlev * OUT_N * OUT_N
+
+    def step():
+        ci.interpolateValues(d_in, out=d_out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = fb.kernel_launches()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for k in range(args.steps):
+        step()
+        ev[k + 1].record()
+    barrier()
+    launches = fb.kernel_launches() - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * values_per_step * args.steps / (total_ms * 1e-3)
+
+    # ---- roofline of the dominant (only) kernel of the step ------------------------------------------------------
+    peak, peak_src = peaks()
+    n_out, n_fp = OUT_N * OUT_N, inX * inY
+    table_bytes = {1: 16, 0: 4, 2: 20}[method_id] * n_out  # compiled table entry per target point, read once per level chunk
+    alg_bytes = 4 * n_out * nlev + 4 * n_fp * nlev + 16 * n_out  # store + compulsory load + two fp64 positions
+    kernel_ms = float(np.mean(per_launch_ms))
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "kernel": {0: "k_gather_nn", 1: "k_gather_bilinear", 2: "k_gather_bicubic"}[method_id],
+                "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_output_value": alg_bytes / values_per_step,
+                "kernel_ms": kernel_ms, "table_bytes_per_chunk": table_bytes}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            with open(traffic_file) as f:
+                roofline["traffic"] = json.load(f).get(roofline["kernel"])
+        except Exception:
+            pass
+
+    # ---- e2e: the same workload through the C ABI with HOST buffers (pinned); copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        h_in = torch.empty((NZ, inY, inX), dtype=torch.float32, pin_memory=True)
+        h_in.copy_(d_in[:NZ].cpu())
+        h_out = torch.empty(NZ * OUT_N * OUT_N, dtype=torch.float32, pin_memory=True)
+        hin_np, hout_np = h_in.numpy(), h_out.numpy()
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        ci.interpolateValues(hin_np, out=hout_np)  # warm-up: scratch pool, page mapping
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            for _t in range(NT):  # 24 time steps, one getDataSlice-sized call each (the way a Fimex host calls it)
+                ci.interpolateValues(hin_np, out=hout_np)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt_ = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
+        dt = float(tt_.item())
+        e2e = {"value": world * values_per_step * e2e_steps / dt, "unit": "values/s", "h2d_bytes_per_step": int(4 * n_fp * nlev),
+               "d2h_bytes_per_step": int(4 * n_out * nlev), "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
+               "how": "fb200_interp_interpolate_values (C ABI) on pinned host buffers, 24 calls of 137 levels per step, "
+                      "H2D + kernel + D2H pipelined in 3 streams inside the call",
+               "checksum": float(hout_np[::100003].astype(np.float64).sum())}
+
+    # ---- CPU baseline (rank 0, N == 1 only): the reference's kernels on this box's host cores -----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            r = run_cpu(method_id, steps=2, warmup=1)
+            cpu = {"value": r["value"], "unit": "values/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+        except Exception as e:  # the baseline is reported, never required
+            cpu = {"value": None, "unit": "values/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": str(e)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "values/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(method), "levels_per_gpu": nlev, "source_footprint": [int(inX), int(inY)],
+                       "crop_offset": [int(x0), int(y0)], "l2": "inputs+outputs >> L2 (52.6 GB written per step), no flush needed",
+                       "parallelism": f"slab{world}", "setup_s": setup_s},
+            "hbm_gbs": achieved, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--method", default="bilinear", choices=sorted(METHODS))
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return main_reference(args)
+    return main_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,33 @@
+"""fimex_b200 -- Fimex's horizontal-regridding hot path on NVIDIA B200, behind Fimex's own interface.
+
+The product is ``fimex_b200/lib/libfimex_b200.so`` (hand-written sm_100a CUDA behind the C ABI of
+``include/fimex_b200.h``).  This package is the thin Python host side used by the tests and the benchmark:
+
+* :mod:`fimex_b200.capi`    -- ctypes binding of every entry point of the header (fails loudly if the library
+  is missing or no GPU is usable; there is no CPU fallback anywhere in this package);
+* :mod:`fimex_b200.cached`  -- mirrors of the reference's ``CachedInterpolation``,
+  ``CachedForwardInterpolation`` and ``CachedVectorReprojection`` classes (same constructor arguments, same
+  method names) working on numpy arrays (host path) or torch CUDA tensors (device-resident path);
+* :mod:`fimex_b200.interpolator` -- the table-producing part of ``CDMInterpolator::changeProjection*`` and the
+  per-slice driver ``getDataSlice`` for in-memory slices;
+* :mod:`fimex_b200.slab`    -- one-process-per-GPU slab partition of the (time x level) stack with a single
+  NCCL broadcast of the cached tables.
+"""
+from .capi import (LATITUDE, LONGITUDE, PROJ_AXIS, MIFI_ERROR, MIFI_OK, MIFI_VECTOR_KEEP_SIZE, FimexB200Error, Method, kernel_launches,
+                   last_error, lib_path, load, mifi_get_values_bicubic_f, mifi_get_values_bilinear_f, mifi_get_values_f,
+                   mifi_get_vector_reproject_matrix, mifi_get_vector_reproject_matrix_field, mifi_get_vector_reproject_matrix_points,
+                   mifi_interpolate_f, mifi_points2position, mifi_project_axes, mifi_project_values, mifi_string_to_interpolation_method,
+                   mifi_vector_reproject_direction_by_matrix_f, mifi_vector_reproject_values_by_matrix_f, mifi_vector_reproject_values_f,
+                   mifi_bad2nanf, mifi_nanf2bad, set_device, version)
+from .cached import CachedForwardInterpolation, CachedInterpolation, CachedVectorReprojection
+from .interpolator import Interpolator
+
+__all__ = [
+    "CachedInterpolation", "CachedForwardInterpolation", "CachedVectorReprojection", "Interpolator", "Method", "FimexB200Error",
+    "MIFI_OK", "MIFI_ERROR", "PROJ_AXIS", "LONGITUDE", "LATITUDE", "MIFI_VECTOR_KEEP_SIZE", "load", "lib_path", "version", "last_error",
+    "set_device", "kernel_launches", "mifi_interpolate_f", "mifi_points2position", "mifi_project_axes", "mifi_project_values",
+    "mifi_get_vector_reproject_matrix", "mifi_get_vector_reproject_matrix_field", "mifi_get_vector_reproject_matrix_points",
+    "mifi_vector_reproject_values_by_matrix_f", "mifi_vector_reproject_direction_by_matrix_f", "mifi_vector_reproject_values_f",
+    "mifi_get_values_f", "mifi_get_values_bilinear_f", "mifi_get_values_bicubic_f", "mifi_string_to_interpolation_method",
+    "mifi_bad2nanf", "mifi_nanf2bad",
+]

@@ -1,0 +1,1334 @@
+// fimex_b200/csrc/api.cu -- the C ABI of include/fimex_b200.h: handle lifetime, device selection, host<->device
+// staging, error mapping (MIFI_OK / MIFI_ERROR).  No arithmetic of the path is done on the host here: the host
+// only parses proj strings, converts axis units (a few hundred doubles) and orchestrates launches.
+#include "../../include/fimex_b200.h"
+
+#include "kernels.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+// ======================================================================================================
+// library state
+// ======================================================================================================
+namespace fb {
+
+static thread_local std::string t_error;
+static thread_local int t_device = -2; // -2: not chosen yet
+static std::atomic<unsigned long long> g_launches{0};
+
+void set_error(const std::string& msg)
+{
+    t_error = msg;
+    if (!std::getenv("FIMEX_B200_QUIET"))
+        fprintf(stderr, "fimex_b200: %s\n", msg.c_str());
+}
+const char* last_error()
+{
+    return t_error.c_str();
+}
+void count_launch(int n)
+{
+    g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed);
+}
+unsigned long long launches()
+{
+    return g_launches.load(std::memory_order_relaxed);
+}
+
+int sm_count()
+{
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess)
+        return 148;
+    if (dev != cached_dev) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+        cached = n;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+namespace {
+
+std::once_flag g_pool_once[64];
+
+// make `dev` current; keep freed stream-ordered scratch in the pool instead of returning it to the driver
+int use_device(int dev)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error(std::string("no usable CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(e));
+        return FB_ERROR;
+    }
+    FB_REQUIRE(dev >= 0 && dev < count, "CUDA device index out of range");
+    FB_CUDA_CHECK(cudaSetDevice(dev));
+    if (dev < 64) {
+        std::call_once(g_pool_once[dev], [dev]() {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+        });
+    }
+    return FB_OK;
+}
+
+int default_device()
+{
+    if (t_device == -2) {
+        const char* env = std::getenv("FIMEX_B200_DEVICE");
+        if (env && *env) {
+            t_device = std::atoi(env);
+        } else {
+            int cur = 0;
+            t_device = (cudaGetDevice(&cur) == cudaSuccess) ? cur : 0;
+        }
+    }
+    return t_device;
+}
+
+cudaStream_t as_stream(void* s)
+{
+    return s ? reinterpret_cast<cudaStream_t>(s) : cudaStreamPerThread;
+}
+
+template <typename T>
+int dev_alloc(T** p, size_t count)
+{
+    FB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(p), sizeof(T) * (count ? count : 1)));
+    return FB_OK;
+}
+
+// RAII for stream-ordered scratch
+struct Scratch {
+    cudaStream_t st;
+    std::vector<void*> ptrs;
+    explicit Scratch(cudaStream_t s) : st(s) {}
+    ~Scratch()
+    {
+        for (void* p : ptrs)
+            cudaFreeAsync(p, st);
+    }
+    template <typename T>
+    int get(T** p, size_t count)
+    {
+        void* q = nullptr;
+        FB_CUDA_CHECK(cudaMallocAsync(&q, sizeof(T) * (count ? count : 1), st));
+        ptrs.push_back(q);
+        *p = static_cast<T*>(q);
+        return FB_OK;
+    }
+    template <typename T>
+    int upload(T** p, const T* host, size_t count)
+    {
+        if (get(p, count) != FB_OK)
+            return FB_ERROR;
+        if (count)
+            FB_CUDA_CHECK(cudaMemcpyAsync(*p, host, sizeof(T) * count, cudaMemcpyHostToDevice, st));
+        return FB_OK;
+    }
+};
+
+int check_status(int* d_status, cudaStream_t st, const char* what)
+{
+    int h = 0;
+    FB_CUDA_CHECK(cudaMemcpyAsync(&h, d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (h != 0) {
+        set_error(std::string(what) + ": projection failed with proj error " + std::to_string(h));
+        return FB_ERROR;
+    }
+    return FB_OK;
+}
+
+int parse_pair(const char* a, const char* b, ProjDef* pa, ProjDef* pb)
+{
+    char msg[256];
+    FB_REQUIRE(a && b, "null projection string");
+    if (parse_proj(a, pa, msg, sizeof(msg)) != 0) {
+        set_error(std::string("Proj error: ") + msg + " in '" + a + "'");
+        return FB_ERROR;
+    }
+    if (parse_proj(b, pb, msg, sizeof(msg)) != 0) {
+        set_error(std::string("Proj error: ") + msg + " in '" + b + "'");
+        return FB_ERROR;
+    }
+    return FB_OK;
+}
+
+// convertAxis (interpolation.c:221-229) / the DEG_TO_RAD transforms of CDMInterpolator.cc:1446-1451,1468-1473
+std::vector<double> axis_in_radians(const double* axis, size_t n, bool degree)
+{
+    std::vector<double> out(n);
+    for (size_t i = 0; i < n; ++i) {
+        volatile double v = degree ? FB_DEG_TO_RAD * axis[i] : axis[i];
+        out[i] = v;
+    }
+    return out;
+}
+
+bool is_backward(int m)
+{
+    return m == FB_NN || m == FB_BILINEAR || m == FB_BICUBIC || m == FB_COORD_NN || m == FB_COORD_NN_KD;
+}
+bool is_forward(int m)
+{
+    return m >= FB_FWD_SUM && m <= FB_FWD_UNDEF_MIN;
+}
+
+} // namespace
+} // namespace fb
+
+using namespace fb;
+
+// ======================================================================================================
+// handles
+// ======================================================================================================
+struct fb200_interp {
+    int method = -1;
+    bool forward = false;
+    int device = 0;
+    size_t inX = 0, inY = 0, outX = 0, outY = 0;
+    size_t npts = 0; // outX*outY (backward) or inX*inY (forward)
+    double* d_px = nullptr;
+    double* d_py = nullptr;
+    // compiled tables (exactly one family is non-null)
+    int* d_nn = nullptr;
+    int4* d_bil = nullptr;
+    int* d_bic_off = nullptr;
+    double2* d_bic_frac = nullptr;
+    ForwardPlan fwd;
+    bool reduced = false;
+    long long xMin = 0, yMin = 0;
+    long long coordnn_ties = 0;
+
+    ~fb200_interp()
+    {
+        cudaSetDevice(device);
+        free_tables();
+        if (d_px)
+            cudaFree(d_px);
+        if (d_py)
+            cudaFree(d_py);
+    }
+    void free_tables()
+    {
+        if (d_nn)
+            cudaFree(d_nn);
+        if (d_bil)
+            cudaFree(d_bil);
+        if (d_bic_off)
+            cudaFree(d_bic_off);
+        if (d_bic_frac)
+            cudaFree(d_bic_frac);
+        d_nn = nullptr;
+        d_bil = nullptr;
+        d_bic_off = nullptr;
+        d_bic_frac = nullptr;
+        forward_free_plan(&fwd);
+    }
+};
+
+struct fb200_vector {
+    int method = 0;
+    int ox = 0, oy = 0;
+    int device = 0;
+    double* d_matrix = nullptr; // [oy][ox][4]
+    double2* d_cs = nullptr;    // compact (cos, sin)
+    ~fb200_vector()
+    {
+        cudaSetDevice(device);
+        if (d_matrix)
+            cudaFree(d_matrix);
+        if (d_cs)
+            cudaFree(d_cs);
+    }
+};
+
+namespace {
+
+// positions -> gather tables (or forward CSR plan); synchronises
+int compile_tables(fb200_interp* h, cudaStream_t st)
+{
+    h->free_tables();
+    const long long n = (long long)h->npts;
+    if (h->forward) {
+        Scratch tmp(st);
+        int* d_cell = nullptr;
+        if (tmp.get(&d_cell, h->npts) != FB_OK)
+            return FB_ERROR;
+        if (launch_compile_forward_cells(h->d_px, h->d_py, n, (int)h->outX, (int)h->outY, d_cell, st) != FB_OK)
+            return FB_ERROR;
+        return forward_build_plan(d_cell, n, (long long)h->outX * (long long)h->outY, &h->fwd, st);
+    }
+    FB_REQUIRE((long long)h->inX * (long long)h->inY < 2147483647LL, "source grid larger than 2^31 cells");
+    switch (h->method) {
+    case FB_BILINEAR:
+        if (dev_alloc(&h->d_bil, h->npts) != FB_OK)
+            return FB_ERROR;
+        if (launch_compile_bilinear(h->d_px, h->d_py, n, (int)h->inX, (int)h->inY, h->d_bil, st) != FB_OK)
+            return FB_ERROR;
+        break;
+    case FB_BICUBIC:
+        if (dev_alloc(&h->d_bic_off, h->npts) != FB_OK || dev_alloc(&h->d_bic_frac, h->npts) != FB_OK)
+            return FB_ERROR;
+        if (launch_compile_bicubic(h->d_px, h->d_py, n, (int)h->inX, (int)h->inY, h->d_bic_off, h->d_bic_frac, st) != FB_OK)
+            return FB_ERROR;
+        break;
+    default:
+        if (dev_alloc(&h->d_nn, h->npts) != FB_OK)
+            return FB_ERROR;
+        if (launch_compile_nn(h->d_px, h->d_py, n, (int)h->inX, (int)h->inY, h->d_nn, st) != FB_OK)
+            return FB_ERROR;
+        break;
+    }
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return FB_OK;
+}
+
+int new_interp(int funcType, bool forward, size_t inX, size_t inY, size_t outX, size_t outY, std::unique_ptr<fb200_interp>* out)
+{
+    if (forward)
+        FB_REQUIRE(is_forward(funcType), "unknown forward interpolation method: " + std::to_string(funcType));
+    else
+        FB_REQUIRE(is_backward(funcType), "unknown interpolation function: " + std::to_string(funcType));
+    FB_REQUIRE(inX < 2147483647u && inY < 2147483647u && outX < 2147483647u && outY < 2147483647u, "grid dimension too large");
+    if (use_device(default_device()) != FB_OK)
+        return FB_ERROR;
+    std::unique_ptr<fb200_interp> h(new fb200_interp());
+    h->method = funcType;
+    h->forward = forward;
+    h->device = default_device();
+    h->inX = inX;
+    h->inY = inY;
+    h->outX = outX;
+    h->outY = outY;
+    h->npts = forward ? inX * inY : outX * outY;
+    if (dev_alloc(&h->d_px, h->npts) != FB_OK || dev_alloc(&h->d_py, h->npts) != FB_OK)
+        return FB_ERROR;
+    *out = std::move(h);
+    return FB_OK;
+}
+
+int create_from_points(int funcType, bool forward, const double* px, const double* py, bool on_device, size_t inX, size_t inY, size_t outX,
+                       size_t outY, fb200_interp** handle)
+{
+    FB_REQUIRE(handle != nullptr, "null handle pointer");
+    *handle = nullptr;
+    std::unique_ptr<fb200_interp> h;
+    if (new_interp(funcType, forward, inX, inY, outX, outY, &h) != FB_OK)
+        return FB_ERROR;
+    FB_REQUIRE(h->npts == 0 || (px && py), "null position table");
+    cudaStream_t st = cudaStreamPerThread;
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (h->npts) {
+        FB_CUDA_CHECK(cudaMemcpyAsync(h->d_px, px, sizeof(double) * h->npts, kind, st));
+        FB_CUDA_CHECK(cudaMemcpyAsync(h->d_py, py, sizeof(double) * h->npts, kind, st));
+    }
+    if (compile_tables(h.get(), st) != FB_OK)
+        return FB_ERROR;
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    *handle = h.release();
+    return FB_OK;
+}
+
+GatherGeom geom_of(const fb200_interp* h, size_t nz)
+{
+    GatherGeom g;
+    g.ix = (int)h->inX;
+    g.iy = (int)h->inY;
+    g.ox = (int)h->outX;
+    g.oy = (int)h->outY;
+    g.in_level = (long long)h->inX * (long long)h->inY;
+    g.out_level = (long long)h->outX * (long long)h->outY;
+    g.nz = (long long)nz;
+    return g;
+}
+
+int run_device(const fb200_interp* h, const float* d_in, size_t nz, float* d_out, cudaStream_t st)
+{
+    if (h->forward)
+        return launch_forward(h->method, h->fwd, d_in, d_out, (long long)nz, st);
+    const GatherGeom g = geom_of(h, nz);
+    switch (h->method) {
+    case FB_BILINEAR:
+        return launch_gather_bilinear(g, h->d_bil, d_in, d_out, st);
+    case FB_BICUBIC:
+        return launch_gather_bicubic(g, h->d_bic_off, h->d_bic_frac, d_in, d_out, st);
+    default:
+        return launch_gather_nn(g, h->d_nn, d_in, d_out, st);
+    }
+}
+
+int run_vector_device(const fb200_interp* h, const fb200_vector* v, const float* d_u, const float* d_v, size_t nz, float* d_uo, float* d_vo,
+                      cudaStream_t st)
+{
+    const GatherGeom g = geom_of(h, nz);
+    const double2* cs = v ? v->d_cs : nullptr;
+    switch (h->method) {
+    case FB_BILINEAR:
+        return launch_gather_vector(FB_BILINEAR, g, h->d_bil, nullptr, cs, d_u, d_v, d_uo, d_vo, st);
+    case FB_BICUBIC:
+        return launch_gather_vector(FB_BICUBIC, g, h->d_bic_off, h->d_bic_frac, cs, d_u, d_v, d_uo, d_vo, st);
+    default:
+        return launch_gather_vector(FB_NN, g, h->d_nn, nullptr, cs, d_u, d_v, d_uo, d_vo, st);
+    }
+}
+
+// Host-buffer execution: levels are cut into chunks that rotate through three (stream, scratch) slots, so that
+// the H2D copy of chunk k+1, the kernel of chunk k and the D2H copy of chunk k-1 overlap.  `nfields` is 1
+// (scalar) or 2 (u/v).  Every call owns its streams and scratch => re-entrant on a shared handle.
+int run_host(const fb200_interp* h, const fb200_vector* v, int nfields, const float* const* in, float* const* out, size_t nz)
+{
+    const size_t in_level = h->inX * h->inY, out_level = h->outX * h->outY;
+    if (nz == 0 || out_level == 0)
+        return FB_OK;
+    const size_t bytes_per_level = (in_level + out_level) * sizeof(float) * (size_t)nfields;
+    size_t zc = (size_t)(192ull << 20) / (bytes_per_level ? bytes_per_level : 1);
+    if (zc < 1)
+        zc = 1;
+    if (zc > nz)
+        zc = nz;
+    const int nslots = (nz > zc) ? 3 : 1;
+    struct Slot {
+        cudaStream_t st = nullptr;
+        float* d_in[2] = {nullptr, nullptr};
+        float* d_out[2] = {nullptr, nullptr};
+    } slots[3];
+    int rc = FB_OK;
+    auto body = [&]() -> int {
+        for (int s = 0; s < nslots; ++s) {
+            FB_CUDA_CHECK(cudaStreamCreateWithFlags(&slots[s].st, cudaStreamNonBlocking));
+            for (int f = 0; f < nfields; ++f) {
+                FB_CUDA_CHECK(cudaMallocAsync(&slots[s].d_in[f], sizeof(float) * ((zc * in_level) > 0 ? zc * in_level : 1), slots[s].st));
+                FB_CUDA_CHECK(cudaMallocAsync(&slots[s].d_out[f], sizeof(float) * zc * out_level, slots[s].st));
+            }
+        }
+        size_t chunk = 0;
+        for (size_t z0 = 0; z0 < nz; z0 += zc, ++chunk) {
+            Slot& sl = slots[chunk % nslots];
+            const size_t zn = (z0 + zc <= nz) ? zc : nz - z0;
+            for (int f = 0; f < nfields; ++f)
+                if (in_level)
+                    FB_CUDA_CHECK(cudaMemcpyAsync(sl.d_in[f], in[f] + z0 * in_level, sizeof(float) * zn * in_level, cudaMemcpyHostToDevice,
+                                                  sl.st));
+            int r;
+            if (nfields == 1)
+                r = run_device(h, sl.d_in[0], zn, sl.d_out[0], sl.st);
+            else
+                r = run_vector_device(h, v, sl.d_in[0], sl.d_in[1], zn, sl.d_out[0], sl.d_out[1], sl.st);
+            if (r != FB_OK)
+                return FB_ERROR;
+            for (int f = 0; f < nfields; ++f)
+                FB_CUDA_CHECK(cudaMemcpyAsync(out[f] + z0 * out_level, sl.d_out[f], sizeof(float) * zn * out_level, cudaMemcpyDeviceToHost,
+                                              sl.st));
+        }
+        for (int s = 0; s < nslots; ++s)
+            FB_CUDA_CHECK(cudaStreamSynchronize(slots[s].st));
+        return FB_OK;
+    };
+    rc = body();
+    for (int s = 0; s < nslots; ++s) {
+        if (!slots[s].st)
+            continue;
+        for (int f = 0; f < nfields; ++f) {
+            if (slots[s].d_in[f])
+                cudaFreeAsync(slots[s].d_in[f], slots[s].st);
+            if (slots[s].d_out[f])
+                cudaFreeAsync(slots[s].d_out[f], slots[s].st);
+        }
+        cudaStreamSynchronize(slots[s].st);
+        cudaStreamDestroy(slots[s].st);
+    }
+    return rc;
+}
+
+int check_interp_call(const fb200_interp* h, size_t size, size_t* nz)
+{
+    FB_REQUIRE(h != nullptr, "null interpolation handle");
+    const size_t in_level = h->inX * h->inY;
+    FB_REQUIRE(in_level > 0, "interpolation with an empty source grid");
+    *nz = size / in_level; // CachedInterpolation.cc:121: inZ = size / (inX*inY), remainder ignored
+    return use_device(h->device);
+}
+
+// deltas of mifi_get_vector_reproject_matrix_proj (interpolation.c:458-513); both derive from the x field
+int pick_deltas(const double* d_in_x, int ox, int oy, cudaStream_t st, double* dx, double* dy)
+{
+    auto fetch = [&](size_t idx, double* v) -> int {
+        FB_CUDA_CHECK(cudaMemcpyAsync(v, d_in_x + idx, sizeof(double), cudaMemcpyDeviceToHost, st));
+        return FB_OK;
+    };
+    const double eps = 1e-3;
+    double a = 0, b = 0, c = 0, e = 0;
+    volatile double d;
+    if (ox > 1 && oy > 1) {
+        const size_t hx = (size_t)ox / 2, hy = (size_t)oy / 2;
+        if (fetch(0, &a) != FB_OK || fetch((size_t)ox + 1, &b) != FB_OK || fetch(hy * ox + hx, &c) != FB_OK ||
+            fetch((hy + 1) * ox + (hx + 1), &e) != FB_OK)
+            return FB_ERROR;
+        FB_CUDA_CHECK(cudaStreamSynchronize(st));
+        d = eps * (b - a);
+        volatile double d2 = eps * (e - c);
+        d = d + d2;
+        d = d / 2;
+    } else if (ox > 1) {
+        if (fetch(0, &a) != FB_OK || fetch(1, &b) != FB_OK)
+            return FB_ERROR;
+        FB_CUDA_CHECK(cudaStreamSynchronize(st));
+        d = eps * (b - a);
+    } else if (oy > 1) {
+        if (fetch(0, &a) != FB_OK || fetch((size_t)ox, &b) != FB_OK)
+            return FB_ERROR;
+        FB_CUDA_CHECK(cudaStreamSynchronize(st));
+        d = eps * (b - a);
+    } else {
+        if (fetch(0, &a) != FB_OK)
+            return FB_ERROR;
+        FB_CUDA_CHECK(cudaStreamSynchronize(st));
+        d = (a > 1) ? (a * eps) : eps;
+    }
+    *dx = d;
+    *dy = d;
+    if (std::fabs(*dx) < 1e-9 || std::fabs(*dy) < 1e-9) {
+        fprintf(stderr, "WARNING, tiny deltaX/Y: %f %f possible singularity in vector-reprojection. Using default: %f\n", *dx, *dy, eps);
+        *dx = eps;
+        *dy = eps;
+    }
+    return FB_OK;
+}
+
+// the three matrix builders share this: d_matrix (device, 4*on) from axes/fields
+enum MatrixInput { MI_AXES, MI_FIELD, MI_POINTS };
+int build_matrix_device(MatrixInput kind, const char* proj_input, const char* proj_output, const double* a, const double* b, int xt, int yt,
+                        int ox, int oy, int input_is_metric, double* d_matrix, cudaStream_t st)
+{
+    ProjDef pin, pout;
+    if (parse_pair(proj_input, proj_output, &pin, &pout) != FB_OK)
+        return FB_ERROR;
+    const long long on = (kind == MI_POINTS) ? (long long)ox : (long long)ox * oy;
+    if (on == 0)
+        return FB_OK;
+    Scratch tmp(st);
+    int* d_status = nullptr;
+    double *d_inx = nullptr, *d_iny = nullptr, *d_outx = nullptr, *d_outy = nullptr;
+    if (tmp.get(&d_status, 1) != FB_OK || tmp.get(&d_inx, on) != FB_OK || tmp.get(&d_iny, on) != FB_OK || tmp.get(&d_outx, on) != FB_OK ||
+        tmp.get(&d_outy, on) != FB_OK)
+        return FB_ERROR;
+    FB_CUDA_CHECK(cudaMemsetAsync(d_status, 0, sizeof(int), st));
+    double dx, dy;
+    if (kind == MI_AXES) {
+        // interpolation.c:744-779: axes (deg->rad where typed so) -> mesh in the OUTPUT crs; in = out -> input crs
+        const std::vector<double> xa = axis_in_radians(a, (size_t)ox, xt == FB_AXIS_LONGITUDE || xt == FB_AXIS_LATITUDE);
+        const std::vector<double> ya = axis_in_radians(b, (size_t)oy, yt == FB_AXIS_LONGITUDE || yt == FB_AXIS_LATITUDE);
+        double *d_xa = nullptr, *d_ya = nullptr;
+        if (tmp.upload(&d_xa, xa.data(), xa.size()) != FB_OK || tmp.upload(&d_ya, ya.data(), ya.size()) != FB_OK)
+            return FB_ERROR;
+        ProjDef ident = pout; // identity "projection": mesh only
+        ident.is_latlong = 1;
+        ProjDef ident2 = ident;
+        if (launch_project_mesh(ident, ident2, d_xa, d_ya, ox, oy, d_outx, d_outy, d_status, st) != FB_OK)
+            return FB_ERROR;
+        if (launch_project_mesh(pout, pin, d_xa, d_ya, ox, oy, d_inx, d_iny, d_status, st) != FB_OK)
+            return FB_ERROR;
+        if (check_status(d_status, st, "mifi_get_vector_reproject_matrix") != FB_OK)
+            return FB_ERROR;
+        if (pick_deltas(d_inx, ox, oy, st, &dx, &dy) != FB_OK)
+            return FB_ERROR;
+    } else if (kind == MI_FIELD) {
+        // :697-708: in fields given (input crs); out = in -> output crs
+        FB_CUDA_CHECK(cudaMemcpyAsync(d_inx, a, sizeof(double) * on, cudaMemcpyHostToDevice, st));
+        FB_CUDA_CHECK(cudaMemcpyAsync(d_iny, b, sizeof(double) * on, cudaMemcpyHostToDevice, st));
+        FB_CUDA_CHECK(cudaMemcpyAsync(d_outx, d_inx, sizeof(double) * on, cudaMemcpyDeviceToDevice, st));
+        FB_CUDA_CHECK(cudaMemcpyAsync(d_outy, d_iny, sizeof(double) * on, cudaMemcpyDeviceToDevice, st));
+        if (launch_project_values(pin, pout, d_outx, d_outy, on, d_status, st) != FB_OK)
+            return FB_ERROR;
+        if (check_status(d_status, st, "mifi_get_vector_reproject_matrix_field") != FB_OK)
+            return FB_ERROR;
+        if (pick_deltas(d_inx, ox, oy, st, &dx, &dy) != FB_OK)
+            return FB_ERROR;
+    } else {
+        // :641-656: out points given (output crs); in = out -> input crs; fixed delta
+        FB_CUDA_CHECK(cudaMemcpyAsync(d_outx, a, sizeof(double) * on, cudaMemcpyHostToDevice, st));
+        FB_CUDA_CHECK(cudaMemcpyAsync(d_outy, b, sizeof(double) * on, cudaMemcpyHostToDevice, st));
+        FB_CUDA_CHECK(cudaMemcpyAsync(d_inx, d_outx, sizeof(double) * on, cudaMemcpyDeviceToDevice, st));
+        FB_CUDA_CHECK(cudaMemcpyAsync(d_iny, d_outy, sizeof(double) * on, cudaMemcpyDeviceToDevice, st));
+        if (launch_project_values(pout, pin, d_inx, d_iny, on, d_status, st) != FB_OK)
+            return FB_ERROR;
+        if (check_status(d_status, st, "mifi_get_vector_reproject_matrix_points") != FB_OK)
+            return FB_ERROR;
+        dx = dy = input_is_metric ? 100 : 0.00001;
+    }
+    if (launch_vector_matrix(pin, pout, d_inx, d_iny, d_outx, d_outy, dx, dy, on, d_matrix, d_status, st) != FB_OK)
+        return FB_ERROR;
+    return check_status(d_status, st, "vector reprojection matrix");
+}
+
+int matrix_to_host(MatrixInput kind, const char* proj_input, const char* proj_output, const double* a, const double* b, int xt, int yt, int ox,
+                   int oy, int metric, double* matrix)
+{
+    if (use_device(default_device()) != FB_OK)
+        return FB_ERROR;
+    cudaStream_t st = cudaStreamPerThread;
+    const long long on = (kind == MI_POINTS) ? (long long)ox : (long long)ox * oy;
+    FB_REQUIRE(on >= 0 && (on == 0 || (a && b && matrix)), "null argument");
+    Scratch tmp(st);
+    double* d_m = nullptr;
+    if (tmp.get(&d_m, 4 * (size_t)on) != FB_OK)
+        return FB_ERROR;
+    if (build_matrix_device(kind, proj_input, proj_output, a, b, xt, yt, ox, oy, metric, d_m, st) != FB_OK)
+        return FB_ERROR;
+    if (on) {
+        FB_CUDA_CHECK(cudaMemcpyAsync(matrix, d_m, sizeof(double) * 4 * on, cudaMemcpyDeviceToHost, st));
+        FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    return FB_OK;
+}
+
+// target axes -> (x, y) in `pdst` on the device: the mesh projection of mifi_project_axes
+int project_axes_device(const ProjDef& psrc, const ProjDef& pdst, const std::vector<double>& xa, const std::vector<double>& ya, double* d_x,
+                        double* d_y, cudaStream_t st, const char* what)
+{
+    Scratch tmp(st);
+    int* d_status = nullptr;
+    double *d_xa = nullptr, *d_ya = nullptr;
+    if (tmp.get(&d_status, 1) != FB_OK || tmp.upload(&d_xa, xa.data(), xa.size()) != FB_OK || tmp.upload(&d_ya, ya.data(), ya.size()) != FB_OK)
+        return FB_ERROR;
+    FB_CUDA_CHECK(cudaMemsetAsync(d_status, 0, sizeof(int), st));
+    if (launch_project_mesh(psrc, pdst, d_xa, d_ya, (int)xa.size(), (int)ya.size(), d_x, d_y, d_status, st) != FB_OK)
+        return FB_ERROR;
+    return check_status(d_status, st, what);
+}
+
+int points2position_device(double* d_pts, long long n, const std::vector<double>& axis, int type, cudaStream_t st)
+{
+    Scratch tmp(st);
+    double* d_axis = nullptr;
+    if (tmp.upload(&d_axis, axis.data(), axis.size()) != FB_OK)
+        return FB_ERROR;
+    if (launch_points2position(d_pts, n, d_axis, axis.data(), (int)axis.size(), type, st) != FB_OK)
+        return FB_ERROR;
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return FB_OK;
+}
+
+const char* kWgs84LatLon = "+proj=latlong +datum=WGS84 +towgs84=0,0,0 +no_defs"; // MIFI_WGS84_LATLON_PROJ4, CDMconstants.h:118
+
+} // namespace
+
+// ======================================================================================================
+// extern "C"
+// ======================================================================================================
+extern "C" {
+
+const char* fb200_version(void)
+{
+    return "fimex_b200 0.1 (path of fimex 0.67.2; sm_100a)";
+}
+const char* fb200_last_error(void)
+{
+    return last_error();
+}
+int fb200_set_device(int device)
+{
+    if (use_device(device) != FB_OK)
+        return MIFI_ERROR;
+    t_device = device;
+    return MIFI_OK;
+}
+int fb200_get_device(void)
+{
+    return default_device();
+}
+unsigned long long fb200_kernel_launches(void)
+{
+    return launches();
+}
+void* fb200_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (use_device(default_device()) != FB_OK)
+        return nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        set_error("cudaHostAlloc failed");
+        return nullptr;
+    }
+    return p;
+}
+void fb200_host_free(void* p)
+{
+    if (p)
+        cudaFreeHost(p);
+}
+
+// ---------------------------------------------------------------------------------------- CachedInterpolation
+int fb200_cached_interpolation_create(int funcType, const double* px, const double* py, size_t inX, size_t inY, size_t outX, size_t outY,
+                                      fb200_interp** handle)
+{
+    return create_from_points(funcType, false, px, py, false, inX, inY, outX, outY, handle);
+}
+
+int fb200_cached_interpolation_create_device(int funcType, const double* d_px, const double* d_py, size_t inX, size_t inY, size_t outX,
+                                             size_t outY, fb200_interp** handle)
+{
+    return create_from_points(funcType, false, d_px, d_py, true, inX, inY, outX, outY, handle);
+}
+
+int fb200_cached_forward_interpolation_create(int funcType, const double* px, const double* py, size_t inX, size_t inY, size_t outX,
+                                              size_t outY, fb200_interp** handle)
+{
+    return create_from_points(funcType, true, px, py, false, inX, inY, outX, outY, handle);
+}
+
+int fb200_cached_interpolation_create_from_projection(int funcType, const char* proj_target, const double* out_x_axis,
+                                                      const double* out_y_axis, size_t outX, size_t outY, int out_x_is_degree,
+                                                      int out_y_is_degree, const char* proj_source, const double* in_x_axis,
+                                                      const double* in_y_axis, size_t inX, size_t inY, int in_is_degree, fb200_interp** handle)
+{
+    FB_REQUIRE(handle != nullptr, "null handle pointer");
+    *handle = nullptr;
+    FB_REQUIRE(funcType == FB_NN || funcType == FB_BILINEAR || funcType == FB_BICUBIC,
+               "changeProjectionByProjectionParameters: method must be nearestneighbor, bilinear or bicubic");
+    FB_REQUIRE(out_x_axis && out_y_axis && in_x_axis && in_y_axis, "null axis");
+    ProjDef ptgt, psrc;
+    if (parse_pair(proj_target, proj_source, &ptgt, &psrc) != FB_OK)
+        return MIFI_ERROR;
+    std::unique_ptr<fb200_interp> h;
+    if (new_interp(funcType, false, inX, inY, outX, outY, &h) != FB_OK)
+        return MIFI_ERROR;
+    cudaStream_t st = cudaStreamPerThread;
+    const std::vector<double> oxa = axis_in_radians(out_x_axis, outX, out_x_is_degree != 0);
+    const std::vector<double> oya = axis_in_radians(out_y_axis, outY, out_y_is_degree != 0);
+    const std::vector<double> ixa = axis_in_radians(in_x_axis, inX, in_is_degree != 0);
+    const std::vector<double> iya = axis_in_radians(in_y_axis, inY, in_is_degree != 0);
+    if (h->npts) {
+        if (project_axes_device(ptgt, psrc, oxa, oya, h->d_px, h->d_py, st, "mifi_project_axes") != FB_OK)
+            return MIFI_ERROR;
+        if (points2position_device(h->d_px, (long long)h->npts, ixa, in_is_degree ? FB_AXIS_LONGITUDE : FB_AXIS_PROJ, st) != FB_OK)
+            return MIFI_ERROR;
+        if (points2position_device(h->d_py, (long long)h->npts, iya, in_is_degree ? FB_AXIS_LATITUDE : FB_AXIS_PROJ, st) != FB_OK)
+            return MIFI_ERROR;
+    }
+    if (compile_tables(h.get(), st) != FB_OK)
+        return MIFI_ERROR;
+    *handle = h.release();
+    return MIFI_OK;
+}
+
+int fb200_cached_interpolation_create_from_coordinates(int funcType, const char* proj_target, const double* out_x_axis,
+                                                       const double* out_y_axis, size_t outX, size_t outY, int out_x_is_degree,
+                                                       int out_y_is_degree, const double* lon2d, const double* lat2d, size_t inX, size_t inY,
+                                                       fb200_interp** handle)
+{
+    FB_REQUIRE(handle != nullptr, "null handle pointer");
+    *handle = nullptr;
+    FB_REQUIRE(funcType == FB_COORD_NN, "changeProjectionByCoordinates: only coord_nearestneighbor is implemented on the device");
+    FB_REQUIRE(out_x_axis && out_y_axis && lon2d && lat2d, "null argument");
+    ProjDef ptgt, pll;
+    if (parse_pair(proj_target, kWgs84LatLon, &ptgt, &pll) != FB_OK)
+        return MIFI_ERROR;
+    std::unique_ptr<fb200_interp> h;
+    if (new_interp(funcType, false, inX, inY, outX, outY, &h) != FB_OK)
+        return MIFI_ERROR;
+    cudaStream_t st = cudaStreamPerThread;
+    const std::vector<double> oxa = axis_in_radians(out_x_axis, outX, out_x_is_degree != 0);
+    const std::vector<double> oya = axis_in_radians(out_y_axis, outY, out_y_is_degree != 0);
+    const std::vector<double> lon = axis_in_radians(lon2d, inX * inY, true); // CDMInterpolator.cc:1358-1359
+    const std::vector<double> lat = axis_in_radians(lat2d, inX * inY, true);
+    if (h->npts) {
+        if (project_axes_device(ptgt, pll, oxa, oya, h->d_px, h->d_py, st, "mifi_project_axes") != FB_OK)
+            return MIFI_ERROR;
+        if (coordnn_search(h->d_px, h->d_py, (long long)h->npts, lon.data(), lat.data(), inX, inY, &h->coordnn_ties, st) != FB_OK)
+            return MIFI_ERROR;
+    }
+    if (compile_tables(h.get(), st) != FB_OK)
+        return MIFI_ERROR;
+    *handle = h.release();
+    return MIFI_OK;
+}
+
+int fb200_cached_forward_interpolation_create_from_coordinates(int funcType, const char* proj_target, const double* out_x_axis,
+                                                               const double* out_y_axis, size_t outX, size_t outY, int out_x_is_degree,
+                                                               int out_y_is_degree, const double* lon2d, const double* lat2d, size_t inX,
+                                                               size_t inY, fb200_interp** handle)
+{
+    FB_REQUIRE(handle != nullptr, "null handle pointer");
+    *handle = nullptr;
+    FB_REQUIRE(out_x_axis && out_y_axis && lon2d && lat2d, "null argument");
+    ProjDef pll, ptgt;
+    if (parse_pair(kWgs84LatLon, proj_target, &pll, &ptgt) != FB_OK)
+        return MIFI_ERROR;
+    std::unique_ptr<fb200_interp> h;
+    if (new_interp(funcType, true, inX, inY, outX, outY, &h) != FB_OK)
+        return MIFI_ERROR;
+    cudaStream_t st = cudaStreamPerThread;
+    const std::vector<double> oxa = axis_in_radians(out_x_axis, outX, out_x_is_degree != 0);
+    const std::vector<double> oya = axis_in_radians(out_y_axis, outY, out_y_is_degree != 0);
+    const std::vector<double> lon = axis_in_radians(lon2d, inX * inY, true); // CDMInterpolator.cc:1265-1266
+    const std::vector<double> lat = axis_in_radians(lat2d, inX * inY, true);
+    if (h->npts) {
+        Scratch tmp(st);
+        int* d_status = nullptr;
+        if (tmp.get(&d_status, 1) != FB_OK)
+            return MIFI_ERROR;
+        FB_CUDA_CHECK(cudaMemsetAsync(d_status, 0, sizeof(int), st));
+        FB_CUDA_CHECK(cudaMemcpyAsync(h->d_px, lon.data(), sizeof(double) * h->npts, cudaMemcpyHostToDevice, st));
+        FB_CUDA_CHECK(cudaMemcpyAsync(h->d_py, lat.data(), sizeof(double) * h->npts, cudaMemcpyHostToDevice, st));
+        if (launch_project_values(pll, ptgt, h->d_px, h->d_py, (long long)h->npts, d_status, st) != FB_OK)
+            return MIFI_ERROR;
+        if (check_status(d_status, st, "mifi_project_values") != FB_OK)
+            return MIFI_ERROR;
+        if (points2position_device(h->d_px, (long long)h->npts, oxa, out_x_is_degree ? FB_AXIS_LONGITUDE : FB_AXIS_PROJ, st) != FB_OK)
+            return MIFI_ERROR;
+        if (points2position_device(h->d_py, (long long)h->npts, oya, out_y_is_degree ? FB_AXIS_LATITUDE : FB_AXIS_PROJ, st) != FB_OK)
+            return MIFI_ERROR;
+    }
+    if (compile_tables(h.get(), st) != FB_OK)
+        return MIFI_ERROR;
+    *handle = h.release();
+    return MIFI_OK;
+}
+
+int fb200_interp_create_reduced_domain(fb200_interp* h, int* reduced, long long* xMin, long long* yMin)
+{
+    FB_REQUIRE(h != nullptr, "null interpolation handle");
+    if (reduced)
+        *reduced = 0;
+    FB_REQUIRE(!h->forward, "createReducedDomain is defined for CachedInterpolation only");
+    if (use_device(h->device) != FB_OK)
+        return MIFI_ERROR;
+    if (h->reduced) { // "don't set twice", CachedInterpolation.cc:161-163
+        if (reduced)
+            *reduced = 1;
+        if (xMin)
+            *xMin = h->xMin;
+        if (yMin)
+            *yMin = h->yMin;
+        return MIFI_OK;
+    }
+    if (h->npts == 0)
+        return MIFI_OK;
+    cudaStream_t st = cudaStreamPerThread;
+    double lox, hix, loy, hiy;
+    if (device_minmax(h->d_px, (long long)h->npts, &lox, &hix, st) != FB_OK || device_minmax(h->d_py, (long long)h->npts, &loy, &hiy, st) != FB_OK)
+        return MIFI_ERROR;
+    auto clamp = [](long long lo, double dv, long long hi) { // CachedInterpolation.cc:149-157
+        const long long v = static_cast<long long>(dv);
+        if (v < lo)
+            return lo;
+        if (v < hi)
+            return v;
+        return hi;
+    };
+    const long long EXT = 2;
+    const long long x0 = clamp(0, std::floor(lox) - EXT, (long long)h->inX - 1);
+    const long long y0 = clamp(0, std::floor(loy) - EXT, (long long)h->inY - 1);
+    const long long x1 = clamp(0, std::ceil(hix) + EXT, (long long)h->inX - 1);
+    const long long y1 = clamp(0, std::ceil(hiy) + EXT, (long long)h->inY - 1);
+    if ((x1 - x0) < 1 || (y1 - y0) < 1)
+        return MIFI_OK;
+    if (launch_shift(h->d_px, (long long)h->npts, (double)x0, st) != FB_OK || launch_shift(h->d_py, (long long)h->npts, (double)y0, st) != FB_OK)
+        return MIFI_ERROR;
+    h->inX = (size_t)(x1 - x0 + 1);
+    h->inY = (size_t)(y1 - y0 + 1);
+    h->xMin = x0;
+    h->yMin = y0;
+    h->reduced = true;
+    if (compile_tables(h, st) != FB_OK)
+        return MIFI_ERROR;
+    if (reduced)
+        *reduced = 1;
+    if (xMin)
+        *xMin = x0;
+    if (yMin)
+        *yMin = y0;
+    return MIFI_OK;
+}
+
+size_t fb200_interp_in_x(const fb200_interp* h)
+{
+    return h ? h->inX : 0;
+}
+size_t fb200_interp_in_y(const fb200_interp* h)
+{
+    return h ? h->inY : 0;
+}
+size_t fb200_interp_out_x(const fb200_interp* h)
+{
+    return h ? h->outX : 0;
+}
+size_t fb200_interp_out_y(const fb200_interp* h)
+{
+    return h ? h->outY : 0;
+}
+int fb200_interp_method(const fb200_interp* h)
+{
+    return h ? h->method : -1;
+}
+
+int fb200_interp_get_points(const fb200_interp* h, double* px, double* py)
+{
+    FB_REQUIRE(h != nullptr && px && py, "null argument");
+    if (use_device(h->device) != FB_OK)
+        return MIFI_ERROR;
+    if (h->npts) {
+        FB_CUDA_CHECK(cudaMemcpy(px, h->d_px, sizeof(double) * h->npts, cudaMemcpyDeviceToHost));
+        FB_CUDA_CHECK(cudaMemcpy(py, h->d_py, sizeof(double) * h->npts, cudaMemcpyDeviceToHost));
+    }
+    return MIFI_OK;
+}
+
+int fb200_interp_device_points(const fb200_interp* h, const double** d_px, const double** d_py, size_t* n)
+{
+    FB_REQUIRE(h != nullptr, "null interpolation handle");
+    if (d_px)
+        *d_px = h->d_px;
+    if (d_py)
+        *d_py = h->d_py;
+    if (n)
+        *n = h->npts;
+    return MIFI_OK;
+}
+
+size_t fb200_interp_new_size(const fb200_interp* h, size_t size)
+{
+    if (!h || h->inX * h->inY == 0)
+        return 0;
+    return h->outX * h->outY * (size / (h->inX * h->inY));
+}
+
+int fb200_interp_interpolate_values(const fb200_interp* h, const float* inData, size_t size, float* outData, size_t* newSize)
+{
+    size_t nz = 0;
+    if (check_interp_call(h, size, &nz) != FB_OK)
+        return MIFI_ERROR;
+    if (newSize)
+        *newSize = h->outX * h->outY * nz;
+    FB_REQUIRE(nz == 0 || (inData && outData), "null data pointer");
+    const float* in[1] = {inData};
+    float* out[1] = {outData};
+    return run_host(h, nullptr, 1, in, out, nz);
+}
+
+int fb200_interp_interpolate_values_device(const fb200_interp* h, const float* d_in, size_t size, float* d_out, size_t* newSize, void* stream)
+{
+    size_t nz = 0;
+    if (check_interp_call(h, size, &nz) != FB_OK)
+        return MIFI_ERROR;
+    if (newSize)
+        *newSize = h->outX * h->outY * nz;
+    FB_REQUIRE(nz == 0 || (d_in && d_out), "null data pointer");
+    return run_device(h, d_in, nz, d_out, as_stream(stream));
+}
+
+void fb200_interp_destroy(fb200_interp* h)
+{
+    delete h;
+}
+
+// ---------------------------------------------------------------------------------------- CachedVectorReprojection
+int fb200_vector_create(int method, const double* matrix, int ox, int oy, fb200_vector** handle)
+{
+    FB_REQUIRE(handle != nullptr, "null handle pointer");
+    *handle = nullptr;
+    FB_REQUIRE(ox >= 0 && oy >= 0, "negative size");
+    if (use_device(default_device()) != FB_OK)
+        return MIFI_ERROR;
+    std::unique_ptr<fb200_vector> v(new fb200_vector());
+    v->method = method;
+    v->ox = ox;
+    v->oy = oy;
+    v->device = default_device();
+    const size_t on = (size_t)ox * oy;
+    if (on && matrix) { // an uninitialised reprojection (no matrix) is the identity, CachedVectorReprojection.cc:37-40
+        cudaStream_t st = cudaStreamPerThread;
+        if (dev_alloc(&v->d_matrix, 4 * on) != FB_OK || dev_alloc(&v->d_cs, on) != FB_OK)
+            return MIFI_ERROR;
+        FB_CUDA_CHECK(cudaMemcpyAsync(v->d_matrix, matrix, sizeof(double) * 4 * on, cudaMemcpyHostToDevice, st));
+        if (launch_matrix_to_cossin(v->d_matrix, (long long)on, v->d_cs, st) != FB_OK)
+            return MIFI_ERROR;
+        FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    *handle = v.release();
+    return MIFI_OK;
+}
+
+int fb200_vector_create_from_projection(int method, const char* proj_input, const char* proj_output, const double* out_x_axis,
+                                        const double* out_y_axis, int xt, int yt, int ox, int oy, fb200_vector** handle)
+{
+    FB_REQUIRE(handle != nullptr, "null handle pointer");
+    *handle = nullptr;
+    FB_REQUIRE(ox > 0 && oy > 0 && out_x_axis && out_y_axis, "empty target grid");
+    if (use_device(default_device()) != FB_OK)
+        return MIFI_ERROR;
+    std::unique_ptr<fb200_vector> v(new fb200_vector());
+    v->method = method;
+    v->ox = ox;
+    v->oy = oy;
+    v->device = default_device();
+    const size_t on = (size_t)ox * oy;
+    cudaStream_t st = cudaStreamPerThread;
+    if (dev_alloc(&v->d_matrix, 4 * on) != FB_OK || dev_alloc(&v->d_cs, on) != FB_OK)
+        return MIFI_ERROR;
+    if (build_matrix_device(MI_AXES, proj_input, proj_output, out_x_axis, out_y_axis, xt, yt, ox, oy, 0, v->d_matrix, st) != FB_OK)
+        return MIFI_ERROR;
+    if (launch_matrix_to_cossin(v->d_matrix, (long long)on, v->d_cs, st) != FB_OK)
+        return MIFI_ERROR;
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    *handle = v.release();
+    return MIFI_OK;
+}
+
+int fb200_vector_reproject_values_device(const fb200_vector* v, float* d_u, float* d_v, size_t size, void* stream)
+{
+    FB_REQUIRE(v != nullptr, "null vector handle");
+    if (v->ox == 0 || v->oy == 0 || v->d_cs == nullptr) {
+        fprintf(stderr, "fimex_b200: CachedVectorReprojection not initialized, using identity\n");
+        return MIFI_OK;
+    }
+    if (use_device(v->device) != FB_OK)
+        return MIFI_ERROR;
+    const long long layer = (long long)v->ox * v->oy;
+    return launch_rotate(v->d_cs, d_u, d_v, layer, (long long)(size / (size_t)layer), as_stream(stream));
+}
+
+int fb200_vector_reproject_values(const fb200_vector* v, float* u, float* vv, size_t size)
+{
+    FB_REQUIRE(v != nullptr, "null vector handle");
+    if (v->ox == 0 || v->oy == 0 || v->d_cs == nullptr) {
+        fprintf(stderr, "fimex_b200: CachedVectorReprojection not initialized, using identity\n");
+        return MIFI_OK;
+    }
+    if (use_device(v->device) != FB_OK)
+        return MIFI_ERROR;
+    const size_t layer = (size_t)v->ox * v->oy;
+    const size_t n = (size / layer) * layer;
+    if (n == 0)
+        return MIFI_OK;
+    FB_REQUIRE(u && vv, "null data pointer");
+    cudaStream_t st = cudaStreamPerThread;
+    Scratch tmp(st);
+    float *d_u = nullptr, *d_v = nullptr;
+    if (tmp.upload(&d_u, u, n) != FB_OK || tmp.upload(&d_v, vv, n) != FB_OK)
+        return MIFI_ERROR;
+    if (launch_rotate(v->d_cs, d_u, d_v, (long long)layer, (long long)(n / layer), st) != FB_OK)
+        return MIFI_ERROR;
+    FB_CUDA_CHECK(cudaMemcpyAsync(u, d_u, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+    FB_CUDA_CHECK(cudaMemcpyAsync(vv, d_v, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return MIFI_OK;
+}
+
+int fb200_vector_reproject_direction_values(const fb200_vector* v, float* angles, size_t size)
+{
+    FB_REQUIRE(v != nullptr, "null vector handle");
+    if (v->ox == 0 || v->oy == 0 || v->d_matrix == nullptr) {
+        fprintf(stderr, "fimex_b200: CachedVectorReprojection not initialized, using identity\n");
+        return MIFI_OK;
+    }
+    if (use_device(v->device) != FB_OK)
+        return MIFI_ERROR;
+    const size_t layer = (size_t)v->ox * v->oy;
+    const size_t n = (size / layer) * layer;
+    if (n == 0)
+        return MIFI_OK;
+    cudaStream_t st = cudaStreamPerThread;
+    Scratch tmp(st);
+    float* d_a = nullptr;
+    if (tmp.upload(&d_a, angles, n) != FB_OK)
+        return MIFI_ERROR;
+    if (launch_rotate_direction(v->d_matrix, d_a, (long long)layer, (long long)(n / layer), st) != FB_OK)
+        return MIFI_ERROR;
+    FB_CUDA_CHECK(cudaMemcpyAsync(angles, d_a, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return MIFI_OK;
+}
+
+int fb200_vector_get_matrix(const fb200_vector* v, double* matrix)
+{
+    FB_REQUIRE(v != nullptr && matrix, "null argument");
+    if (use_device(v->device) != FB_OK)
+        return MIFI_ERROR;
+    if (v->d_matrix)
+        FB_CUDA_CHECK(cudaMemcpy(matrix, v->d_matrix, sizeof(double) * 4 * (size_t)v->ox * v->oy, cudaMemcpyDeviceToHost));
+    return MIFI_OK;
+}
+
+void fb200_vector_destroy(fb200_vector* v)
+{
+    delete v;
+}
+
+static int check_vector_call(const fb200_interp* h, const fb200_vector* v)
+{
+    FB_REQUIRE(h != nullptr, "null interpolation handle");
+    FB_REQUIRE(!h->forward, "vector data cannot be interpolated with forward interpolation"); // CDMInterpolator.cc:1332
+    if (v && v->d_cs)
+        FB_REQUIRE((size_t)v->ox == h->outX && (size_t)v->oy == h->outY && v->device == h->device,
+                   "vector reprojection and interpolation have different target grids or devices");
+    return FB_OK;
+}
+
+int fb200_interp_interpolate_vector_device(const fb200_interp* h, const fb200_vector* v, const float* d_u, const float* d_v, size_t size,
+                                           float* d_uo, float* d_vo, size_t* newSize, void* stream)
+{
+    size_t nz = 0;
+    if (check_vector_call(h, v) != FB_OK || check_interp_call(h, size, &nz) != FB_OK)
+        return MIFI_ERROR;
+    if (newSize)
+        *newSize = h->outX * h->outY * nz;
+    return run_vector_device(h, (v && v->d_cs) ? v : nullptr, d_u, d_v, nz, d_uo, d_vo, as_stream(stream));
+}
+
+int fb200_interp_interpolate_vector(const fb200_interp* h, const fb200_vector* v, const float* uIn, const float* vIn, size_t size, float* uOut,
+                                    float* vOut, size_t* newSize)
+{
+    size_t nz = 0;
+    if (check_vector_call(h, v) != FB_OK || check_interp_call(h, size, &nz) != FB_OK)
+        return MIFI_ERROR;
+    if (newSize)
+        *newSize = h->outX * h->outY * nz;
+    FB_REQUIRE(nz == 0 || (uIn && vIn && uOut && vOut), "null data pointer");
+    const float* in[2] = {uIn, vIn};
+    float* out[2] = {uOut, vOut};
+    return run_host(h, (v && v->d_cs) ? v : nullptr, 2, in, out, nz);
+}
+
+// ---------------------------------------------------------------------------------------- mifi_* drop-ins
+int mifi_string_to_interpolation_method(const char* s)
+{
+    // src/interpolation.c:66-101; "forward_undef_min" -> FORWARD_MIN is the reference's behaviour (:97-98)
+    static const struct {
+        const char* name;
+        int method;
+    } table[] = {{"bilinear", FB_BILINEAR},
+                 {"nearestneighbor", FB_NN},
+                 {"bicubic", FB_BICUBIC},
+                 {"coord_nearestneighbor", FB_COORD_NN},
+                 {"coord_kdtree", FB_COORD_NN_KD},
+                 {"forward_sum", FB_FWD_SUM},
+                 {"forward_mean", FB_FWD_MEAN},
+                 {"forward_median", FB_FWD_MEDIAN},
+                 {"forward_max", FB_FWD_MAX},
+                 {"forward_min", FB_FWD_MIN},
+                 {"forward_undef_sum", FB_FWD_UNDEF_SUM},
+                 {"forward_undef_mean", FB_FWD_UNDEF_MEAN},
+                 {"forward_undef_median", FB_FWD_UNDEF_MEDIAN},
+                 {"forward_undef_max", FB_FWD_UNDEF_MAX},
+                 {"forward_undef_min", FB_FWD_MIN}};
+    if (!s)
+        return -1;
+    for (const auto& e : table)
+        if (std::strcmp(e.name, s) == 0)
+            return e.method;
+    return -1;
+}
+
+int mifi_project_values(const char* proj_input, const char* proj_output, double* x, double* y, const int num)
+{
+    ProjDef pin, pout;
+    if (parse_pair(proj_input, proj_output, &pin, &pout) != FB_OK)
+        return MIFI_ERROR;
+    if (num <= 0)
+        return MIFI_OK;
+    FB_REQUIRE(x && y, "null argument");
+    if (use_device(default_device()) != FB_OK)
+        return MIFI_ERROR;
+    cudaStream_t st = cudaStreamPerThread;
+    Scratch tmp(st);
+    double *d_x = nullptr, *d_y = nullptr;
+    int* d_status = nullptr;
+    if (tmp.upload(&d_x, x, (size_t)num) != FB_OK || tmp.upload(&d_y, y, (size_t)num) != FB_OK || tmp.get(&d_status, 1) != FB_OK)
+        return MIFI_ERROR;
+    FB_CUDA_CHECK(cudaMemsetAsync(d_status, 0, sizeof(int), st));
+    if (launch_project_values(pin, pout, d_x, d_y, num, d_status, st) != FB_OK)
+        return MIFI_ERROR;
+    if (check_status(d_status, st, "mifi_project_values") != FB_OK)
+        return MIFI_ERROR;
+    FB_CUDA_CHECK(cudaMemcpyAsync(x, d_x, sizeof(double) * num, cudaMemcpyDeviceToHost, st));
+    FB_CUDA_CHECK(cudaMemcpyAsync(y, d_y, sizeof(double) * num, cudaMemcpyDeviceToHost, st));
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return MIFI_OK;
+}
+
+int mifi_project_axes(const char* proj_input, const char* proj_output, const double* in_x_axis, const double* in_y_axis, const int ix,
+                      const int iy, double* out_x, double* out_y)
+{
+    ProjDef pin, pout;
+    if (parse_pair(proj_input, proj_output, &pin, &pout) != FB_OK)
+        return MIFI_ERROR;
+    if (ix <= 0 || iy <= 0)
+        return MIFI_OK;
+    FB_REQUIRE(in_x_axis && in_y_axis && out_x && out_y, "null argument");
+    if (use_device(default_device()) != FB_OK)
+        return MIFI_ERROR;
+    cudaStream_t st = cudaStreamPerThread;
+    const size_t n = (size_t)ix * iy;
+    Scratch tmp(st);
+    double *d_x = nullptr, *d_y = nullptr;
+    if (tmp.get(&d_x, n) != FB_OK || tmp.get(&d_y, n) != FB_OK)
+        return MIFI_ERROR;
+    const std::vector<double> xa(in_x_axis, in_x_axis + ix), ya(in_y_axis, in_y_axis + iy);
+    if (project_axes_device(pin, pout, xa, ya, d_x, d_y, st, "mifi_project_axes") != FB_OK)
+        return MIFI_ERROR;
+    FB_CUDA_CHECK(cudaMemcpyAsync(out_x, d_x, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    FB_CUDA_CHECK(cudaMemcpyAsync(out_y, d_y, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return MIFI_OK;
+}
+
+int mifi_points2position(double* points, const int n, const double* axis, const int num, const int axis_type)
+{
+    if (n <= 0)
+        return MIFI_OK;
+    FB_REQUIRE(points && axis && num >= 2, "mifi_points2position: null argument or axis shorter than 2");
+    if (use_device(default_device()) != FB_OK)
+        return MIFI_ERROR;
+    cudaStream_t st = cudaStreamPerThread;
+    Scratch tmp(st);
+    double* d_p = nullptr;
+    if (tmp.upload(&d_p, points, (size_t)n) != FB_OK)
+        return MIFI_ERROR;
+    const std::vector<double> ax(axis, axis + num);
+    if (points2position_device(d_p, n, ax, axis_type, st) != FB_OK)
+        return MIFI_ERROR;
+    FB_CUDA_CHECK(cudaMemcpyAsync(points, d_p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return MIFI_OK;
+}
+
+int mifi_interpolate_f(int method, const char* proj_input, const float* infield, const double* in_x_axis, const double* in_y_axis,
+                       const int in_x_axis_type, const int in_y_axis_type, const int ix, const int iy, const int iz, const char* proj_output,
+                       float* outfield, const double* out_x_axis, const double* out_y_axis, const int out_x_axis_type,
+                       const int out_y_axis_type, const int ox, const int oy)
+{
+    // src/interpolation.c:281-297: only the three gather methods; anything else is an error before any work
+    if (method != FB_NN && method != FB_BILINEAR && method != FB_BICUBIC)
+        return MIFI_ERROR;
+    FB_REQUIRE(ix > 0 && iy > 0 && iz >= 0 && ox >= 0 && oy >= 0, "mifi_interpolate_f: bad dimensions");
+    FB_REQUIRE(in_x_axis && in_y_axis && out_x_axis && out_y_axis, "mifi_interpolate_f: null axis");
+    ProjDef pin, pout;
+    // the reference ignores a failing mifi_project_axes here (:257) and interpolates garbage; failing is the
+    // only defined behaviour we can offer
+    if (parse_pair(proj_input, proj_output, &pin, &pout) != FB_OK)
+        return MIFI_ERROR;
+    auto typed_deg = [](int t) { return t == FB_AXIS_LONGITUDE || t == FB_AXIS_LATITUDE; };
+    const std::vector<double> ixa = axis_in_radians(in_x_axis, (size_t)ix, typed_deg(in_x_axis_type));
+    const std::vector<double> iya = axis_in_radians(in_y_axis, (size_t)iy, typed_deg(in_y_axis_type));
+    const std::vector<double> oxa = axis_in_radians(out_x_axis, (size_t)ox, typed_deg(out_x_axis_type));
+    const std::vector<double> oya = axis_in_radians(out_y_axis, (size_t)oy, typed_deg(out_y_axis_type));
+    std::unique_ptr<fb200_interp> h;
+    if (new_interp(method, false, (size_t)ix, (size_t)iy, (size_t)ox, (size_t)oy, &h) != FB_OK)
+        return MIFI_ERROR;
+    cudaStream_t st = cudaStreamPerThread;
+    if (h->npts) {
+        if (project_axes_device(pout, pin, oxa, oya, h->d_px, h->d_py, st, "mifi_interpolate_f") != FB_OK)
+            return MIFI_ERROR;
+        if (points2position_device(h->d_px, (long long)h->npts, ixa, in_x_axis_type, st) != FB_OK)
+            return MIFI_ERROR;
+        if (points2position_device(h->d_py, (long long)h->npts, iya, in_y_axis_type, st) != FB_OK)
+            return MIFI_ERROR;
+    }
+    if (compile_tables(h.get(), st) != FB_OK)
+        return MIFI_ERROR;
+    if (iz == 0 || h->npts == 0)
+        return MIFI_OK;
+    FB_REQUIRE(infield && outfield, "mifi_interpolate_f: null field");
+    const float* in[1] = {infield};
+    float* out[1] = {outfield};
+    return run_host(h.get(), nullptr, 1, in, out, (size_t)iz);
+}
+
+int mifi_get_vector_reproject_matrix(const char* proj_input, const char* proj_output, const double* out_x_axis, const double* out_y_axis,
+                                     int xt, int yt, int ox, int oy, double* matrix)
+{
+    return matrix_to_host(MI_AXES, proj_input, proj_output, out_x_axis, out_y_axis, xt, yt, ox, oy, 0, matrix);
+}
+
+int mifi_get_vector_reproject_matrix_field(const char* proj_input, const char* proj_output, const double* in_x_field, const double* in_y_field,
+                                           int ox, int oy, double* matrix)
+{
+    return matrix_to_host(MI_FIELD, proj_input, proj_output, in_x_field, in_y_field, 0, 0, ox, oy, 0, matrix);
+}
+
+int mifi_get_vector_reproject_matrix_points(const char* proj_input, const char* proj_output, int inputIsMetric, const double* out_x_points,
+                                            const double* out_y_points, int on, double* matrix)
+{
+    return matrix_to_host(MI_POINTS, proj_input, proj_output, out_x_points, out_y_points, 0, 0, on, 1, inputIsMetric, matrix);
+}
+
+int mifi_vector_reproject_values_by_matrix_f(int method, const double* matrix, float* u_out, float* v_out, int ox, int oy, int oz)
+{
+    fb200_vector* v = nullptr;
+    if (fb200_vector_create(method, matrix, ox, oy, &v) != MIFI_OK)
+        return MIFI_ERROR;
+    const int rc = (ox > 0 && oy > 0 && oz > 0) ? fb200_vector_reproject_values(v, u_out, v_out, (size_t)ox * oy * oz) : MIFI_OK;
+    fb200_vector_destroy(v);
+    return rc;
+}
+
+int mifi_vector_reproject_direction_by_matrix_f(int method, const double* matrix, float* angle_out, int ox, int oy, int oz)
+{
+    fb200_vector* v = nullptr;
+    if (fb200_vector_create(method, matrix, ox, oy, &v) != MIFI_OK)
+        return MIFI_ERROR;
+    const int rc = (ox > 0 && oy > 0 && oz > 0) ? fb200_vector_reproject_direction_values(v, angle_out, (size_t)ox * oy * oz) : MIFI_OK;
+    fb200_vector_destroy(v);
+    return rc;
+}
+
+int mifi_vector_reproject_values_f(int method, const char* proj_input, const char* proj_output, float* u_out, float* v_out,
+                                   const double* out_x_axis, const double* out_y_axis, int xt, int yt, int ox, int oy, int oz)
+{
+    // src/interpolation.c:837-859, without the round trip of the matrix through the host
+    fb200_vector* v = nullptr;
+    if (fb200_vector_create_from_projection(method, proj_input, proj_output, out_x_axis, out_y_axis, xt, yt, ox, oy, &v) != MIFI_OK)
+        return MIFI_ERROR;
+    const int rc = (oz > 0) ? fb200_vector_reproject_values(v, u_out, v_out, (size_t)ox * oy * oz) : MIFI_OK;
+    fb200_vector_destroy(v);
+    return rc;
+}
+
+static int one_point(int method, const float* infield, float* outvalues, double x, double y, int ix, int iy, int iz)
+{
+    fb200_interp* h = nullptr;
+    if (fb200_cached_interpolation_create(method, &x, &y, (size_t)ix, (size_t)iy, 1, 1, &h) != MIFI_OK)
+        return MIFI_ERROR;
+    size_t ns = 0;
+    const int rc = fb200_interp_interpolate_values(h, infield, (size_t)ix * iy * iz, outvalues, &ns);
+    fb200_interp_destroy(h);
+    return rc;
+}
+
+int mifi_get_values_f(const float* infield, float* outfield, const double x, const double y, const int ix, const int iy, const int iz)
+{
+    return one_point(FB_NN, infield, outfield, x, y, ix, iy, iz);
+}
+int mifi_get_values_bilinear_f(const float* infield, float* outvalues, const double x, const double y, const int ix, const int iy, const int iz)
+{
+    return one_point(FB_BILINEAR, infield, outvalues, x, y, ix, iy, iz);
+}
+int mifi_get_values_bicubic_f(const float* infield, float* outvalues, const double x, const double y, const int ix, const int iy, const int iz)
+{
+    return one_point(FB_BICUBIC, infield, outvalues, x, y, ix, iy, iz);
+}
+
+int mifi_setNumThreads(int n)
+{
+    (void)n; // src/ThreadPool.c:33-46 sets the OpenMP team size; the GPU path has no host threads to size
+    return MIFI_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,219 @@
+// fimex_b200/csrc/forward_kernels.cu -- K8: forward ("scatter") interpolation as sort-then-segment.
+//
+// Replaces CachedForwardInterpolation::interpolateValues
+// (/root/reference/src/CachedForwardInterpolation.cc:92-131, aggregators :38-59).  The reference pushes
+// every defined input value into a std::vector per target cell, in input (row-major) order, then
+// aggregates each vector.  Here the bucketing is done ONCE per grid: input indices are stably sorted by
+// target cell (CSR: `perm` + `offsets`), and each slice runs one segmented-reduce kernel in which a thread
+// walks its cell's segment in ascending input order -- the same order as the reference's vectors, so the
+// sequential fp32 sum of forward_mean/forward_sum is bit-identical; max/min are order-free.
+//
+// Per level: reads 4 B per input value + 4 B per perm entry + 4 B per cell offset, writes 4 B per cell.
+// The one-time stable sort uses cub::DeviceRadixSort (CUDA toolkit); the per-slice kernel is hand-written.
+#include "kernels.h"
+
+#include <cub/device/device_radix_sort.cuh>
+
+namespace fb {
+
+namespace {
+constexpr int kThreads = 256;
+
+__global__ void k_forward_keys(const int* __restrict__ cell, long long n, unsigned n_cells, unsigned* __restrict__ keys,
+                               int* __restrict__ vals)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int c = cell[i];
+        keys[i] = c >= 0 ? (unsigned)c : n_cells; // unmapped points sort behind every cell
+        vals[i] = (int)i;
+    }
+}
+
+// offsets[c] = first position in the sorted keys whose key >= c  (c in [0, n_cells])
+__global__ void k_forward_offsets(const unsigned* __restrict__ sorted_keys, long long n, long long n_cells, int* __restrict__ offsets)
+{
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c <= n_cells; c += (long long)gridDim.x * blockDim.x) {
+        long long lo = 0, hi = n;
+        while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            if (sorted_keys[mid] < (unsigned)c)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        offsets[c] = (int)lo;
+    }
+}
+
+enum { AG_SUM = 0, AG_MEAN = 1, AG_MEDIAN = 2, AG_MAX = 3, AG_MIN = 4 };
+
+template <int AGG, bool UNDEF>
+__global__ void __launch_bounds__(kThreads) k_forward(const int* __restrict__ perm, const int* __restrict__ offsets,
+                                                    const float* __restrict__ in, float* __restrict__ out, long long n_in,
+                                                    long long n_cells, long long nz)
+{
+    const long long c = blockIdx.x * (long long)kThreads + threadIdx.x;
+    if (c >= n_cells)
+        return;
+    const int beg = __ldg(offsets + c), end = __ldg(offsets + c + 1);
+    for (long long z = blockIdx.y; z < nz; z += gridDim.y) {
+        const float* lv = in + z * n_in;
+        float res = undef_f();
+        if (AGG == AG_SUM || AGG == AG_MEAN) {
+            float s = 0.f; // std::accumulate(begin, end, 0.f): sequential, input order
+            long long cnt = 0;
+            for (int k = beg; k < end; ++k) {
+                const float v = __ldg(lv + __ldg(perm + k));
+                if (UNDEF || !isnan(v)) {
+                    s = __fadd_rn(s, v);
+                    ++cnt;
+                }
+            }
+            if (cnt > 0)
+                res = (AGG == AG_MEAN) ? __fdiv_rn(s, __ll2float_rn(cnt)) : s;
+        } else if (AGG == AG_MAX || AGG == AG_MIN) {
+            bool have = false;
+            float best = 0.f;
+            for (int k = beg; k < end; ++k) {
+                const float v = __ldg(lv + __ldg(perm + k));
+                if (UNDEF || !isnan(v)) {
+                    if (!have) {
+                        best = v;
+                        have = true;
+                    } else if (AGG == AG_MAX ? (best < v) : (v < best)) { // std::max_element / min_element
+                        best = v;
+                    }
+                }
+            }
+            if (have)
+                res = best;
+        } else { // median = sorted[n/2] (nth_element, :49-53); rank selection, O(n^2) but segments are short
+            long long cnt = 0;
+            for (int k = beg; k < end; ++k) {
+                const float v = __ldg(lv + __ldg(perm + k));
+                if (UNDEF || !isnan(v))
+                    ++cnt;
+            }
+            if (cnt > 0) {
+                const long long want = cnt / 2;
+                for (int k = beg; k < end; ++k) {
+                    const float v = __ldg(lv + __ldg(perm + k));
+                    if (!(UNDEF || !isnan(v)))
+                        continue;
+                    long long less = 0, eq = 0;
+                    for (int j = beg; j < end; ++j) {
+                        const float w = __ldg(lv + __ldg(perm + j));
+                        if (!(UNDEF || !isnan(w)))
+                            continue;
+                        less += (w < v);
+                        eq += (w == v);
+                    }
+                    if (less <= want && want < less + eq) {
+                        res = v;
+                        break;
+                    }
+                }
+            }
+        }
+        __stcs(out + z * n_cells + c, res);
+    }
+}
+
+template <int AGG>
+int launch_agg(bool undef, dim3 grid, cudaStream_t st, const ForwardPlan& p, const float* in, float* out, long long nz)
+{
+    if (undef)
+        k_forward<AGG, true><<<grid, kThreads, 0, st>>>(p.d_perm, p.d_offsets, in, out, p.n_in, p.n_cells, nz);
+    else
+        k_forward<AGG, false><<<grid, kThreads, 0, st>>>(p.d_perm, p.d_offsets, in, out, p.n_in, p.n_cells, nz);
+    count_launch();
+    FB_CUDA_CHECK(cudaGetLastError());
+    return FB_OK;
+}
+
+} // namespace
+
+int forward_build_plan(const int* d_cell, long long n_in, long long n_cells, ForwardPlan* plan, cudaStream_t st)
+{
+    FB_REQUIRE(n_in < 2147483647LL && n_cells < 2147483647LL, "forward interpolation: more than 2^31 points or cells");
+    plan->n_in = n_in;
+    plan->n_cells = n_cells;
+    FB_CUDA_CHECK(cudaMalloc(&plan->d_perm, sizeof(int) * (size_t)(n_in > 0 ? n_in : 1)));
+    FB_CUDA_CHECK(cudaMalloc(&plan->d_offsets, sizeof(int) * (size_t)(n_cells + 1)));
+    if (n_in == 0) {
+        FB_CUDA_CHECK(cudaMemsetAsync(plan->d_offsets, 0, sizeof(int) * (size_t)(n_cells + 1), st));
+        return FB_OK;
+    }
+    unsigned *d_keys = nullptr, *d_keys_sorted = nullptr;
+    int* d_vals = nullptr;
+    void* d_tmp = nullptr;
+    FB_CUDA_CHECK(cudaMallocAsync(&d_keys, sizeof(unsigned) * (size_t)n_in, st));
+    FB_CUDA_CHECK(cudaMallocAsync(&d_keys_sorted, sizeof(unsigned) * (size_t)n_in, st));
+    FB_CUDA_CHECK(cudaMallocAsync(&d_vals, sizeof(int) * (size_t)n_in, st));
+    const int blocks = (int)((n_in + kThreads - 1) / kThreads < 65535 * 16 ? (n_in + kThreads - 1) / kThreads : 65535 * 16);
+    k_forward_keys<<<blocks, kThreads, 0, st>>>(d_cell, n_in, (unsigned)n_cells, d_keys, d_vals);
+    count_launch();
+    int end_bit = 1;
+    while (end_bit < 32 && (1ull << end_bit) <= (unsigned long long)n_cells)
+        ++end_bit;
+    size_t tmp_bytes = 0;
+    FB_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys_sorted, d_vals, plan->d_perm, (int)n_in, 0, end_bit, st));
+    FB_CUDA_CHECK(cudaMallocAsync(&d_tmp, tmp_bytes ? tmp_bytes : 16, st));
+    // LSD radix sort is stable: inside a cell the input indices stay ascending
+    FB_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys_sorted, d_vals, plan->d_perm, (int)n_in, 0, end_bit, st));
+    count_launch(4);
+    const long long nb = (n_cells + 1 + kThreads - 1) / kThreads;
+    k_forward_offsets<<<(int)(nb < 65535 * 16 ? nb : 65535 * 16), kThreads, 0, st>>>(d_keys_sorted, n_in, n_cells, plan->d_offsets);
+    count_launch();
+    FB_CUDA_CHECK(cudaGetLastError());
+    int last = 0;
+    FB_CUDA_CHECK(cudaMemcpyAsync(&last, plan->d_offsets + n_cells, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FB_CUDA_CHECK(cudaFreeAsync(d_keys, st));
+    FB_CUDA_CHECK(cudaFreeAsync(d_keys_sorted, st));
+    FB_CUDA_CHECK(cudaFreeAsync(d_vals, st));
+    FB_CUDA_CHECK(cudaFreeAsync(d_tmp, st));
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    plan->n_mapped = last;
+    return FB_OK;
+}
+
+void forward_free_plan(ForwardPlan* plan)
+{
+    if (plan->d_perm)
+        cudaFree(plan->d_perm);
+    if (plan->d_offsets)
+        cudaFree(plan->d_offsets);
+    plan->d_perm = nullptr;
+    plan->d_offsets = nullptr;
+}
+
+int launch_forward(int method, const ForwardPlan& plan, const float* d_in, float* d_out, long long nz, cudaStream_t st)
+{
+    if (plan.n_cells == 0 || nz == 0)
+        return FB_OK;
+    const bool undef = method >= FB_FWD_UNDEF_SUM;
+    const int gx = ceil_div(plan.n_cells, kThreads);
+    dim3 grid(gx, (unsigned)(nz < 64 ? nz : 64));
+    switch (method) {
+    case FB_FWD_SUM:
+    case FB_FWD_UNDEF_SUM:
+        return launch_agg<AG_SUM>(undef, grid, st, plan, d_in, d_out, nz);
+    case FB_FWD_MEAN:
+    case FB_FWD_UNDEF_MEAN:
+        return launch_agg<AG_MEAN>(undef, grid, st, plan, d_in, d_out, nz);
+    case FB_FWD_MEDIAN:
+    case FB_FWD_UNDEF_MEDIAN:
+        return launch_agg<AG_MEDIAN>(undef, grid, st, plan, d_in, d_out, nz);
+    case FB_FWD_MAX:
+    case FB_FWD_UNDEF_MAX:
+        return launch_agg<AG_MAX>(undef, grid, st, plan, d_in, d_out, nz);
+    case FB_FWD_MIN:
+    case FB_FWD_UNDEF_MIN:
+        return launch_agg<AG_MIN>(undef, grid, st, plan, d_in, d_out, nz);
+    default:
+        set_error("unknown forward interpolation method");
+        return FB_ERROR;
+    }
+}
+
+} // namespace fb

@@ -1,0 +1,75 @@
+// fimex_b200/csrc/kernels.h -- internal launch interface between api.cu and the kernel files.
+// All pointers are DEVICE pointers unless a name says host; all functions enqueue on `st` and return
+// FB_OK / FB_ERROR without synchronising unless stated.
+#pragma once
+
+#include "common.cuh"
+#include "proj.cuh"
+
+namespace fb {
+
+// ---- setup_kernels.cu (K1, K2, K7, crop, table compilation) ------------------------------------------
+// K1: expand axes to a mesh and transform src -> dst (mifi_project_axes, interpolation.c:1199-1244).
+// d_status receives a non-zero PROJ error number when a point fails non-transiently.
+int launch_project_mesh(const ProjDef& src, const ProjDef& dst, const double* d_xaxis, const double* d_yaxis, int nx, int ny, double* d_xo,
+                        double* d_yo, int* d_status, cudaStream_t st);
+// K1: transform arrays in place (mifi_project_values, interpolation.c:1158-1197)
+int launch_project_values(const ProjDef& src, const ProjDef& dst, double* d_x, double* d_y, long long n, int* d_status, cudaStream_t st);
+// K2: coordinate -> fractional array position, in place (mifi_points2position, interpolation.c:148-217)
+int launch_points2position(double* d_points, long long n, const double* d_axis, const double* h_axis, int num, int axis_type,
+                           cudaStream_t st);
+// min/max of an array (std::min_element / max_element of CachedInterpolation.cc:165-168); synchronises
+int device_minmax(const double* d_v, long long n, double* h_min, double* h_max, cudaStream_t st);
+// v[i] -= delta (CachedInterpolation.cc:183-186)
+int launch_shift(double* d_v, long long n, double delta, cudaStream_t st);
+// deg -> rad / copy (convertAxis, interpolation.c:221-229)
+int launch_scale(double* d_v, long long n, double factor, cudaStream_t st);
+
+// positions -> gather tables
+int launch_compile_nn(const double* d_px, const double* d_py, long long n, int ix, int iy, int* d_off, cudaStream_t st);
+int launch_compile_bilinear(const double* d_px, const double* d_py, long long n, int ix, int iy, int4* d_tab, cudaStream_t st);
+int launch_compile_bicubic(const double* d_px, const double* d_py, long long n, int ix, int iy, int* d_off, double2* d_frac,
+                           cudaStream_t st);
+// forward: positions (per INPUT point) -> target cell or -1 (CachedForwardInterpolation.cc:73-74, Utils.cc:42-58)
+int launch_compile_forward_cells(const double* d_px, const double* d_py, long long n, int ox, int oy, int* d_cell, cudaStream_t st);
+
+// K7: rotation matrix from the three projected fields (interpolation.c:330-438)
+int launch_vector_matrix(const ProjDef& in, const ProjDef& out, const double* d_in_x, const double* d_in_y, const double* d_out_x,
+                         const double* d_out_y, double dx, double dy, long long n, double* d_matrix, int* d_status, cudaStream_t st);
+// matrix [n][4] -> compact (cos, sin) pairs
+int launch_matrix_to_cossin(const double* d_matrix, long long n, double2* d_cs, cudaStream_t st);
+
+// K9: coord_nearestneighbor search (CDMInterpolator.cc:1141-1220) -- see coordnn_kernels.cu
+int coordnn_search(double* d_px, double* d_py, long long n, const double* h_lon, const double* h_lat, size_t nx, size_t ny,
+                   long long* ties, cudaStream_t st);
+
+// ---- gather_kernels.cu (K3, K4, K5, K6) -------------------------------------------------------------
+struct GatherGeom {
+    int ix, iy, ox, oy;
+    long long in_level;  // ix*iy
+    long long out_level; // ox*oy
+    long long nz;
+};
+int launch_gather_nn(const GatherGeom& g, const int* d_off, const float* d_in, float* d_out, cudaStream_t st);
+int launch_gather_bilinear(const GatherGeom& g, const int4* d_tab, const float* d_in, float* d_out, cudaStream_t st);
+int launch_gather_bicubic(const GatherGeom& g, const int* d_off, const double2* d_frac, const float* d_in, float* d_out, cudaStream_t st);
+// fused u/v: interpolate both components with one table and rotate (K6 fused); d_cs may be null (no rotation)
+int launch_gather_vector(int method, const GatherGeom& g, const void* d_tab, const void* d_tab2, const double2* d_cs, const float* d_u_in,
+                         const float* d_v_in, float* d_u_out, float* d_v_out, cudaStream_t st);
+// K6 stand-alone: rotate u, v in place (mifi_vector_reproject_values_by_matrix_f, interpolation.c:790-812)
+int launch_rotate(const double2* d_cs, float* d_u, float* d_v, long long layer, long long nz, cudaStream_t st);
+// mifi_vector_reproject_direction_by_matrix_f (interpolation.c:814-835)
+int launch_rotate_direction(const double* d_matrix, float* d_angle, long long layer, long long nz, cudaStream_t st);
+
+// ---- forward_kernels.cu (K8) ---------------------------------------------------------------------------
+struct ForwardPlan {
+    long long n_in = 0, n_cells = 0;
+    int* d_perm = nullptr;    // input indices grouped by target cell, ascending inside each cell
+    int* d_offsets = nullptr; // n_cells + 1
+    long long n_mapped = 0;
+};
+int forward_build_plan(const int* d_cell, long long n_in, long long n_cells, ForwardPlan* plan, cudaStream_t st);
+void forward_free_plan(ForwardPlan* plan);
+int launch_forward(int method, const ForwardPlan& plan, const float* d_in, float* d_out, long long nz, cudaStream_t st);
+
+} // namespace fb

@@ -1,0 +1,216 @@
+"""Host-side mirror of the part of CDMInterpolator that sits on the hot path.
+
+Reference: /root/reference/src/CDMInterpolator.cc
+  changeProjection(method, proj_input, out_x_axis, out_y_axis, units)          :420-450   (dispatch on method)
+  changeProjectionByProjectionParameters / ...ByCoordinates / ...ByForwardInterpolation  :1422-1503 / :1336-1420 / :1242-1334
+  getDataSlice                                                                   :235-287   (per-slice driver)
+  data2InterpolationArray / interpolationArray2Data                              :115-124   (bad <-> NaN adapters)
+and the axis-string grammar of SpatialAxisSpec (src/SpatialAxisSpec.cc:84-150, include/fimex/Utils.h:373-407).
+
+The CDM metadata side of the reference (coordinate-system discovery, CDM rewrite, NetCDF readers) stays with
+the host application; here the source grid is described directly by its proj4 string and axes (or 2-D lon/lat),
+which is exactly what the reference extracts from the CDM before it calls the functions this package replaces.
+All array arithmetic happens in libfimex_b200.so on the GPU.
+"""
+from __future__ import annotations
+
+import re
+
+import numpy as np
+
+from . import capi
+from .cached import CachedForwardInterpolation, CachedInterpolation, CachedVectorReprojection
+from .capi import FimexB200Error, Method
+
+_DEGREE = re.compile(r".*degree.*", re.S)  # boost::regex degree(".*degree.*"), CDMInterpolator.cc:1443
+
+MIFI_WGS84_LATLON_PROJ4 = "+proj=latlong +datum=WGS84 +towgs84=0,0,0 +no_defs"  # include/fimex/CDMconstants.h:118
+MIFI_EARTH_RADIUS_M = 6371000  # include/fimex/CDMconstants.h:113
+
+
+def tokenize_dotted(spec: str, delimiter: str = ",") -> list:
+    """tokenizeDotted<double> (include/fimex/Utils.h:373-407): "0,0.5,...,3" -> [0, 0.5, 1, ..., 3]"""
+    toks = [t for t in spec.split(delimiter)]
+    vals: list = []
+    i = 0
+    while i < len(toks):
+        cur = toks[i].strip()
+        if cur == "...":
+            if len(vals) < 2:
+                raise FimexB200Error("tokenizeDotted: cannot use ... expansion, need at least two values before")
+            last = vals[-1]
+            dist = last - vals[-2]
+            cur_val = last + dist
+            direction = 1.0 if dist > 0 else -1.0
+            i += 1
+            if i < len(toks):
+                after = float(toks[i])
+                round_error = direction * dist * -1.0e-5
+                while (cur_val - after) * direction < round_error:
+                    vals.append(cur_val)
+                    cur_val += dist
+                vals.append(after)
+        else:
+            vals.append(float(cur))
+        i += 1
+    return vals
+
+
+def spatial_axis_spec(spec) -> np.ndarray:
+    """SpatialAxisSpec for absolute axis strings (src/SpatialAxisSpec.cc:84-150); relativeStart needs the source
+    bounding box and is left to the caller."""
+    if not isinstance(spec, str):
+        return np.asarray(spec, dtype=np.float64)
+    steps = None
+    for part in spec.split(";"):
+        kv = part.split("=")
+        if len(kv) == 1:
+            if steps is not None:
+                raise FimexB200Error("axis-steps redefined")
+            steps = kv[0]
+        elif kv[0] == "relativeStart":
+            raise FimexB200Error("relativeStart axis specs need the source bounding box; pass explicit values")
+        elif kv[0] == "unit":
+            raise FimexB200Error("unit not supported yet in SpatialAxisSpec, please enter values in m or degree")
+        else:
+            raise FimexB200Error(f"unknown axisSpec parameter: '{kv[0]}'")
+    return np.asarray(tokenize_dotted(steps or ""), dtype=np.float64)
+
+
+def lon_lat_vals_to_matrix(lon_vals, lat_vals):
+    """lonLatVals2Matrix (CDMInterpolator.cc:1226-1239): index ix + iy*lonSize"""
+    lon_vals = np.asarray(lon_vals, dtype=np.float64)
+    lat_vals = np.asarray(lat_vals, dtype=np.float64)
+    lon2d = np.tile(lon_vals, lat_vals.size)
+    lat2d = np.repeat(lat_vals, lon_vals.size)
+    return lon2d, lat2d
+
+
+class Interpolator:
+    """The hot-path half of CDMInterpolator for one horizontal coordinate system.
+
+    source_proj4 : proj4 string of the source CRS (Projection::getProj4String, ProjectionImpl.cc:116-137)
+    x_axis,y_axis: source axes in the projection's unit ("m") or degrees when `is_degree`
+                   (Projection::isDegree(): lat/long and rotated lat/long)
+    lon2d, lat2d : optional 2-D coordinates in degrees (index ix + iy*nx) for coord_* and forward_* methods;
+                   derived from the axes when the source is a lat/long grid (latLonProj, :1376-1380)
+    has_xy_vectors: whether the data contains x/y-directed vector pairs (hasXYSpatialVectors(), :1490)
+    """
+
+    def __init__(self, source_proj4, x_axis, y_axis, is_degree, lon2d=None, lat2d=None, has_xy_vectors=False, x_dim="x", y_dim="y"):
+        self.source_proj4 = source_proj4
+        self.x_axis = np.asarray(x_axis, dtype=np.float64)
+        self.y_axis = np.asarray(y_axis, dtype=np.float64)
+        self.is_degree = bool(is_degree)
+        self.lon2d = None if lon2d is None else np.asarray(lon2d, dtype=np.float64).ravel()
+        self.lat2d = None if lat2d is None else np.asarray(lat2d, dtype=np.float64).ravel()
+        self.has_xy_vectors = has_xy_vectors
+        self.x_dim, self.y_dim = x_dim, y_dim
+        self.cachedInterpolation = None
+        self.cachedVectorReprojection = None
+        self.method = Method.UNKNOWN
+
+    # ---- setup --------------------------------------------------------------------------------
+    def changeProjection(self, method, proj_input, out_x_axis, out_y_axis, out_x_axis_unit="m", out_y_axis_unit="m"):
+        """CDMInterpolator::changeProjection (:345-450).  `method` may be the option string
+        (--interpolate.method) or the enum value; axes may be option strings ("0,0.5,...,10") or arrays."""
+        if isinstance(method, str):
+            m = capi.mifi_string_to_interpolation_method(method)
+        else:
+            m = int(method)
+        out_x = spatial_axis_spec(out_x_axis)
+        out_y = spatial_axis_spec(out_y_axis)
+        self.cachedInterpolation = None
+        self.cachedVectorReprojection = None
+        if m in (Method.NEAREST_NEIGHBOR, Method.BILINEAR, Method.BICUBIC):
+            self._by_projection_parameters(m, proj_input, out_x, out_y, out_x_axis_unit, out_y_axis_unit)
+        elif m in (Method.COORD_NN, Method.COORD_NN_KD):
+            self._by_coordinates(m, proj_input, out_x, out_y, out_x_axis_unit, out_y_axis_unit)
+        elif Method.FORWARD_SUM <= m <= Method.FORWARD_UNDEF_MIN:
+            self._by_forward_interpolation(m, proj_input, out_x, out_y, out_x_axis_unit, out_y_axis_unit)
+        else:
+            raise FimexB200Error(f"unknown projection method: {m}")
+        self.method = Method(m)
+        return self
+
+    def _by_projection_parameters(self, method, proj_input, out_x, out_y, xunit, yunit):
+        # :1440-1503
+        x_deg = bool(_DEGREE.match(xunit))
+        y_deg = bool(_DEGREE.match(yunit))
+        ci = CachedInterpolation.fromProjection(method, proj_input, out_x, out_y, x_deg, y_deg, self.source_proj4, self.x_axis, self.y_axis,
+                                                self.is_degree, self.x_dim, self.y_dim)
+        ci.createReducedDomain(self.x_dim, self.y_dim)  # :1483-1485 (vector pairs share the horizontal id here)
+        self.cachedInterpolation = ci
+        if self.has_xy_vectors:  # :1490-1500; note the ORIGINAL (unconverted) axes and their types go in
+            xt = capi.LONGITUDE if x_deg else capi.PROJ_AXIS
+            yt = capi.LATITUDE if y_deg else capi.PROJ_AXIS
+            self.cachedVectorReprojection = CachedVectorReprojection.fromProjection(capi.MIFI_VECTOR_KEEP_SIZE, self.source_proj4, proj_input,
+                                                                                    out_x, out_y, xt, yt)
+
+    def _source_lonlat(self):
+        if self.lon2d is not None and self.lat2d is not None:
+            return self.lon2d, self.lat2d
+        if self.is_degree and "ob_tran" not in self.source_proj4:
+            return lon_lat_vals_to_matrix(self.x_axis, self.y_axis)  # latLonProj branch, :1376-1380
+        raise FimexB200Error("coordinate-based interpolation needs 2-D longitude/latitude of the source grid")
+
+    def _by_coordinates(self, method, proj_input, out_x, out_y, xunit, yunit):
+        # :1336-1420
+        if method != Method.COORD_NN:
+            raise FimexB200Error("coord_kdtree is not part of this path; use coord_nearestneighbor")
+        lon2d, lat2d = self._source_lonlat()
+        self.cachedInterpolation = CachedInterpolation.fromCoordinates(method, proj_input, out_x, out_y, bool(_DEGREE.match(xunit)),
+                                                                       bool(_DEGREE.match(yunit)), lon2d, lat2d, self.x_axis.size,
+                                                                       self.y_axis.size, self.x_dim, self.y_dim)
+        # no reduced domain, no vector rotation on this path (:1417-1419)
+
+    def _by_forward_interpolation(self, method, proj_input, out_x, out_y, xunit, yunit):
+        # :1242-1334
+        lon2d, lat2d = self._source_lonlat()
+        self.cachedInterpolation = CachedForwardInterpolation.fromCoordinates(method, proj_input, out_x, out_y, bool(_DEGREE.match(xunit)),
+                                                                              bool(_DEGREE.match(yunit)), lon2d, lat2d, self.x_axis.size,
+                                                                              self.y_axis.size, self.x_dim, self.y_dim)
+
+    # ---- per slice ------------------------------------------------------------------------------
+    def getDataSlice(self, data, bad_value=np.nan, counterpart=None, direction="x", out_dtype=None):
+        """CDMInterpolator::getDataSlice for an in-memory slice [.., y, x] of the FULL source grid (:235-287):
+        crop to the reduced domain, fill -> NaN, interpolate, [rotate with the counterpart component], NaN -> fill
+        and cast back to the variable's type."""
+        ci = self.cachedInterpolation
+        if ci is None:
+            raise FimexB200Error("no cached interpolation: call changeProjection first")
+        data = np.asarray(data)
+        dtype = np.dtype(out_dtype) if out_dtype is not None else data.dtype
+        lead = data.shape[:-2]
+        arr = self._to_interpolation_array(ci.getInputDataSlice(data), bad_value)
+        if counterpart is not None and self.cachedVectorReprojection is not None:
+            other = self._to_interpolation_array(ci.getInputDataSlice(np.asarray(counterpart)), bad_value)
+            if "x" in direction:
+                out, _ = ci.interpolateVector(arr, other, self.cachedVectorReprojection)
+            elif "y" in direction:
+                _, out = ci.interpolateVector(other, arr, self.cachedVectorReprojection)
+            else:
+                raise FimexB200Error(f"could not find x,y direction for vector, direction: {direction}")
+        else:
+            out = ci.interpolateValues(arr)
+        out = self._from_interpolation_array(out, dtype, bad_value)
+        return out.reshape(lead + (ci.getOutY(), ci.getOutX()))
+
+    @staticmethod
+    def _to_interpolation_array(data, bad_value):
+        # data2InterpolationArray (:115-119): asFloat() then mifi_bad2nanf
+        arr = np.ascontiguousarray(data, dtype=np.float32)
+        if bad_value is not None and not np.isnan(bad_value):
+            arr = capi.mifi_bad2nanf(arr, np.float32(bad_value)).reshape(arr.shape)
+        return arr
+
+    @staticmethod
+    def _from_interpolation_array(out, dtype, bad_value):
+        # interpolationArray2Data (:121-124): NaN -> badValue, scale 1 / offset 0, cast (round for integer types)
+        if dtype == np.float32:
+            if bad_value is not None and not np.isnan(bad_value):
+                out = capi.mifi_nanf2bad(out, np.float32(bad_value)).reshape(out.shape)
+            return out
+        # other variable types need the fused NaN->fill + round + cast store; doing that
+        # arithmetic in numpy here would be a CPU path, so it is refused until the device kernel exists
+        raise FimexB200Error(f"output type {dtype} not supported yet on the device path (float32 only)")

@@ -357,13 +357,23 @@ class Reference(_Base):
     def available():
         return os.path.exists(REF_SO)
 
-    def cached_interpolate(self, method, px, py, inX, inY, outX, outY, indata, nthreads=1):
-        """The reference kernels driven by a Python restatement of CachedInterpolation.cc:118-147
-        (point by point; for small parity cases only)."""
-        a = np.ascontiguousarray(indata, dtype=np.float32)
+    def cached_interpolate(self, method, px, py, inX, inY, outX, outY, indata, nthreads=0, out=None):
+        """The reference's own kernels (mifi_get_values_*_f) inside the restated CachedInterpolation.cc:118-147
+        loop of oracle/ref_driver.c (OpenMP over target points, like the reference)."""
+        pxa, pxp = _d(px)
+        pya, pyp = _d(py)
+        a, ap = _f(indata)
         inZ = a.size // (inX * inY)
-        out = np.empty((inZ, outY * outX), dtype=np.float32)
-        m = {COORD_NN: NEAREST_NEIGHBOR, COORD_NN_KD: NEAREST_NEIGHBOR}.get(method, method)
-        for i in range(outX * outY):
-            out[:, i] = self.get_values(m, a, px[i], py[i], inX, inY, inZ)
+        if out is None:
+            out = np.empty(inZ * outX * outY, dtype=np.float32)
+        f = self.lib.ref_cached_interpolate
+        f.restype = C.c_int
+        f.argtypes = [C.c_int, _dp, _dp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, _fp, C.c_size_t, _fp, C.c_int]
+        rc = f(int(method), pxp, pyp, inX, inY, outX, outY, ap, a.size, out.ctypes.data_as(_fp), nthreads)
+        if rc != MIFI_OK:
+            raise RuntimeError("ref_cached_interpolate failed")
         return out.reshape(inZ, outY, outX)
+
+    def max_threads(self):
+        self.lib.ref_max_threads.restype = C.c_int
+        return self.lib.ref_max_threads()

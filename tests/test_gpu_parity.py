@@ -1,0 +1,582 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the CPU oracle and the golden
+vectors produced by the compiled reference.  Run on the B200 box with `pytest -m gpu`.
+
+Bars (BASELINE.json north_star): bit-exact for nearest-neighbour indices, copied values and fill masks; bit-exact
+as well for bilinear / bicubic / rotation here, because the kernels replay the reference's operation order
+without FMA contraction (the stated bar is 1e-5 relative); <= 1e-9 degree for fp64 coordinate transforms.
+"""
+import numpy as np
+import pytest
+
+from conftest import assert_bit_equal
+
+pytestmark = pytest.mark.gpu
+
+import fimex_b200 as fb  # noqa: E402
+from fimex_b200 import Method  # noqa: E402
+
+EMEP = "+ellps=sphere +a=127.4 +e=0 +proj=stere +lat_0=90 +lon_0=-32 +lat_ts=60 +x_0=7 +y_0=109"
+LATLONG = "+ellps=sphere +a=6370 +e=0 +proj=latlong"
+SRC_LL = "+proj=latlong +a=6371000 +e=0 +no_defs"
+ROTPOLE = "+proj=ob_tran +o_proj=longlat +lon_0=-40 +o_lat_p=22 +R=6.371e+06 +no_defs"
+STERE = "+proj=stere +lat_0=90 +lon_0=0 +lat_ts=60 +a=6371000 +e=0"
+LCC = "+proj=lcc +lat_0=63 +lon_0=15 +lat_1=63 +lat_2=63 +no_defs +R=6.371e+06"
+WGS84 = "+proj=latlong +datum=WGS84 +towgs84=0,0,0 +no_defs"
+DEG = np.pi / 180
+TOL_RAD = 1e-9 * DEG  # 1e-9 degree
+
+
+# =====================================================================================================
+# the reference's known-answer tests, through the drop-in mifi_* symbols (test/testInterpolation.cc)
+# =====================================================================================================
+def test_mifi_points2position():
+    # :49-58 and :61-70
+    rc, p = fb.mifi_points2position([-3.0, 5.0, 1.3, 2.0, 6.0], [1.0, 2, 3, 4, 5], fb.PROJ_AXIS)
+    assert rc == fb.MIFI_OK and np.allclose(p, [-4.0, 4.0, 0.3, 1.0, 5.0], atol=1e-10, rtol=0)
+    rc, p = fb.mifi_points2position([-3.0, 5.0, 1.3, 2.0, 6.0], [5.0, 4, 3, 2, 1], fb.PROJ_AXIS)
+    assert rc == fb.MIFI_OK and np.allclose(p, [8.0, 0.0, 3.7, 3.0, -1.0], atol=1e-10, rtol=0)
+
+
+def test_mifi_get_values_f():
+    # :73-80
+    rc, out = fb.mifi_get_values_f([1.0, 2.0, 1.0, 2.0], 0.3, 0.3, 2, 2, 1)
+    assert rc == fb.MIFI_OK and out[0] == 1.0
+
+
+def test_mifi_get_values_bilinear_f():
+    # :83-112
+    f = np.array([1.0, 2.0, 2.0, 1 + np.sqrt(np.float32(2.0))], dtype=np.float32)
+    g = lambda x, y: float(fb.mifi_get_values_bilinear_f(f, x, y, 2, 2, 1)[1][0])
+    assert abs(g(0.3, 0.0) - 1.3) < 1e-6 and abs(g(0.3, 0.0001) - 1.3) < 1e-4
+    assert abs(g(0.0, 0.3) - 1.3) < 1e-6 and abs(g(0.0001, 0.3) - 1.3) < 1e-4
+    assert not np.isnan(g(0, 0)) and not np.isnan(g(1, 1))
+    for x, y in ((1.5, 0.5), (0.5, 1.5), (0.5, -0.5), (-0.5, 0.5)):
+        assert np.isnan(g(x, y))
+
+
+def test_mifi_get_values_bicubic_f():
+    # :115-155
+    f = np.array([1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1], dtype=np.float32)
+    ft = f.reshape(4, 4).T.copy().ravel()
+    g = lambda a, x, y: float(fb.mifi_get_values_bicubic_f(a, x, y, 4, 4, 1)[1][0])
+    for a, x, y, want in ((f, 1, 1, 2.0), (f, 1, 1.99999, 2.0), (f, 1, 1.5, 2.125), (f, 1.5, 1, 2.0), (ft, 1, 1, 2.0), (ft, 1.99999, 1, 2.0),
+                          (ft, 1.5, 1, 2.125), (ft, 1, 1.5, 2.0)):
+        assert g(a, x, y) == pytest.approx(want, rel=1e-5)
+    for x, y in ((0.5, 1), (1, 0.5), (2.5, 1), (1, 2.5)):
+        assert np.isnan(g(f, x, y))
+
+
+def test_mifi_project_axes_emep():
+    # :265-278
+    rc, x, y = fb.mifi_project_axes(EMEP, LATLONG, [6.0, 7, 8], [108.0, 109, 110])
+    assert rc == fb.MIFI_OK and np.all(y / DEG > 89)
+    assert y[4] / DEG == pytest.approx(90.0, abs=1e-9)
+
+
+def test_mifi_interpolate_f_emep(golden):
+    # :280-393; the golden fields come from the compiled reference (projection evaluated with glibc there, with the
+    # CUDA math library here: positions may differ in the last ulp, so allow a handful of half-cell flips)
+    g = golden("emep")
+    for name, m in (("nn", Method.NEAREST_NEIGHBOR), ("bilinear", Method.BILINEAR), ("bicubic", Method.BICUBIC)):
+        rc, out = fb.mifi_interpolate_f(m, EMEP, g["infield"], np.arange(170) + 1.0, np.arange(150) + 1.0, fb.PROJ_AXIS, fb.PROJ_AXIS, 1,
+                                        LATLONG, g["lon"], g["lat"], fb.LONGITUDE, fb.LATITUDE)
+        assert rc == fb.MIFI_OK
+        assert abs(out[0, 25, 9] - 32) < 1e-6
+        want = g[name]
+        assert np.array_equal(np.isnan(out), np.isnan(want)) or (np.isnan(out) != np.isnan(want)).sum() <= 3
+        both = ~np.isnan(out) & ~np.isnan(want)
+        differing = (out[both] != want[both]).sum()
+        assert differing <= 0.002 * both.sum(), (name, differing)
+
+
+@pytest.mark.parametrize("lon0,tol", [(90, 1e-4), (180, 1e-5)])
+def test_mifi_vector_reproject_values_rotate(lon0, tol):
+    # :396-453 and :455-512
+    a = "+ellps=sphere +a=127.4 +e=0 +proj=stere +lat_0=90 +lon_0=0 +lat_ts=60"
+    b = f"+ellps=sphere +a=127.4 +e=0 +proj=stere +lat_0=90 +lon_0={lon0} +lat_ts=60"
+    ax = np.arange(5) - 2.0
+    u = np.arange(25, dtype=np.float32)
+    v = 25 - np.arange(25, dtype=np.float32)
+    _, uo = fb.mifi_interpolate_f(0, a, u, ax, ax, 0, 0, 1, b, ax, ax, 0, 0)
+    _, vo = fb.mifi_interpolate_f(0, a, v, ax, ax, 0, 0, 1, b, ax, ax, 0, 0)
+    rc, ur, vr = fb.mifi_vector_reproject_values_f(fb.MIFI_VECTOR_KEEP_SIZE, a, b, uo, vo, ax, ax, 0, 0, 1)
+    assert rc == fb.MIFI_OK
+    uo, vo, ur, vr = uo.ravel(), vo.ravel(), ur.ravel(), vr.ravel()
+    if lon0 == 90:
+        assert np.all(np.abs(vo - ur) < tol) and np.all(np.abs(uo + vr) < tol)
+    else:
+        assert np.all(np.abs(vo + vr) < tol) and np.all(np.abs(uo + ur) < tol)
+
+
+def test_mifi_vector_reproject_keep_size_and_directions():
+    # :515-583
+    ai, aj = np.arange(4) + 6.0, np.arange(4) + 108.0
+    lon, lat = np.arange(4) * 60.0, np.arange(4) / 2.0 + 88.5
+    u = np.arange(16, dtype=np.float32)
+    v = -16 + np.arange(16, dtype=np.float32)
+    _, uo = fb.mifi_interpolate_f(0, EMEP, u, ai, aj, 0, 0, 1, LATLONG, lon, lat, fb.LONGITUDE, fb.LATITUDE)
+    _, vo = fb.mifi_interpolate_f(0, EMEP, v, ai, aj, 0, 0, 1, LATLONG, lon, lat, fb.LONGITUDE, fb.LATITUDE)
+    rc, ur, vr = fb.mifi_vector_reproject_values_f(0, EMEP, LATLONG, uo, vo, lon, lat, fb.LONGITUDE, fb.LATITUDE, 1)
+    assert rc == fb.MIFI_OK
+    d = ur.ravel().astype(np.float64)**2 + vr.ravel().astype(np.float64)**2 - uo.ravel().astype(np.float64)**2 - vo.ravel().astype(np.float64)**2
+    d = d[~np.isnan(d)]
+    assert d.size > 0 and np.all(np.abs(d) < 1e-3)
+    # :586-654
+    a = "+ellps=sphere +a=127.4 +e=0 +proj=stere +lat_0=90 +lon_0=0 +lat_ts=60"
+    ax = (np.arange(5) - 2) * 1000.0
+    xf, yf = np.meshgrid(ax, ax)
+    rc, m = fb.mifi_get_vector_reproject_matrix_field(a, LATLONG, xf.ravel(), yf.ravel(), 5, 5)
+    assert rc == fb.MIFI_OK
+    rc, ang = fb.mifi_vector_reproject_direction_by_matrix_f(0, m, np.zeros(25, dtype=np.float32), 5, 5, 1)
+    close = lambda want, got: abs(got - want) <= 0.01 * max(abs(want), abs(got))
+    assert close(315, ang[0]) and close(270, ang[10]) and close(225, ang[20])
+    assert close(180, ang[2 + 15]) and close(180, ang[2 + 20])
+    assert close(45, ang[4]) and close(90, ang[4 + 10]) and close(135, ang[4 + 20])
+
+
+# =====================================================================================================
+# golden vectors from the compiled reference: identical inputs => identical bits
+# =====================================================================================================
+def test_golden_kernels_bit_exact(golden):
+    g = golden("kernels")
+    field, px, py = g["field"], g["px"], g["py"]
+    iz, iy, ix = field.shape
+    n = px.size
+    for name, m in (("nn", Method.NEAREST_NEIGHBOR), ("bilinear", Method.BILINEAR), ("bicubic", Method.BICUBIC)):
+        ci = fb.CachedInterpolation("x", "y", m, px, py, ix, iy, n, 1)
+        out = ci.interpolateValues(field).reshape(iz, n)
+        assert_bit_equal(out, g[name], f"{name} vs compiled reference")
+
+
+def test_golden_points2position_bit_exact(golden):
+    g = golden("points2position")
+    for k in ("asc", "desc", "lon360", "lon180", "lon_regional", "lon_desc", "lat_desc", "nonuniform", "metric"):
+        rc, got = fb.mifi_points2position(g[k + "_in"], g[k + "_axis"], int(g[k + "_type"]))
+        assert rc == fb.MIFI_OK
+        assert np.array_equal(got.view(np.uint64), g[k + "_out"].view(np.uint64)), k
+
+
+def test_golden_projections_within_1e9_degree(golden):
+    g = golden("projections")
+    cases = {
+        "rot_to_ll": (ROTPOLE, SRC_LL, True), "stere_to_ll": (STERE, SRC_LL, True), "lcc_to_ll": (LCC, SRC_LL, True),
+        "lcc_to_wgs84": (LCC, WGS84, True), "emep_to_ll": (EMEP, LATLONG, True), "ll_to_rot": (SRC_LL, ROTPOLE, True),
+        "ll_to_stere": (SRC_LL, STERE, False), "ll_to_lcc": (SRC_LL, LCC, False), "rot_to_stere": (ROTPOLE, STERE, False),
+    }
+    for k, (pin, pout, angular) in cases.items():
+        rc, xo, yo = fb.mifi_project_axes(pin, pout, g[k + "_xa"], g[k + "_ya"])
+        assert rc == fb.MIFI_OK, k
+        wx, wy = g[k + "_xo"], g[k + "_yo"]
+        finite = np.isfinite(wx) & np.isfinite(wy)
+        assert np.array_equal(finite, np.isfinite(xo) & np.isfinite(yo)), k
+        tol = TOL_RAD if angular else TOL_RAD * 6371000.0  # 1e-9 degree of arc
+        dx = np.abs(xo[finite] - wx[finite])
+        if angular:
+            dx = np.minimum(dx, np.abs(dx - 2 * np.pi))
+        assert dx.max() <= tol and np.abs(yo[finite] - wy[finite]).max() <= tol, (k, dx.max())
+
+
+def test_golden_vector_rotation(golden):
+    g = golden("vectors")
+    cases = {"ll_rot": (SRC_LL, ROTPOLE, fb.LONGITUDE, fb.LATITUDE), "ll_stere": (SRC_LL, STERE, 0, 0), "ll_lcc": (SRC_LL, LCC, 0, 0),
+             "stere_ll": (STERE, SRC_LL, fb.LONGITUDE, fb.LATITUDE), "rot_stere": (ROTPOLE, STERE, 0, 0)}
+    for k, (pin, pout, xt, yt) in cases.items():
+        m, u, v = g[k + "_m"], g[k + "_u"], g[k + "_v"]
+        oz, oy, ox = u.shape
+        # rotation with the reference's matrix: bit-exact
+        rc, ur, vr = fb.mifi_vector_reproject_values_by_matrix_f(0, m, u, v, ox, oy, oz)
+        assert rc == fb.MIFI_OK
+        assert_bit_equal(ur.reshape(u.shape), g[k + "_ur"], k + " u")
+        assert_bit_equal(vr.reshape(v.shape), g[k + "_vr"], k + " v")
+        cvr = fb.CachedVectorReprojection(fb.MIFI_VECTOR_KEEP_SIZE, m, ox, oy)
+        u2, v2 = u.copy(), v.copy()
+        cvr.reprojectValues(u2, v2)
+        assert_bit_equal(u2, g[k + "_ur"], k + " u (class)")
+        # matrix built on the device: angle within 1e-9 degree of the reference's
+        rc, m2 = fb.mifi_get_vector_reproject_matrix(pin, pout, g[k + "_xa"], g[k + "_ya"], xt, yt)
+        assert rc == fb.MIFI_OK
+        dphi = np.abs(m2[3::4] - m[3::4])
+        assert dphi.max() <= 1e-7 * DEG, (k, dphi.max())  # angle from differences of 1e-3-cell steps: conditioned ~1e2
+        assert np.abs(m2[0::4] - m[0::4]).max() < 1e-9 and np.abs(m2[1::4] - m[1::4]).max() < 1e-9
+        assert np.array_equal(m2[2::4], -m2[1::4])
+
+
+# =====================================================================================================
+# seeded random parity against the oracle: CachedInterpolation (A3-A8)
+# =====================================================================================================
+def _random_case(seed, inX, inY, inZ, outX, outY, nan_frac=0.02, spill=1.5):
+    rng = np.random.default_rng(seed)
+    field = rng.normal(250, 30, (inZ, inY, inX)).astype(np.float32)
+    field[rng.random(field.shape) < nan_frac] = np.nan
+    n = outX * outY
+    px = rng.uniform(-spill, inX - 1 + spill, n)
+    py = rng.uniform(-spill, inY - 1 + spill, n)
+    k = n // 10
+    px[:k] = np.round(px[:k] * 2) / 2
+    py[k // 2:k + k // 2] = np.round(py[k // 2:k + k // 2] * 2) / 2
+    px[-3:] = [-999.0, 0.0, inX - 1.0]
+    py[-3:] = [-999.0, inY - 1.0, 0.0]
+    return field, px, py
+
+
+def _mask_ub(oracle, method, px, py, inX, inY, out):
+    """positions where the reference itself reads out of bounds (interpolation.c:936) are NaN on both sides"""
+    if method != Method.BILINEAR:
+        return 0
+    ub = np.array([oracle.bilinear_is_ub(a, b, inX, inY) for a, b in zip(px, py)])
+    return int(ub.sum())
+
+
+@pytest.mark.parametrize("method", [Method.NEAREST_NEIGHBOR, Method.BILINEAR, Method.BICUBIC])
+@pytest.mark.parametrize("shape", [(37, 23, 3, 40, 25), (64, 48, 5, 101, 7), (9, 7, 70, 33, 4), (200, 150, 2, 256, 128), (2, 2, 1, 5, 5)])
+def test_cached_interpolation_bit_exact(oracle, method, shape):
+    inX, inY, inZ, outX, outY = shape
+    field, px, py = _random_case(hash(shape) % 10000 + int(method), inX, inY, inZ, outX, outY)
+    want = oracle.cached_interpolate(int(method), px, py, inX, inY, outX, outY, field)
+    ci = fb.CachedInterpolation("x", "y", method, px, py, inX, inY, outX, outY)
+    assert (ci.getInX(), ci.getInY(), ci.getOutX(), ci.getOutY()) == (inX, inY, outX, outY)
+    got = ci.interpolateValues(field)
+    assert got.shape == (inZ, outY, outX)
+    assert_bit_equal(got, want, f"method {method} shape {shape}")
+    _mask_ub(oracle, method, px, py, inX, inY, got)
+
+
+def test_cached_interpolation_device_path_equals_host_path(oracle):
+    import torch
+    inX, inY, inZ, outX, outY = 120, 90, 40, 300, 200  # 60000 points: the 128-bit store path; 40 levels
+    field, px, py = _random_case(5, inX, inY, inZ, outX, outY)
+    for method in (Method.NEAREST_NEIGHBOR, Method.BILINEAR, Method.BICUBIC, Method.COORD_NN):
+        ci = fb.CachedInterpolation("x", "y", method, px, py, inX, inY, outX, outY)
+        host = ci.interpolateValues(field)
+        dev = ci.interpolateValues(torch.from_numpy(field).cuda())
+        torch.cuda.synchronize()
+        assert_bit_equal(dev.cpu().numpy(), host, f"device vs host path, method {method}")
+        want = oracle.cached_interpolate(int(method), px, py, inX, inY, outX, outY, field)
+        assert_bit_equal(host, want, f"oracle, method {method}")
+
+
+def test_reduced_domain_matches_oracle(oracle):
+    inX, inY, inZ, outX, outY = 300, 200, 3, 64, 48
+    rng = np.random.default_rng(11)
+    px = rng.uniform(100.3, 140.7, outX * outY)
+    py = rng.uniform(50.2, 77.9, outX * outY)
+    field = rng.normal(0, 1, (inZ, inY, inX)).astype(np.float32)
+    red, opx, opy, oinX, oinY, ominX, ominY = oracle.reduced_domain(px, py, inX, inY)
+    assert red
+    for method in (Method.BILINEAR, Method.BICUBIC, Method.NEAREST_NEIGHBOR):
+        ci = fb.CachedInterpolation("x", "y", method, px, py, inX, inY, outX, outY)
+        assert ci.createReducedDomain()
+        assert (ci.getInX(), ci.getInY()) == (oinX, oinY)
+        assert ci.reducedDomain()[2:4] == (ominX, ominY)
+        gx, gy = ci.points()
+        assert np.array_equal(gx.view(np.uint64), opx.view(np.uint64)) and np.array_equal(gy.view(np.uint64), opy.view(np.uint64))
+        cropped = ci.getInputDataSlice(field)
+        assert cropped.shape == (inZ, oinY, oinX)
+        want = oracle.cached_interpolate(int(method), opx, opy, oinX, oinY, outX, outY, cropped)
+        assert_bit_equal(ci.interpolateValues(cropped), want, f"cropped, method {method}")
+        # and the crop changes nothing: same values as on the full grid
+        full = oracle.cached_interpolate(int(method), px, py, inX, inY, outX, outY, field)
+        assert_bit_equal(want, full, "crop invariance (oracle)")
+        assert not ci.createReducedDomain() or ci.reducedDomain()[2:4] == (ominX, ominY)  # "don't set twice"
+    # degenerate: all positions in one cell column -> (maxX - minX) >= 1 still holds because of EXTEND; a 1-wide grid does not reduce
+    ci = fb.CachedInterpolation("x", "y", Method.BILINEAR, np.zeros(4), np.zeros(4), 1, 1, 2, 2)
+    assert not ci.createReducedDomain()
+
+
+def test_edge_cases(oracle):
+    # empty slice (inZ == 0), a single target point, everything outside, ragged level sizes
+    ci = fb.CachedInterpolation("x", "y", Method.BILINEAR, [0.5], [0.5], 2, 2, 1, 1)
+    out = ci.interpolateValues(np.zeros(0, dtype=np.float32))
+    assert out.size == 0
+    out = ci.interpolateValues(np.array([1, 2, 3, 4], dtype=np.float32))
+    assert out.shape == (1, 1, 1) and out[0, 0, 0] == 2.5
+    # size not a multiple of inX*inY: the remainder is ignored like the reference's integer division
+    out = ci.interpolateValues(np.array([1, 2, 3, 4, 9, 9], dtype=np.float32))
+    assert out.shape == (1, 1, 1)
+    ci = fb.CachedInterpolation("x", "y", Method.NEAREST_NEIGHBOR, np.full(7, -999.0), np.full(7, -999.0), 3, 3, 7, 1)
+    out = ci.interpolateValues(np.arange(18, dtype=np.float32))
+    assert out.shape == (2, 1, 7) and np.all(out.view(np.uint32) == 0x7fc00000)  # canonical quiet NaN fill mask
+    # NaN taps poison the result even with zero weight (SURVEY trap 1); inf arithmetic like the reference
+    f = np.array([1, np.nan, 3, 4, np.inf, 1, 1, 1], dtype=np.float32)
+    px, py = np.array([0.0, 0.25]), np.array([0.0, 0.5])
+    ci = fb.CachedInterpolation("x", "y", Method.BILINEAR, px, py, 2, 2, 2, 1)
+    got = ci.interpolateValues(f)
+    want = oracle.cached_interpolate(1, px, py, 2, 2, 2, 1, f)
+    assert_bit_equal(got, want, "NaN/inf taps")
+    assert np.isnan(got[0, 0, 0])
+    # unknown method / wrong table size
+    with pytest.raises(fb.FimexB200Error):
+        fb.CachedInterpolation("x", "y", 99, [0.0], [0.0], 2, 2, 1, 1)
+    with pytest.raises(fb.FimexB200Error):
+        fb.CachedInterpolation("x", "y", Method.FORWARD_MEAN, [0.0], [0.0], 2, 2, 1, 1)
+
+
+def test_seam_and_border_traps(oracle):
+    # SURVEY traps 2, 3, 5: lround ties, half-cell strips, no wrap across the longitude seam
+    lon = np.radians(np.arange(1440) * 0.25)
+    pts = np.radians(np.array([-0.1, 359.9, 359.75, 0.0, 179.99, -179.9, 360.1]))
+    rc, pos = fb.mifi_points2position(pts, lon, fb.LONGITUDE)
+    want = oracle.points2position(pts, lon, 1)
+    assert np.array_equal(pos.view(np.uint64), want.view(np.uint64))
+    assert pos[0] == pytest.approx(-0.4, abs=1e-9)  # probe quoted in SURVEY.md 8a trap 5
+    field = np.arange(4 * 1440, dtype=np.float32).reshape(1, 4, 1440)
+    py = np.full(pos.size, 1.5)
+    for m in (Method.NEAREST_NEIGHBOR, Method.BILINEAR, Method.BICUBIC):
+        ci = fb.CachedInterpolation("x", "y", m, pos, py, 1440, 4, pos.size, 1)
+        assert_bit_equal(ci.interpolateValues(field), oracle.cached_interpolate(int(m), pos, py, 1440, 4, pos.size, 1, field), f"seam {m}")
+
+
+# =====================================================================================================
+# fused u/v interpolation + rotation (A13, A14) and the matrix (A15)
+# =====================================================================================================
+@pytest.mark.parametrize("method", [Method.NEAREST_NEIGHBOR, Method.BILINEAR, Method.BICUBIC])
+@pytest.mark.parametrize("outX,outY", [(33, 9), (64, 32)])
+def test_fused_vector_bit_exact(oracle, method, outX, outY):
+    inX, inY, inZ = 50, 40, 6
+    rng = np.random.default_rng(int(method) + outX)
+    u, px, py = _random_case(21, inX, inY, inZ, outX, outY)
+    v = rng.normal(0, 8, u.shape).astype(np.float32)
+    phi = rng.uniform(-np.pi, np.pi, outX * outY)
+    matrix = np.stack([np.cos(phi), np.sin(phi), -np.sin(phi), phi], axis=1).ravel()
+    ui = oracle.cached_interpolate(int(method), px, py, inX, inY, outX, outY, u)
+    vi = oracle.cached_interpolate(int(method), px, py, inX, inY, outX, outY, v)
+    wu, wv = oracle.vector_reproject_by_matrix(matrix, ui, vi, outX, outY, inZ)
+    ci = fb.CachedInterpolation("x", "y", method, px, py, inX, inY, outX, outY)
+    cvr = fb.CachedVectorReprojection(fb.MIFI_VECTOR_KEEP_SIZE, matrix, outX, outY)
+    gu, gv = ci.interpolateVector(u, v, cvr)
+    assert_bit_equal(gu, wu.reshape(gu.shape), "fused u")
+    assert_bit_equal(gv, wv.reshape(gv.shape), "fused v")
+    # un-fused: interpolateValues twice + reprojectValues, as the reference host does (CDMInterpolator.cc:255-276)
+    a, b = ci.interpolateValues(u).copy(), ci.interpolateValues(v).copy()
+    cvr.reprojectValues(a, b)
+    assert_bit_equal(a, gu, "un-fused u")
+    assert_bit_equal(b, gv, "un-fused v")
+    # no rotation handle: plain interpolation of both
+    pu, pv = ci.interpolateVector(u, v, None)
+    assert_bit_equal(pu, ui, "no-rotation u")
+    assert_bit_equal(pv, vi, "no-rotation v")
+    assert np.array_equal(cvr.getMatrix().view(np.uint64), matrix.view(np.uint64))
+
+
+def test_uninitialised_vector_reprojection_is_identity():
+    # CachedVectorReprojection.cc:37-40
+    cvr = fb.CachedVectorReprojection()
+    u = np.arange(6, dtype=np.float32)
+    v = np.arange(6, dtype=np.float32)[::-1].copy()
+    cvr.reprojectValues(u, v)
+    assert np.array_equal(u, np.arange(6)) and np.array_equal(v, np.arange(6)[::-1])
+
+
+@pytest.mark.parametrize("target,axes,types", [
+    (ROTPOLE, (np.linspace(-10, 10, 41), np.linspace(-8, 8, 33)), (1, 2)),
+    (STERE, (np.linspace(-2e6, 2e6, 41), np.linspace(-2e6, 2e6, 33)), (0, 0)),
+    (LCC, (np.linspace(-1e6, 1e6, 41), np.linspace(-2e6, 2e6, 33)), (0, 0)),
+])
+def test_vector_matrix_against_oracle(oracle, target, axes, types):
+    rc, want = oracle.vector_matrix(SRC_LL, target, axes[0], axes[1], types[0], types[1])
+    assert rc == 1
+    rc, got = fb.mifi_get_vector_reproject_matrix(SRC_LL, target, axes[0], axes[1], types[0], types[1])
+    assert rc == fb.MIFI_OK
+    assert np.abs(got[3::4] - want[3::4]).max() <= 1e-7 * DEG
+    assert np.abs(got[0::4]**2 + got[1::4]**2 - 1).max() < 1e-14
+    cvr = fb.CachedVectorReprojection.fromProjection(0, SRC_LL, target, axes[0], axes[1], types[0], types[1])
+    assert np.array_equal(cvr.getMatrix().view(np.uint64), got.view(np.uint64))
+
+
+# =====================================================================================================
+# forward interpolation (A16, A17)
+# =====================================================================================================
+@pytest.mark.parametrize("method", [Method.FORWARD_MEAN, Method.FORWARD_MAX, Method.FORWARD_SUM, Method.FORWARD_MIN, Method.FORWARD_MEDIAN,
+                                    Method.FORWARD_UNDEF_MEAN, Method.FORWARD_UNDEF_MAX, Method.FORWARD_UNDEF_SUM, Method.FORWARD_UNDEF_MIN])
+@pytest.mark.parametrize("dense", [False, True])
+def test_forward_bit_exact(oracle, method, dense):
+    rng = np.random.default_rng(int(method) * 2 + dense)
+    inX, inY, inZ = 211, 57, 3
+    outX, outY = (19, 13) if dense else (160, 90)  # dense: ~50 points per cell; sparse: many empty cells
+    n = inX * inY
+    px = rng.uniform(-2, outX + 1, n)
+    py = rng.uniform(-2, outY + 1, n)
+    px[:50] = np.round(px[:50] * 2) / 2  # x.5 ties: round() goes away from zero
+    px[50:60] = np.nan
+    py[60:70] = -999.0
+    data = rng.normal(10, 5, (inZ, inY, inX)).astype(np.float32)
+    data[rng.random(data.shape) < 0.05] = np.nan
+    want = oracle.forward_interpolate(int(method), px, py, inX, inY, outX, outY, data)
+    cfi = fb.CachedForwardInterpolation("x", "y", method, px, py, inX, inY, outX, outY)
+    got = cfi.interpolateValues(data)
+    if method in (Method.FORWARD_UNDEF_MAX, Method.FORWARD_UNDEF_MIN):
+        # NaN payload/sign may differ where the aggregate is NaN; compare the mask and the numbers
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        assert np.array_equal(got[~np.isnan(got)], want[~np.isnan(want)])
+    else:
+        assert_bit_equal(got, want, f"forward method {method} dense={dense}")
+    assert np.isnan(got).any() or dense
+
+
+def test_forward_from_coordinates_against_oracle(oracle):
+    # the table-producing part of changeProjectionByForwardInterpolation + the scatter, swath-like input
+    rng = np.random.default_rng(3)
+    ny, nx = 120, 80
+    lat = 60 + np.linspace(0, 4, ny)[:, None] + np.linspace(0, 0.4, nx)[None, :]
+    lon = 10 + np.linspace(0, 1, ny)[:, None] + np.linspace(0, 6, nx)[None, :]
+    lat += rng.normal(0, 1e-3, lat.shape)
+    ox = np.arange(-200e3, 200e3 + 1, 5e3)
+    oy = np.arange(-350e3, 150e3 + 1, 5e3)
+    data = rng.normal(0, 1, (1, ny, nx)).astype(np.float32)
+    data[rng.random(data.shape) < 0.02] = np.nan
+    # oracle pipeline (CDMInterpolator.cc:1265-1317)
+    rc, x, y = oracle.project_values(WGS84, LCC, np.radians(lon.ravel()), np.radians(lat.ravel()))
+    assert rc == 1
+    x = oracle.points2position(x, ox, 0)
+    y = oracle.points2position(y, oy, 0)
+    for m in (Method.FORWARD_MEAN, Method.FORWARD_MAX):
+        want = oracle.forward_interpolate(int(m), x, y, nx, ny, ox.size, oy.size, data)
+        cfi = fb.CachedForwardInterpolation.fromCoordinates(m, LCC, ox, oy, False, False, lon.ravel(), lat.ravel(), nx, ny)
+        got = cfi.interpolateValues(data)
+        gx, gy = cfi.points()
+        assert np.abs(gx - x).max() < 1e-6 and np.abs(gy - y).max() < 1e-6  # cell units; 1e-9 deg ~ 2e-8 cells here
+        flips = (np.round(gx) != np.round(x)).sum() + (np.round(gy) != np.round(y)).sum()
+        if flips == 0:
+            assert_bit_equal(got, want, f"forward from coordinates {m}")
+        else:  # a point within 1e-6 of a cell edge moved: bounded, reported
+            assert flips <= 3 and (got.view(np.uint32) != want.view(np.uint32)).sum() <= 2 * flips
+
+
+# =====================================================================================================
+# table production on the device (A9, A10, A18, A19)
+# =====================================================================================================
+def _config2_like(n=200):
+    lon = np.arange(1440) * 0.25
+    lat = 90 - np.arange(721) * 0.25
+    ax = (np.arange(n) - (n - 1) / 2) * (45.0 / n)
+    return lon, lat, ax
+
+
+@pytest.mark.parametrize("method", [Method.NEAREST_NEIGHBOR, Method.BILINEAR, Method.BICUBIC])
+def test_from_projection_against_oracle(oracle, method):
+    lon, lat, ax = _config2_like(160)
+    # oracle pipeline: CDMInterpolator.cc:1446-1476 + createReducedDomain
+    rc, x, y = oracle.project_axes(ROTPOLE, SRC_LL, np.radians(ax), np.radians(ax))
+    assert rc == 1
+    px = oracle.points2position(x, np.radians(lon), 1)
+    py = oracle.points2position(y, np.radians(lat), 2)
+    red, opx, opy, inX, inY, x0, y0 = oracle.reduced_domain(px, py, 1440, 721)
+    assert red
+    ci = fb.CachedInterpolation.fromProjection(method, ROTPOLE, ax, ax, True, True, SRC_LL, lon, lat, True)
+    assert ci.createReducedDomain()
+    assert (ci.getInX(), ci.getInY()) == (inX, inY) and ci.reducedDomain()[2:4] == (x0, y0)
+    gx, gy = ci.points()
+    # 1e-9 degree on a 0.25-degree grid is 4e-9 cells
+    assert np.abs(gx - opx).max() <= 4e-9 and np.abs(gy - opy).max() <= 4e-9
+    rng = np.random.default_rng(2)
+    field = rng.normal(250, 30, (4, inY, inX)).astype(np.float32)
+    got = ci.interpolateValues(field)
+    # with the device's own positions the gather is bit-exact against the oracle ...
+    assert_bit_equal(got, oracle.cached_interpolate(int(method), gx, gy, inX, inY, ax.size, ax.size, field), "own positions")
+    # ... and against the oracle's positions only points within ~1e-9 cells of a cell/half-cell boundary may differ
+    want = oracle.cached_interpolate(int(method), opx, opy, inX, inY, ax.size, ax.size, field)
+    if method == Method.NEAREST_NEIGHBOR:
+        flips = (got[0] != want[0]).sum()
+        assert flips <= 2, flips
+    else:
+        rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-30)
+        assert np.nanmax(rel) <= 1e-5
+
+
+def test_coord_nearestneighbor_against_oracle(oracle):
+    lon = np.arange(0, 360, 1.5)
+    lat = 90 - np.arange(0, 180.1, 1.5)
+    ax = (np.arange(60) - 29.5) * 0.7
+    lon2d, lat2d = oracle.lonlat_to_matrix(np.radians(lon), np.radians(lat))
+    rc, tx, ty = oracle.project_axes(ROTPOLE, WGS84, np.radians(ax), np.radians(ax))
+    assert rc == 1
+    wx, wy, ties = oracle.coordnn(tx, ty, lon2d, lat2d, lon.size, lat.size)
+    ci = fb.CachedInterpolation.fromCoordinates(Method.COORD_NN, ROTPOLE, ax, ax, True, True, np.degrees(lon2d), np.degrees(lat2d), lon.size,
+                                                lat.size)
+    gx, gy = ci.points()
+    differ = ((gx != wx) | (gy != wy)).sum()
+    assert differ <= max(2, ties), (differ, ties)  # only (near-)equidistant candidates may resolve differently
+    assert (gx >= 0).all() and (gy >= 0).all()
+    field = np.random.default_rng(1).normal(0, 1, (2, lat.size, lon.size)).astype(np.float32)
+    got = ci.interpolateValues(field)
+    assert_bit_equal(got, oracle.cached_interpolate(3, gx, gy, lon.size, lat.size, ax.size, ax.size, field), "coord_nn gather")
+    # a target far from every source point gets (-1,-1) -> NaN (LL_POINT default, CDMInterpolator.cc:1134)
+    ci2 = fb.CachedInterpolation.fromCoordinates(Method.COORD_NN, SRC_LL, [10.0, 200.0], [45.0], True, True, [10.0, 10.5, 10.0, 10.5],
+                                                 [45.0, 45.0, 45.5, 45.5], 2, 2)
+    gx, gy = ci2.points()
+    assert gx[0] == 0 and gy[0] == 0 and gx[1] == -1 and gy[1] == -1
+
+
+def test_interpolator_config1_hirlam12_like(oracle):
+    # BASELINE config 1: test/hirlam12.nc geometry (Xc = 5.0..6.6 step 0.1, Yc = 61.5..62.6, 2 levels x 2 times) bilinear
+    # to a 0.5-degree lat/long grid via the option strings of the fimex CLI (src/binSrc/fimex.cc:1008-1034)
+    xc = 5.0 + 0.1 * np.arange(17)
+    yc = 61.5 + 0.1 * np.arange(12)
+    rng = np.random.default_rng(12)
+    fill = np.float32(9.96921e+36)
+    data = rng.normal(280, 5, (2, 2, 12, 17)).astype(np.float32)
+    data[0, 1, 3, 4] = fill
+    xw = rng.normal(0, 5, data.shape).astype(np.float32)
+    yw = rng.normal(0, 5, data.shape).astype(np.float32)
+    proj_out = "+proj=latlong +a=6371000 +e=0 +no_defs"
+    ip = fb.Interpolator(SRC_LL, xc, yc, True, has_xy_vectors=True)
+    ip.changeProjection("bilinear", proj_out, "5,5.5,6,6.5", "61.5,62,62.5", "degree", "degree")
+    out = ip.getDataSlice(data, bad_value=fill)
+    assert out.shape == (2, 2, 3, 4)
+    # oracle: same pipeline on the CPU
+    rc, x, y = oracle.project_axes(proj_out, SRC_LL, np.radians([5, 5.5, 6, 6.5]), np.radians([61.5, 62, 62.5]))
+    px = oracle.points2position(x, np.radians(xc), 1)
+    py = oracle.points2position(y, np.radians(yc), 2)
+    red, px, py, inX, inY, x0, y0 = oracle.reduced_domain(px, py, 17, 12)
+    crop = data[..., y0:y0 + inY, x0:x0 + inX]
+    want = oracle.cached_interpolate(1, px, py, inX, inY, 4, 3, oracle.bad2nan(crop, fill))
+    want = np.where(np.isnan(want), fill, want).reshape(out.shape)
+    assert_bit_equal(out, want, "config 1 scalar")
+    assert (out == fill).sum() >= 1
+    # x_wind / y_wind: rotated with the lat/long-target bearing branch of the matrix (interpolation.c:366,408)
+    ux = ip.getDataSlice(xw, counterpart=yw, direction="x")
+    uy = ip.getDataSlice(yw, counterpart=xw, direction="y")
+    rc, m = oracle.vector_matrix(SRC_LL, proj_out, [5, 5.5, 6, 6.5], [61.5, 62, 62.5], 1, 2)
+    ui = oracle.cached_interpolate(1, px, py, inX, inY, 4, 3, xw[..., y0:y0 + inY, x0:x0 + inX])
+    vi = oracle.cached_interpolate(1, px, py, inX, inY, 4, 3, yw[..., y0:y0 + inY, x0:x0 + inX])
+    wu, wv = oracle.vector_reproject_by_matrix(m, ui, vi, 4, 3, 4)
+    assert np.allclose(ux.ravel(), wu.ravel(), rtol=1e-5, atol=1e-6) and np.allclose(uy.ravel(), wv.ravel(), rtol=1e-5, atol=1e-6)
+
+
+# =====================================================================================================
+# full BASELINE size (config 2): properties that need no oracle run over 5e8 values
+# =====================================================================================================
+def test_full_size_bilinear_properties(oracle):
+    import torch
+    lon = np.arange(1440) * 0.25
+    lat = 90 - np.arange(721) * 0.25
+    ax = (np.arange(2000) - 999.5) * 0.0225
+    ci = fb.CachedInterpolation.fromProjection(Method.BILINEAR, ROTPOLE, ax, ax, True, True, SRC_LL, lon, lat, True)
+    assert ci.createReducedDomain()
+    inX, inY, nz = ci.getInX(), ci.getInY(), 137
+    g = torch.Generator(device="cuda").manual_seed(20261018)
+    a = torch.randn((nz, inY, inX), generator=g, device="cuda", dtype=torch.float32)
+    b = torch.randn((nz, inY, inX), generator=g, device="cuda", dtype=torch.float32)
+    oa = ci.interpolateValues(a)
+    assert oa.shape == (nz, 2000, 2000) and not torch.isnan(oa).any()
+    # (1) a plane a*x + b*y + c is reproduced (bilinear is exact for it) to fp32 rounding
+    xs = torch.arange(inX, device="cuda", dtype=torch.float32)[None, None, :]
+    ys = torch.arange(inY, device="cuda", dtype=torch.float32)[None, :, None]
+    plane = (0.5 * xs + 0.25 * ys + 3.0).expand(2, inY, inX).contiguous()
+    op = ci.interpolateValues(plane)
+    px, py = ci.points()
+    want = torch.from_numpy((0.5 * px + 0.25 * py + 3.0).astype(np.float32)).cuda().view(2000, 2000)
+    assert (op[0] - want).abs().max().item() <= 2e-5 * want.abs().max().item()
+    # (2) linearity: I(a + b) == I(a) + I(b) within fp32 rounding of the sums
+    ob = ci.interpolateValues(b)
+    oab = ci.interpolateValues(a + b)
+    assert (oab - (oa + ob)).abs().max().item() <= 1e-5 * 8
+    # (3) a random sample of target columns against the oracle, all 137 levels, bit for bit
+    rng = np.random.default_rng(0)
+    sample = rng.integers(0, 2000 * 2000, 2000)
+    host = a.cpu().numpy()
+    want = oracle.cached_interpolate(1, px[sample], py[sample], inX, inY, sample.size, 1, host)
+    got = oa.view(nz, -1)[:, torch.from_numpy(sample).cuda()].cpu().numpy().reshape(want.shape)
+    assert_bit_equal(got, want, "full-size sample vs oracle")
+    # (4) checksum of checksums: per-level sums of the output equal the sums of per-row sums (layout sanity)
+    assert torch.allclose(oa.sum(dim=(1, 2), dtype=torch.float64), oa.sum(dim=2, dtype=torch.float64).sum(dim=1))
