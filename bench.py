@@ -222,7 +222,7 @@ def main_b200(args):
     setup_s = time.perf_counter() - t_setup0
 
     # ---- synthetic slab, generated on the device ---------------------------------------------------------------
-    nlev = NZ * NT
+    nlev = NZ * args.times
     g = torch.Generator(device=dev).manual_seed(20261018 + rank)
     lo = torch.deg2rad(torch.tensor(lon[x0:x0 + inX], device=dev, dtype=torch.float32))[None, None, :]
     la = torch.deg2rad(torch.tensor(lat[y0:y0 + inY], device=dev, dtype=torch.float32))[None, :, None]
@@ -296,7 +296,7 @@ def main_b200(args):
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            for _t in range(NT):  # 24 time steps, one getDataSlice-sized call each (the way a Fimex host calls it)
+            for _t in range(args.times):  # 24 time steps, one getDataSlice-sized call each (the way a Fimex host calls it)
                 ci.interpolateValues(hin_np, out=hout_np)
         barrier()
         dt = time.perf_counter() - t0
@@ -324,7 +324,7 @@ def main_b200(args):
             "metric": METRIC, "value": value, "unit": "values/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": workload_name(method), "levels_per_gpu": nlev, "source_footprint": [int(inX), int(inY)],
+            "config": {"workload": workload_name(method) if args.times == NT else workload_name(method) + f" [REDUCED to {args.times} time steps: profiling only]", "levels_per_gpu": nlev, "source_footprint": [int(inX), int(inY)],
                        "crop_offset": [int(x0), int(y0)], "l2": "inputs+outputs >> L2 (52.6 GB written per step), no flush needed",
                        "parallelism": f"slab{world}", "setup_s": setup_s},
             "hbm_gbs": achieved, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
@@ -342,6 +342,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--method", default="bilinear", choices=sorted(METHODS))
+    ap.add_argument("--times", type=int, default=NT, help="time steps per GPU slab (24 = the BASELINE workload; fewer only for profiling)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

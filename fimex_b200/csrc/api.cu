@@ -210,6 +210,7 @@ struct fb200_interp {
     int* d_bic_off = nullptr;
     double2* d_bic_frac = nullptr;
     ForwardPlan fwd;
+    TileTable tiles; // staged fast path of the bilinear gather
     bool reduced = false;
     long long xMin = 0, yMin = 0;
     long long coordnn_ties = 0;
@@ -238,6 +239,7 @@ struct fb200_interp {
         d_bic_off = nullptr;
         d_bic_frac = nullptr;
         forward_free_plan(&fwd);
+        tile_table_free(&tiles);
     }
 };
 
@@ -280,6 +282,10 @@ int compile_tables(fb200_interp* h, cudaStream_t st)
             return FB_ERROR;
         if (launch_compile_bilinear(h->d_px, h->d_py, n, (int)h->inX, (int)h->inY, h->d_bil, st) != FB_OK)
             return FB_ERROR;
+        if (tile_table_supported((int)h->inX, (int)h->inY, (int)h->outX, (int)h->outY) && !std::getenv("FIMEX_B200_DIRECT_GATHER")) {
+            if (tile_table_build(h->d_px, h->d_py, (int)h->inX, (int)h->inY, (int)h->outX, (int)h->outY, &h->tiles, st) != FB_OK)
+                return FB_ERROR;
+        }
         break;
     case FB_BICUBIC:
         if (dev_alloc(&h->d_bic_off, h->npts) != FB_OK || dev_alloc(&h->d_bic_frac, h->npts) != FB_OK)
@@ -364,6 +370,8 @@ int run_device(const fb200_interp* h, const float* d_in, size_t nz, float* d_out
     const GatherGeom g = geom_of(h, nz);
     switch (h->method) {
     case FB_BILINEAR:
+        if (h->tiles.ready())
+            return launch_gather_bilinear_staged(g, h->tiles, d_in, d_out, st);
         return launch_gather_bilinear(g, h->d_bil, d_in, d_out, st);
     case FB_BICUBIC:
         return launch_gather_bicubic(g, h->d_bic_off, h->d_bic_frac, d_in, d_out, st);

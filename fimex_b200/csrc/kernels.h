@@ -61,6 +61,21 @@ int launch_rotate(const double2* d_cs, float* d_u, float* d_v, long long layer, 
 // mifi_vector_reproject_direction_by_matrix_f (interpolation.c:814-835)
 int launch_rotate_direction(const double* d_matrix, float* d_angle, long long layer, long long nz, cudaStream_t st);
 
+// ---- staged_kernels.cu (K4 fast path) -------------------------------------------------------------------
+struct TileTable {
+    int tiles_x = 0, tiles_y = 0;
+    int* d_cells = nullptr;   // [tile][1024] sorted distinct source cells (+ neighbour flags)
+    int* d_ncells = nullptr;  // [tile]
+    uint4* d_meta = nullptr;  // [tile][256] 4 x (local cell | mode << 16)
+    float4* d_xf = nullptr;   // [tile][256]
+    float4* d_yf = nullptr;   // [tile][256]
+    bool ready() const { return d_cells != nullptr; }
+};
+bool tile_table_supported(int ix, int iy, int ox, int oy);
+int tile_table_build(const double* d_px, const double* d_py, int ix, int iy, int ox, int oy, TileTable* tt, cudaStream_t st);
+void tile_table_free(TileTable* tt);
+int launch_gather_bilinear_staged(const GatherGeom& g, const TileTable& tt, const float* d_in, float* d_out, cudaStream_t st);
+
 // ---- forward_kernels.cu (K8) ---------------------------------------------------------------------------
 struct ForwardPlan {
     long long n_in = 0, n_cells = 0;

@@ -7,6 +7,7 @@
 // __dadd_rn/__dmul_rn/__ddiv_rn so that nvcc cannot contract it into FMAs: given identical inputs the
 // positions and tables are bit-identical to what the reference's C code computes on x86-64.
 #include "kernels.h"
+#include "tables.cuh"
 
 #include <math.h>
 
@@ -171,14 +172,6 @@ __global__ void k_scale(double* __restrict__ v, long long n, double f)
 }
 
 // --------------------------------------------------------------------------------------------- table compilation
-// Positions whose magnitude does not fit an int are "outside": the reference narrows lround()/floor() to
-// int (interpolation.c:864-865, 883-886), which is undefined for such values; finite positions of real
-// grids never get there (-999 marks projection failures).
-__device__ __forceinline__ bool fits_int(double v)
-{
-    return v > -2147483000.0 && v < 2147483000.0;
-}
-
 __global__ void k_compile_nn(const double* __restrict__ px, const double* __restrict__ py, long long n, int ix, int iy,
                              int* __restrict__ off)
 {
@@ -197,45 +190,8 @@ __global__ void k_compile_nn(const double* __restrict__ px, const double* __rest
 __global__ void k_compile_bilinear(const double* __restrict__ px, const double* __restrict__ py, long long n, int ix, int iy,
                                    int4* __restrict__ tab)
 {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const double x = px[i], y = py[i];
-        int4 e = make_int4(0, 0, 0, FB_BL_NAN);
-        if (fits_int(x) && fits_int(y)) {
-            const int x0 = (int)floor(x), y0 = (int)floor(y);
-            const float xf = __double2float_rn(__dsub_rn(x, (double)x0)); // :885
-            const float yf = __double2float_rn(__dsub_rn(y, (double)y0)); // :888
-            e.y = __float_as_int(xf);
-            e.z = __float_as_int(yf);
-            const bool x_in = (0 <= x0) && (x0 + 1 < ix);
-            const bool y_in = (0 <= y0) && (y0 + 1 < iy);
-            if (x_in && y_in) {
-                e.x = y0 * ix + x0;
-                e.w = FB_BL_FULL;
-            } else if (x_in) {
-                const long long ry = llround(y);
-                if (ry >= 0 && ry < iy) {
-                    e.x = (int)ry * ix + x0;
-                    e.w = FB_BL_XLIN;
-                }
-            } else {
-                const long long rx = llround(x);
-                if (rx >= 0 && rx < ix) {
-                    if (y_in) {
-                        e.x = y0 * ix + (int)rx;
-                        e.w = FB_BL_YLIN;
-                    } else {
-                        const long long ry = llround(y);
-                        // ry == iy is the reference's out-of-bounds read (:936); NaN here
-                        if (ry >= 0 && ry < iy) {
-                            e.x = (int)ry * ix + (int)rx;
-                            e.w = FB_BL_NEAR;
-                        }
-                    }
-                }
-            }
-        }
-        tab[i] = e;
-    }
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        tab[i] = classify_bilinear(px[i], py[i], ix, iy);
 }
 
 __global__ void k_compile_bicubic(const double* __restrict__ px, const double* __restrict__ py, long long n, int ix, int iy,

@@ -64,10 +64,21 @@ def bits(a):
     return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
 
 
-def assert_bit_equal(a, b, what=""):
+def assert_bit_equal(a, b, what="", nan_payload=False):
+    """Every non-NaN value bit-identical (signed zeros and infinities included) and the NaN masks identical.
+
+    With nan_payload=True the NaN bit patterns must match too: that holds for copied values and for the fill
+    value MIFI_UNDEFINED_F (0x7fc00000), i.e. everything nearest-neighbour produces.  NaNs that come out of
+    ARITHMETIC (bilinear / bicubic / rotation with a NaN tap) carry the operand's payload on x86 and the
+    canonical 0x7fffffff on NVIDIA GPUs; the value is NaN either way and the next stage of the reference
+    (interpolationArray2Data, CDMInterpolator.cc:121-124) replaces it by the fill value."""
     a = np.ascontiguousarray(a, dtype=np.float32)
     b = np.ascontiguousarray(b, dtype=np.float32)
     assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
-    bad = np.flatnonzero(a.view(np.uint32).ravel() != b.view(np.uint32).ravel())
+    ua, ub = a.view(np.uint32).ravel(), b.view(np.uint32).ravel()
+    differ = ua != ub
+    if not nan_payload:
+        differ &= ~(np.isnan(a).ravel() & np.isnan(b).ravel())
+    bad = np.flatnonzero(differ)
     assert bad.size == 0, f"{what}: {bad.size} of {a.size} values differ bitwise; first at {bad[:5]}: " \
                           f"{a.ravel()[bad[:5]]} vs {b.ravel()[bad[:5]]}"
