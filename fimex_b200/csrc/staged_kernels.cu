@@ -170,13 +170,43 @@ __device__ __forceinline__ float eval_cell(int mode, const float4 s, float wx0, 
     }
 }
 
+// 4-byte asynchronous global->shared copy (LDGSTS); src_bytes == 0 writes a zero without reading
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_src, int src_bytes)
+{
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(dst), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit()
+{
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
+constexpr int kSlotNone = -2, kSlotZero = -1;
+
+// offset (inside a level) of staging element r = 4*cell + tap, kSlotZero for a tap outside the level,
+// kSlotNone past the end of the tile's list
+__device__ __forceinline__ int staging_slot(const int* s_cells, int r, int ntaps, int ix)
+{
+    if (r >= ntaps)
+        return kSlotNone;
+    const unsigned packed = (unsigned)s_cells[r >> 2];
+    const int tap = r & 3;
+    const bool right = (packed & kHasRight) != 0, down = (packed & kHasDown) != 0;
+    const bool ok = (!(tap & 1) || right) && (!(tap & 2) || down);
+    return ok ? (int)(packed & kOffMask) + (tap & 1) + ((tap & 2) ? ix : 0) : kSlotZero;
+}
+
 template <bool VEC_STORE>
 __global__ void __launch_bounds__(kThreads, 5) k_gather_bilinear_staged(GatherGeom g, int tiles_x, const int* __restrict__ cells,
                                                                      const int* __restrict__ ncells, const uint4* __restrict__ meta,
                                                                      const float4* __restrict__ xf4, const float4* __restrict__ yf4,
                                                                      const float* __restrict__ in, float* __restrict__ out)
 {
-    __shared__ float4 s_stage[kStageCells];
+    __shared__ float4 s_stage[2][kStageCells]; // double buffer: batch b+1 lands while batch b is consumed
     __shared__ int s_cells[kTilePts];
     const int tile = blockIdx.x;
     const int t = threadIdx.x;
@@ -202,82 +232,90 @@ __global__ void __launch_bounds__(kThreads, 5) k_gather_bilinear_staged(GatherGe
     const int tx = tile % tiles_x, ty = tile / tiles_x;
     const int y = ty * kTileY + (t >> 5);
     const int x0 = tx * kTileX + (t & 31) * 4;
-    long long valid = (y < g.oy) ? (long long)g.ox - x0 : 0;
-    if (valid > 4)
-        valid = 4;
-    if (valid < 0)
-        valid = 0;
+    int valid = (y < g.oy) ? g.ox - x0 : 0;
+    valid = valid > 4 ? 4 : (valid < 0 ? 0 : valid);
     const long long per = (g.nz + gridDim.y - 1) / gridDim.y;
     const long long z0 = (long long)blockIdx.y * per;
     const long long z1 = z0 + per < g.nz ? z0 + per : g.nz;
     float* o = out + z0 * g.out_level + (long long)y * g.ox + x0;
     const int zb = (nc <= kStageCells / kMaxBatch) ? kMaxBatch : (nc > 0 ? kStageCells / nc : kMaxBatch);
     const int ntaps = nc * 4;
-    float* stage_f = reinterpret_cast<float*>(s_stage);
     __syncthreads();
-    for (long long z = z0; z < z1; z += zb) {
-        const int nb = (int)((z1 - z) < zb ? (z1 - z) : zb);
-        // 1. stage the distinct cells of this tile for nb levels
+    // the staging elements this thread copies every level: r = t and r = t + 256 (covers tiles of <= 128 cells,
+    // 96 % of them at the BASELINE geometry); larger tiles loop over the rest
+    const int slot0 = staging_slot(s_cells, t, ntaps, g.ix);
+    const int slot1 = staging_slot(s_cells, t + kThreads, ntaps, g.ix);
+
+    auto issue = [&](int buf, long long z, int nb) {
+        float* dst = reinterpret_cast<float*>(s_stage[buf]);
         const float* lv = in + z * g.in_level;
-        for (int zi = 0; zi < nb; ++zi, lv += g.in_level) {
-            for (int r = t; r < ntaps; r += kThreads) {
-                const unsigned packed = (unsigned)s_cells[r >> 2];
-                const int tap = r & 3;
-                const bool right = (packed & kHasRight) != 0, down = (packed & kHasDown) != 0;
-                const bool ok = (!(tap & 1) || right) && (!(tap & 2) || down);
-                float v = 0.f;
-                if (ok)
-                    v = __ldg(lv + (packed & kOffMask) + (tap & 1) + ((tap & 2) ? g.ix : 0));
-                stage_f[zi * ntaps + r] = v;
+#pragma unroll 4
+        for (int zi = 0; zi < nb; ++zi, lv += g.in_level, dst += ntaps) {
+            if (slot0 != kSlotNone)
+                cp_async_f32(dst + t, lv + (slot0 >= 0 ? slot0 : 0), slot0 >= 0 ? 4 : 0);
+            if (slot1 != kSlotNone)
+                cp_async_f32(dst + t + kThreads, lv + (slot1 >= 0 ? slot1 : 0), slot1 >= 0 ? 4 : 0);
+            for (int r = t + 2 * kThreads; r < ntaps; r += kThreads) {
+                const int s = staging_slot(s_cells, r, ntaps, g.ix);
+                cp_async_f32(dst + r, lv + (s >= 0 ? s : 0), s >= 0 ? 4 : 0);
             }
         }
-        __syncthreads();
-        // 2. one 128-bit shared load per output value
-        if (valid > 0) {
-            if (all_full) {
+        cp_async_commit();
+    };
+
+    if (z0 < z1)
+        issue(0, z0, (int)((z1 - z0) < zb ? (z1 - z0) : zb));
+    int buf = 0;
+    for (long long z = z0; z < z1; z += zb, buf ^= 1) {
+        const int nb = (int)((z1 - z) < zb ? (z1 - z) : zb);
+        cp_async_wait_all();
+        __syncthreads(); // batch z has landed for every thread, and every thread is done reading the other buffer
+        const long long zn = z + zb;
+        if (zn < z1)
+            issue(buf ^ 1, zn, (int)((z1 - zn) < zb ? (z1 - zn) : zb));
+        if (valid == 0)
+            continue;
+        const float4* cell = s_stage[buf];
+        if (all_full) {
 #pragma unroll 2
-                for (int zi = 0; zi < nb; ++zi) {
-                    const float4* cell = s_stage + zi * nc;
-                    float r[4];
+            for (int zi = 0; zi < nb; ++zi, cell += nc) {
+                float r[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float4 s = cell[idx[k]];
-                        const float top = __fadd_rn(__fmul_rn(wx0[k], s.x), __fmul_rn(xf[k], s.y));
-                        const float bot = __fadd_rn(__fmul_rn(wx0[k], s.z), __fmul_rn(xf[k], s.w));
-                        r[k] = __fadd_rn(__fmul_rn(wy0[k], top), __fmul_rn(yf[k], bot));
-                    }
-                    if (VEC_STORE && valid == 4) {
-                        __stcs(reinterpret_cast<float4*>(o), make_float4(r[0], r[1], r[2], r[3]));
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (k < valid)
-                                __stcs(o + k, r[k]);
-                    }
-                    o += g.out_level;
+                for (int k = 0; k < 4; ++k) {
+                    const float4 s = cell[idx[k]];
+                    const float top = __fadd_rn(__fmul_rn(wx0[k], s.x), __fmul_rn(xf[k], s.y));
+                    const float bot = __fadd_rn(__fmul_rn(wx0[k], s.z), __fmul_rn(xf[k], s.w));
+                    r[k] = __fadd_rn(__fmul_rn(wy0[k], top), __fmul_rn(yf[k], bot));
                 }
-            } else {
-                for (int zi = 0; zi < nb; ++zi) {
-                    const float4* cell = s_stage + zi * nc;
-                    float r[4];
+                if (VEC_STORE && valid == 4) {
+                    __stcs(reinterpret_cast<float4*>(o), make_float4(r[0], r[1], r[2], r[3]));
+                } else {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float4 s = (mode[k] != FB_BL_NAN) ? cell[idx[k]] : make_float4(0.f, 0.f, 0.f, 0.f);
-                        r[k] = eval_cell(mode[k], s, wx0[k], xf[k], wy0[k], yf[k]);
-                    }
-                    if (VEC_STORE && valid == 4) {
-                        __stcs(reinterpret_cast<float4*>(o), make_float4(r[0], r[1], r[2], r[3]));
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (k < valid)
-                                __stcs(o + k, r[k]);
-                    }
-                    o += g.out_level;
+                    for (int k = 0; k < 4; ++k)
+                        if (k < valid)
+                            __stcs(o + k, r[k]);
                 }
+                o += g.out_level;
+            }
+        } else {
+            for (int zi = 0; zi < nb; ++zi, cell += nc) {
+                float r[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float4 s = (mode[k] != FB_BL_NAN) ? cell[idx[k]] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    r[k] = eval_cell(mode[k], s, wx0[k], xf[k], wy0[k], yf[k]);
+                }
+                if (VEC_STORE && valid == 4) {
+                    __stcs(reinterpret_cast<float4*>(o), make_float4(r[0], r[1], r[2], r[3]));
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (k < valid)
+                            __stcs(o + k, r[k]);
+                }
+                o += g.out_level;
             }
         }
-        __syncthreads();
     }
 }
 
