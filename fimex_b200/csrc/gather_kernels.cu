@@ -17,6 +17,8 @@
 // x86-64, which has no FMA either (SURVEY.md 8a trap 7).
 #include "kernels.h"
 
+#include <cstdlib>
+
 namespace fb {
 
 namespace {
@@ -367,28 +369,38 @@ __global__ void __launch_bounds__(kThreads) k_rotate_direction(const double* __r
     }
 }
 
-// choose the number of level chunks: enough CTAs for >= ~16 waves, but chunks of >= 32 levels so that the
-// table entry read per chunk stays small against 4 B/level of output
-int z_chunks(long long ctas_x, long long nz)
-{
-    const long long want = (long long)sm_count() * 8 * 16;
-    long long gy = (want + ctas_x - 1) / ctas_x;
-    const long long max_gy = nz / 32 > 1 ? nz / 32 : 1;
-    if (gy > max_gy)
-        gy = max_gy;
-    if (gy < 1)
-        gy = 1;
-    if (gy > 65535)
-        gy = 65535;
-    return (int)gy;
-}
-
 bool aligned16(const void* p)
 {
     return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
 }
 
 } // namespace
+
+// Number of level chunks (gridDim.y).  A CTA walks `chunk` consecutive levels of its target points, so the table
+// entry of a point is read once per chunk.  Measured on B200 (profiles/): chunks of 32..96 levels run at the same
+// speed, longer ones are slower (CTAs drift apart in z and the set of DRAM pages being written at any moment
+// grows: 658-level chunks cost 40 % more time per level than 64-level chunks), shorter ones re-read the tables too
+// often.  So: ~64 levels per chunk, and at least ~4 CTAs per SM in flight for small slices.
+int z_chunks(long long ctas_x, long long nz)
+{
+    long long gy = (nz + 63) / 64;
+    const long long min_ctas = (long long)sm_count() * 4;
+    if (ctas_x * gy < min_ctas) {
+        const long long more = (min_ctas + ctas_x - 1) / ctas_x;
+        const long long cap = nz / 8 > 1 ? nz / 8 : 1; // never below 8 levels per chunk
+        gy = more < cap ? more : cap;
+    }
+    if (const char* env = std::getenv("FIMEX_B200_ZCHUNK")) { // experiments only: levels per CTA
+        const long long want_chunk = std::atoll(env);
+        if (want_chunk > 0)
+            gy = (nz + want_chunk - 1) / want_chunk;
+    }
+    if (gy < 1)
+        gy = 1;
+    if (gy > 65535)
+        gy = 65535;
+    return (int)gy;
+}
 
 // ------------------------------------------------------------------------------------------------- launchers
 #define FB_GATHER_PRECHECK()                                                                                                              \

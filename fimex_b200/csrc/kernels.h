@@ -50,6 +50,7 @@ struct GatherGeom {
     long long out_level; // ox*oy
     long long nz;
 };
+int z_chunks(long long ctas_x, long long nz); // gridDim.y policy shared by the gather kernels
 int launch_gather_nn(const GatherGeom& g, const int* d_off, const float* d_in, float* d_out, cudaStream_t st);
 int launch_gather_bilinear(const GatherGeom& g, const int4* d_tab, const float* d_in, float* d_out, cudaStream_t st);
 int launch_gather_bicubic(const GatherGeom& g, const int* d_off, const double2* d_frac, const float* d_in, float* d_out, cudaStream_t st);
@@ -64,9 +65,9 @@ int launch_rotate_direction(const double* d_matrix, float* d_angle, long long la
 // ---- staged_kernels.cu (K4 fast path) -------------------------------------------------------------------
 struct TileTable {
     int tiles_x = 0, tiles_y = 0;
-    int* d_cells = nullptr;   // [tile][1024] sorted distinct source cells (+ neighbour flags)
-    int* d_ncells = nullptr;  // [tile]
-    uint4* d_meta = nullptr;  // [tile][256] 4 x (local cell | mode << 16)
+    int* d_cells = nullptr;   // [tile][4096] sorted distinct source offsets ("taps") of the tile
+    int* d_ncells = nullptr;  // [tile] number of taps
+    uint4* d_meta = nullptr;  // [tile][256] 4 x (a | b << 12 | mode << 24)
     float4* d_xf = nullptr;   // [tile][256]
     float4* d_yf = nullptr;   // [tile][256]
     bool ready() const { return d_cells != nullptr; }
