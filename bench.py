@@ -268,14 +268,16 @@ def main_b200(args):
     # ---- roofline of the dominant (only) kernel of the step ------------------------------------------------------
     peak, peak_src = peaks()
     n_out, n_fp = OUT_N * OUT_N, inX * inY
-    table_bytes = {1: 16, 0: 4, 2: 20}[method_id] * n_out  # compiled table entry per target point, read once per level chunk
     alg_bytes = 4 * n_out * nlev + 4 * n_fp * nlev + 16 * n_out  # store + compulsory load + two fp64 positions
     kernel_ms = float(np.mean(per_launch_ms))
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "kernel": {0: "k_gather_nn", 1: "k_gather_bilinear", 2: "k_gather_bicubic"}[method_id],
+                "peak_source": peak_src,
+                "kernel": {0: "k_gather_nn", 1: "k_gather_bilinear_staged", 2: "k_gather_bicubic"}[method_id],
                 "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_output_value": alg_bytes / values_per_step,
-                "kernel_ms": kernel_ms, "table_bytes_per_chunk": table_bytes}
+                "kernel_ms": kernel_ms,
+                "formula": "4*N_out*Z (store) + 4*N_fp*Z (compulsory load of the cropped footprint) + 16*N_out (two fp64 positions)",
+                "n_out": n_out, "n_fp": n_fp, "levels": nlev}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:

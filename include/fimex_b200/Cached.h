@@ -1,0 +1,163 @@
+// fimex_b200/Cached.h -- header-only C++ mirror of the reference's cached regridding operators, forwarding to the C ABI
+// of libfimex_b200.so (include/fimex_b200.h).
+//
+// Reference classes (arebru/fimex 0.67.2):
+//   MetNoFimex::CachedInterpolationInterface / CachedInterpolation   include/fimex/CachedInterpolation.h:60-161
+//   MetNoFimex::CachedForwardInterpolation                           src/CachedForwardInterpolation.h:34-61
+//   MetNoFimex::CachedVectorReprojection                             include/fimex/CachedVectorReprojection.h:33-63
+// Same constructor arguments, same method names and meaning, same error behaviour (an exception where the reference
+// throws CDMException).  boost::shared_array<float> becomes std::shared_ptr<float[]>; the reader-side methods
+// (getInputDataSlice) stay in the host application because they only touch CDM metadata and I/O.
+//
+// In a Fimex tree the three .cc files would include this header and forward; stand-alone it lets
+// the reference's own tests be restated nearly verbatim (tests/cpp/).
+#ifndef FIMEX_B200_CACHED_H_
+#define FIMEX_B200_CACHED_H_
+
+#include "../fimex_b200.h"
+
+#include <cstddef>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace MetNoFimexB200 {
+
+class CDMException : public std::runtime_error
+{
+public:
+    explicit CDMException(const std::string& msg) : std::runtime_error(msg) {}
+};
+
+typedef std::shared_ptr<float[]> shared_float_array;
+
+struct ReducedInterpolationDomain
+{
+    std::string xDim, yDim;
+    size_t xMin, yMin, xOrg, yOrg;
+};
+
+/** include/fimex/CachedInterpolation.h:60-99 */
+class CachedInterpolationInterface
+{
+public:
+    CachedInterpolationInterface(const std::string& xDimName, const std::string& yDimName)
+        : _xDimName(xDimName), _yDimName(yDimName), handle_(0) {}
+    virtual ~CachedInterpolationInterface() { fb200_interp_destroy(handle_); }
+
+    /** interpolateValues(inData, size, newSize): [inZ][inY][inX] -> newly allocated [inZ][outY][outX] */
+    virtual shared_float_array interpolateValues(shared_float_array inData, size_t size, size_t& newSize) const
+    {
+        newSize = fb200_interp_new_size(handle_, size);
+        shared_float_array out(new float[newSize ? newSize : 1]);
+        size_t n = 0;
+        if (fb200_interp_interpolate_values(handle_, inData.get(), size, out.get(), &n) != MIFI_OK)
+            throw CDMException(std::string("error during interpolation: ") + fb200_last_error());
+        return out;
+    }
+    virtual size_t getInX() const { return fb200_interp_in_x(handle_); }
+    virtual size_t getInY() const { return fb200_interp_in_y(handle_); }
+    virtual size_t getOutX() const { return fb200_interp_out_x(handle_); }
+    virtual size_t getOutY() const { return fb200_interp_out_y(handle_); }
+    std::shared_ptr<ReducedInterpolationDomain> reducedDomain() const { return reducedDomain_; }
+    const fb200_interp* handle() const { return handle_; }
+
+protected:
+    std::string _xDimName, _yDimName;
+    fb200_interp* handle_;
+    std::shared_ptr<ReducedInterpolationDomain> reducedDomain_;
+
+private:
+    CachedInterpolationInterface(const CachedInterpolationInterface&);
+    CachedInterpolationInterface& operator=(const CachedInterpolationInterface&);
+};
+
+/** include/fimex/CachedInterpolation.h:105-161, src/CachedInterpolation.cc:93-200 */
+class CachedInterpolation : public CachedInterpolationInterface
+{
+public:
+    CachedInterpolation(const std::string& xDimName, const std::string& yDimName, int funcType, const std::vector<double>& pointsOnXAxis,
+                        const std::vector<double>& pointsOnYAxis, size_t inX, size_t inY, size_t outX, size_t outY)
+        : CachedInterpolationInterface(xDimName, yDimName)
+    {
+        if (pointsOnXAxis.size() != outX * outY || pointsOnYAxis.size() != outX * outY)
+            throw CDMException("pointsOnXAxis/pointsOnYAxis must hold outX*outY values");
+        if (fb200_cached_interpolation_create(funcType, pointsOnXAxis.data(), pointsOnYAxis.data(), inX, inY, outX, outY, &handle_) != MIFI_OK)
+            throw CDMException(std::string("unknown interpolation function or device error: ") + fb200_last_error());
+    }
+
+    /** src/CachedInterpolation.cc:159-200 */
+    void createReducedDomain(std::string xDimName, std::string yDimName)
+    {
+        if (reducedDomain_)
+            return; // don't set twice
+        const size_t xOrg = getInX(), yOrg = getInY();
+        int reduced = 0;
+        long long x0 = 0, y0 = 0;
+        if (fb200_interp_create_reduced_domain(handle_, &reduced, &x0, &y0) != MIFI_OK)
+            throw CDMException(std::string("createReducedDomain: ") + fb200_last_error());
+        if (!reduced)
+            return;
+        std::shared_ptr<ReducedInterpolationDomain> rid(new ReducedInterpolationDomain());
+        rid->xDim = xDimName;
+        rid->yDim = yDimName;
+        rid->xMin = static_cast<size_t>(x0);
+        rid->yMin = static_cast<size_t>(y0);
+        rid->xOrg = xOrg;
+        rid->yOrg = yOrg;
+        reducedDomain_ = rid;
+    }
+};
+
+/** src/CachedForwardInterpolation.h:34-61, src/CachedForwardInterpolation.cc:62-131 */
+class CachedForwardInterpolation : public CachedInterpolationInterface
+{
+public:
+    CachedForwardInterpolation(const std::string& xDimName, const std::string& yDimName, int funcType, const std::vector<double>& pOnX,
+                               const std::vector<double>& pOnY, size_t inX, size_t inY, size_t outX, size_t outY)
+        : CachedInterpolationInterface(xDimName, yDimName)
+    {
+        if (pOnX.size() != inX * inY || pOnY.size() != inX * inY)
+            throw CDMException("pOnX/pOnY must hold inX*inY values");
+        if (fb200_cached_forward_interpolation_create(funcType, pOnX.data(), pOnY.data(), inX, inY, outX, outY, &handle_) != MIFI_OK)
+            throw CDMException(std::string("unknown forward interpolation method or device error: ") + fb200_last_error());
+    }
+};
+
+/** include/fimex/CachedVectorReprojection.h:33-63, src/CachedVectorReprojection.cc:35-55 */
+class CachedVectorReprojection
+{
+public:
+    CachedVectorReprojection() : handle_(0), ox(0), oy(0) { fb200_vector_create(MIFI_VECTOR_KEEP_SIZE, 0, 0, 0, &handle_); }
+    CachedVectorReprojection(int method, std::shared_ptr<double[]> matrix, int ox, int oy) : handle_(0), ox(ox), oy(oy)
+    {
+        if (fb200_vector_create(method, matrix.get(), ox, oy, &handle_) != MIFI_OK)
+            throw CDMException(std::string("CachedVectorReprojection: ") + fb200_last_error());
+    }
+    virtual ~CachedVectorReprojection() { fb200_vector_destroy(handle_); }
+
+    void reprojectValues(shared_float_array& uValues, shared_float_array& vValues, size_t size) const
+    {
+        if (fb200_vector_reproject_values(handle_, uValues.get(), vValues.get(), size) != MIFI_OK)
+            throw CDMException("Error during reprojection of vector-values");
+    }
+    void reprojectDirectionValues(shared_float_array& angles, size_t size) const
+    {
+        if (fb200_vector_reproject_direction_values(handle_, angles.get(), size) != MIFI_OK)
+            throw CDMException("Error during reprojection of vector-direction-values");
+    }
+    size_t getXSize() const { return static_cast<size_t>(ox); }
+    size_t getYSize() const { return static_cast<size_t>(oy); }
+    const fb200_vector* handle() const { return handle_; }
+
+private:
+    fb200_vector* handle_;
+    int ox, oy;
+    CachedVectorReprojection(const CachedVectorReprojection&);
+    CachedVectorReprojection& operator=(const CachedVectorReprojection&);
+};
+
+} // namespace MetNoFimexB200
+
+#endif
