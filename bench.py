@@ -133,14 +133,22 @@ def synth_field_np(nlev, inX, inY, x0, y0, t=0, seed=20261018):
     return (250 + 30 * np.sin(la) * np.cos(2 * lo) + 0.1 * z + t + 0.5 * rng.standard_normal((nlev, inY, inX))).astype(np.float32)
 
 
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def cpu_driver():
+    """(driver, kind, threads, description).  torchrun exports OMP_NUM_THREADS=1; the thread count is therefore passed
+    explicitly: all the cores this process may run on."""
     from oracle import oracle as orc
+    cores = host_cores()
     if orc.Reference.available():
-        r = orc.Reference()
-        return r, "reference", r.max_threads(), "reference src/interpolation.c (gcc -O2 -fopenmp, unmodified) in the restated " \
-                                                 "CachedInterpolation.cc:118-147 loop"
-    o = orc.Oracle()
-    return o, "port", os.cpu_count(), "oracle/mifi_oracle.c restatement (gcc -O2 -fopenmp)"
+        return orc.Reference(), "reference", cores, "reference src/interpolation.c (gcc -O2 -fopenmp, unmodified) in the restated " \
+                                                     "CachedInterpolation.cc:118-147 loop"
+    return orc.Oracle(), "port", cores, "oracle/mifi_oracle.c restatement (gcc -O2 -fopenmp)"
 
 
 def run_cpu(method_id, steps, warmup, nlev=NZ):
@@ -151,7 +159,7 @@ def run_cpu(method_id, steps, warmup, nlev=NZ):
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        drv.cached_interpolate(method_id, px, py, inX, inY, OUT_N, OUT_N, field, out=out)
+        drv.cached_interpolate(method_id, px, py, inX, inY, OUT_N, OUT_N, field, nthreads=cores, out=out)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
@@ -201,6 +209,7 @@ def main_b200(args):
     fb.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout for the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     method = args.method
     method_id = METHODS[method]
