@@ -13,7 +13,7 @@ import re
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(HERE, "lib", "libfimex_b200.so")
+_LIB_PATH = os.environ.get("FIMEX_B200_LIB") or os.path.join(HERE, "lib", "libfimex_b200.so")  # override: A/B experiments only
 HEADER = os.path.normpath(os.path.join(HERE, "..", "include", "fimex_b200.h"))
 
 MIFI_OK, MIFI_ERROR = 1, -1

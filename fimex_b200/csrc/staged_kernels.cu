@@ -37,6 +37,8 @@ constexpr int kMaxTaps = 4 * kTilePts;                              // worst cas
 constexpr int kStageFloats = 4096;                                  // one staging buffer (16 KB), two of them
 constexpr int kMaxBatch = 8;                                        // levels staged per barrier
 constexpr int kNoTap = 0x7fffffff;
+constexpr int kLvlStride = kMaxBatch + 1;                            // tap-major staging: element (tap r, level zi) at r*9 + zi
+constexpr int kFastTaps = kStageFloats / kLvlStride;                // tiles with at most 455 taps use it (all but pole/seam tiles)
 
 // ------------------------------------------------------------------------------------------------ table compiler
 __global__ void __launch_bounds__(kThreads) k_compile_tiles(const double* __restrict__ px, const double* __restrict__ py, int ox, int oy,
@@ -173,7 +175,7 @@ __device__ __forceinline__ void cp_async_wait_all()
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 }
 
-__global__ void __launch_bounds__(kThreads, 5) k_gather_bilinear_staged(GatherGeom g, int tiles_x, const int* __restrict__ taps,
+__global__ void __launch_bounds__(kThreads, 3) k_gather_bilinear_staged(GatherGeom g, int tiles_x, const int* __restrict__ taps,
                                                                      const int* __restrict__ ntaps_tab, const uint4* __restrict__ meta,
                                                                      const float4* __restrict__ xf4, const float4* __restrict__ yf4,
                                                                      const float* __restrict__ in, float* __restrict__ out)
@@ -214,19 +216,41 @@ __global__ void __launch_bounds__(kThreads, 5) k_gather_bilinear_staged(GatherGe
     const long long z1 = z0 + per < g.nz ? z0 + per : g.nz;
     float* o = out + z0 * g.out_level + (long long)yw * g.ox + x;
     const long long row8 = 8ll * g.ox;
-    const int zb = (ntaps * kMaxBatch <= kStageFloats) ? kMaxBatch : (ntaps > 0 ? kStageFloats / ntaps : kMaxBatch);
+    // Two staging layouts.  fast: tap-major, element (tap r, level zi) at r*9 + zi -- a thread's eight row pointers are then
+    // constant for a whole batch and the level is an immediate offset of the shared load (no address arithmetic in the
+    // inner loop; 9 is odd, so any 32 taps with distinct r mod 32 still hit distinct banks).  Tiles with more than 455 taps
+    // (over the pole, across the seam) keep the level-major layout with as many levels per batch as fit.
+    const bool fast = ntaps <= kFastTaps;
+    const int zb = fast ? kMaxBatch : (kStageFloats / ntaps);
     // the first staging element of this thread is the same for every level; larger tiles loop over the rest
     const int tap0 = (t < ntaps) ? __ldg(my_taps + t) : -1;
 
     auto issue = [&](int buf, long long z, int nb) {
         float* dst = s_stage[buf];
         const float* lv = in + z * g.in_level;
-#pragma unroll 4
-        for (int zi = 0; zi < nb; ++zi, lv += g.in_level, dst += ntaps) {
-            if (tap0 >= 0)
-                cp_async_f32(dst + t, lv + tap0);
-            for (int r = t + kThreads; r < ntaps; r += kThreads)
-                cp_async_f32(dst + r, lv + __ldg(my_taps + r));
+        if (fast) {
+            if (tap0 >= 0) { // warps past the end of the tap list (most of them: ~50 taps per tile) skip the loop entirely
+                const float* src = lv + tap0;
+                float* d = dst + t * kLvlStride;
+#pragma unroll
+                for (int zi = 0; zi < kMaxBatch; ++zi)
+                    if (zi < nb)
+                        cp_async_f32(d + zi, src + zi * g.in_level);
+            }
+            if (ntaps > kThreads) {
+                for (int r = t + kThreads; r < ntaps; r += kThreads) {
+                    const float* src = lv + __ldg(my_taps + r);
+                    for (int zi = 0; zi < nb; ++zi)
+                        cp_async_f32(dst + r * kLvlStride + zi, src + zi * g.in_level);
+                }
+            }
+        } else {
+            for (int zi = 0; zi < nb; ++zi, lv += g.in_level, dst += ntaps) {
+                if (tap0 >= 0)
+                    cp_async_f32(dst + t, lv + tap0);
+                for (int r = t + kThreads; r < ntaps; r += kThreads)
+                    cp_async_f32(dst + r, lv + __ldg(my_taps + r));
+            }
         }
         cp_async_commit();
     };
@@ -244,43 +268,56 @@ __global__ void __launch_bounds__(kThreads, 5) k_gather_bilinear_staged(GatherGe
         if (nvalid == 0)
             continue;
         const float* lvl = s_stage[buf];
-        if (all_full && nvalid == 4) {
-#pragma unroll 2
-            for (int zi = 0; zi < nb; ++zi, lvl += ntaps) {
-                float r[4];
+        if (fast && all_full && nvalid == 4) {
+            const float* pa[4];
+            const float* pb[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float s00 = lvl[ia[k]], s01 = lvl[ia[k] + 1], s10 = lvl[ib[k]], s11 = lvl[ib[k] + 1];
-                    const float top = __fadd_rn(__fmul_rn(wx0[k], s00), __fmul_rn(xf[k], s01));
-                    const float bot = __fadd_rn(__fmul_rn(wx0[k], s10), __fmul_rn(xf[k], s11));
-                    r[k] = __fadd_rn(__fmul_rn(wy0[k], top), __fmul_rn(yf[k], bot));
-                }
-                __stcs(o, r[0]);
-                __stcs(o + row8, r[1]);
-                __stcs(o + 2 * row8, r[2]);
-                __stcs(o + 3 * row8, r[3]);
-                o += g.out_level;
+            for (int k = 0; k < 4; ++k) {
+                pa[k] = lvl + ia[k] * kLvlStride;
+                pb[k] = lvl + ib[k] * kLvlStride;
             }
-        } else { // grid edge: per-point mode (interpolation.c:904-953)
-            for (int zi = 0; zi < nb; ++zi, lvl += ntaps) {
+#pragma unroll
+            for (int zi = 0; zi < kMaxBatch; ++zi) {
+                if (zi < nb) {
+                    float r[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float s00 = pa[k][zi], s01 = pa[k][kLvlStride + zi], s10 = pb[k][zi], s11 = pb[k][kLvlStride + zi];
+                        const float top = __fadd_rn(__fmul_rn(wx0[k], s00), __fmul_rn(xf[k], s01));
+                        const float bot = __fadd_rn(__fmul_rn(wx0[k], s10), __fmul_rn(xf[k], s11));
+                        r[k] = __fadd_rn(__fmul_rn(wy0[k], top), __fmul_rn(yf[k], bot));
+                    }
+                    __stcs(o, r[0]);
+                    __stcs(o + row8, r[1]);
+                    __stcs(o + 2 * row8, r[2]);
+                    __stcs(o + 3 * row8, r[3]);
+                    o += g.out_level;
+                }
+            }
+        } else { // grid edge, partial tile or a tile with many taps: per-point mode (interpolation.c:904-953)
+            const int sr = fast ? kLvlStride : 1;      // stride between neighbouring taps
+            const int sz = fast ? 1 : ntaps;           // stride between levels
+            for (int zi = 0; zi < nb; ++zi, lvl += sz) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     float v = undef_f();
+                    const float* qa = lvl + ia[k] * sr;
+                    const float* qb = lvl + ib[k] * sr;
                     switch (mode[k]) {
                     case FB_BL_FULL: {
-                        const float top = __fadd_rn(__fmul_rn(wx0[k], lvl[ia[k]]), __fmul_rn(xf[k], lvl[ia[k] + 1]));
-                        const float bot = __fadd_rn(__fmul_rn(wx0[k], lvl[ib[k]]), __fmul_rn(xf[k], lvl[ib[k] + 1]));
+                        const float top = __fadd_rn(__fmul_rn(wx0[k], qa[0]), __fmul_rn(xf[k], qa[sr]));
+                        const float bot = __fadd_rn(__fmul_rn(wx0[k], qb[0]), __fmul_rn(xf[k], qb[sr]));
                         v = __fadd_rn(__fmul_rn(wy0[k], top), __fmul_rn(yf[k], bot));
                         break;
                     }
                     case FB_BL_XLIN:
-                        v = __fadd_rn(__fmul_rn(wx0[k], lvl[ia[k]]), __fmul_rn(xf[k], lvl[ia[k] + 1]));
+                        v = __fadd_rn(__fmul_rn(wx0[k], qa[0]), __fmul_rn(xf[k], qa[sr]));
                         break;
                     case FB_BL_YLIN:
-                        v = __fadd_rn(__fmul_rn(wy0[k], lvl[ia[k]]), __fmul_rn(yf[k], lvl[ib[k]]));
+                        v = __fadd_rn(__fmul_rn(wy0[k], qa[0]), __fmul_rn(yf[k], qb[0]));
                         break;
                     case FB_BL_NEAR:
-                        v = lvl[ia[k]];
+                        v = qa[0];
                         break;
                     default:
                         break;
