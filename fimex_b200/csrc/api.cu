@@ -283,7 +283,7 @@ int compile_tables(fb200_interp* h, cudaStream_t st)
         if (launch_compile_bilinear(h->d_px, h->d_py, n, (int)h->inX, (int)h->inY, h->d_bil, st) != FB_OK)
             return FB_ERROR;
         if (tile_table_supported((int)h->inX, (int)h->inY, (int)h->outX, (int)h->outY) && !std::getenv("FIMEX_B200_DIRECT_GATHER")) {
-            if (tile_table_build(h->d_px, h->d_py, (int)h->inX, (int)h->inY, (int)h->outX, (int)h->outY, &h->tiles, st) != FB_OK)
+            if (tile_table_build(false, h->d_px, h->d_py, (int)h->inX, (int)h->inY, (int)h->outX, (int)h->outY, &h->tiles, st) != FB_OK)
                 return FB_ERROR;
         }
         break;
@@ -298,6 +298,10 @@ int compile_tables(fb200_interp* h, cudaStream_t st)
             return FB_ERROR;
         if (launch_compile_nn(h->d_px, h->d_py, n, (int)h->inX, (int)h->inY, h->d_nn, st) != FB_OK)
             return FB_ERROR;
+        if (tile_table_supported((int)h->inX, (int)h->inY, (int)h->outX, (int)h->outY) && !std::getenv("FIMEX_B200_DIRECT_GATHER")) {
+            if (tile_table_build(true, h->d_px, h->d_py, (int)h->inX, (int)h->inY, (int)h->outX, (int)h->outY, &h->tiles, st) != FB_OK)
+                return FB_ERROR;
+        }
         break;
     }
     FB_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -376,6 +380,8 @@ int run_device(const fb200_interp* h, const float* d_in, size_t nz, float* d_out
     case FB_BICUBIC:
         return launch_gather_bicubic(g, h->d_bic_off, h->d_bic_frac, d_in, d_out, st);
     default:
+        if (h->tiles.ready())
+            return launch_gather_bilinear_staged(g, h->tiles, d_in, d_out, st);
         return launch_gather_nn(g, h->d_nn, d_in, d_out, st);
     }
 }

@@ -70,11 +70,13 @@ struct TileTable {
     uint4* d_meta = nullptr;  // [tile][256] 4 x (a | b << 12 | mode << 24)
     float4* d_xf = nullptr;   // [tile][256]
     float4* d_yf = nullptr;   // [tile][256]
+    bool nn = false;          // nearest-neighbour table (one tap per point, no xf/yf)
     bool ready() const { return d_cells != nullptr; }
 };
 bool tile_table_supported(int ix, int iy, int ox, int oy);
-int tile_table_build(const double* d_px, const double* d_py, int ix, int iy, int ox, int oy, TileTable* tt, cudaStream_t st);
+int tile_table_build(bool nn, const double* d_px, const double* d_py, int ix, int iy, int ox, int oy, TileTable* tt, cudaStream_t st);
 void tile_table_free(TileTable* tt);
+// staged gather for bilinear and nearest-neighbour tables
 int launch_gather_bilinear_staged(const GatherGeom& g, const TileTable& tt, const float* d_in, float* d_out, cudaStream_t st);
 
 // ---- forward_kernels.cu (K8) ---------------------------------------------------------------------------

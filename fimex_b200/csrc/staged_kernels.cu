@@ -41,6 +41,7 @@ constexpr int kLvlStride = kMaxBatch + 1;                            // tap-majo
 constexpr int kFastTaps = kStageFloats / kLvlStride;                // tiles with at most 455 taps use it (all but pole/seam tiles)
 
 // ------------------------------------------------------------------------------------------------ table compiler
+template <bool NN>
 __global__ void __launch_bounds__(kThreads) k_compile_tiles(const double* __restrict__ px, const double* __restrict__ py, int ox, int oy,
                                                           int ix, int iy, int tiles_x, int* __restrict__ taps, int* __restrict__ ntaps,
                                                           uint4* __restrict__ meta, float4* __restrict__ xf4, float4* __restrict__ yf4)
@@ -61,7 +62,7 @@ __global__ void __launch_bounds__(kThreads) k_compile_tiles(const double* __rest
         const int y = yw + 8 * k;
         if (y < oy && x < ox) {
             const long long i = (long long)y * ox + x;
-            e = classify_bilinear(px[i], py[i], ix, iy);
+            e = NN ? classify_nn(px[i], py[i], ix, iy) : classify_bilinear(px[i], py[i], ix, iy);
         }
         off[k] = e.x;
         xf[k] = __int_as_float(e.y);
@@ -155,8 +156,10 @@ __global__ void __launch_bounds__(kThreads) k_compile_tiles(const double* __rest
     }
     const size_t slot = (size_t)tile * kThreads + t;
     meta[slot] = make_uint4(m[0], m[1], m[2], m[3]);
-    xf4[slot] = make_float4(xf[0], xf[1], xf[2], xf[3]);
-    yf4[slot] = make_float4(yf[0], yf[1], yf[2], yf[3]);
+    if (!NN) {
+        xf4[slot] = make_float4(xf[0], xf[1], xf[2], xf[3]);
+        yf4[slot] = make_float4(yf[0], yf[1], yf[2], yf[3]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ gather
@@ -175,6 +178,7 @@ __device__ __forceinline__ void cp_async_wait_all()
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 }
 
+template <bool NN>
 __global__ void __launch_bounds__(kThreads, 3) k_gather_bilinear_staged(GatherGeom g, int tiles_x, const int* __restrict__ taps,
                                                                      const int* __restrict__ ntaps_tab, const uint4* __restrict__ meta,
                                                                      const float4* __restrict__ xf4, const float4* __restrict__ yf4,
@@ -187,12 +191,13 @@ __global__ void __launch_bounds__(kThreads, 3) k_gather_bilinear_staged(GatherGe
     const int* my_taps = taps + (size_t)tile * kMaxTaps;
     const size_t slot = (size_t)tile * kThreads + t;
     const uint4 m = __ldg(meta + slot);
-    const float4 fx = __ldg(xf4 + slot), fy = __ldg(yf4 + slot);
+    const float4 fx = NN ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(xf4 + slot);
+    const float4 fy = NN ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(yf4 + slot);
     const unsigned mm[4] = {m.x, m.y, m.z, m.w};
     const float xf[4] = {fx.x, fx.y, fx.z, fx.w}, yf[4] = {fy.x, fy.y, fy.z, fy.w};
     int ia[4], ib[4], mode[4];
     float wx0[4], wy0[4];
-    bool all_full = true;
+    bool all_full = true; // every point of this thread takes the common branch: 4 taps (bilinear) / 1 tap (nearest neighbour)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         ia[k] = (int)(mm[k] & 0xfffu);
@@ -200,7 +205,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_gather_bilinear_staged(GatherGe
         mode[k] = (int)(mm[k] >> 24);
         wx0[k] = __fsub_rn(1.f, xf[k]);
         wy0[k] = __fsub_rn(1.f, yf[k]);
-        all_full = all_full && (mode[k] == FB_BL_FULL);
+        all_full = all_full && (mode[k] == (NN ? FB_BL_NEAR : FB_BL_FULL));
     }
     // lane = x inside the tile: a warp reads 32 consecutive target points of one row per shared load (a handful
     // of neighbouring taps: no bank conflicts) and writes 128 contiguous bytes per store
@@ -282,10 +287,14 @@ __global__ void __launch_bounds__(kThreads, 3) k_gather_bilinear_staged(GatherGe
                     float r[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const float s00 = pa[k][zi], s01 = pa[k][kLvlStride + zi], s10 = pb[k][zi], s11 = pb[k][kLvlStride + zi];
-                        const float top = __fadd_rn(__fmul_rn(wx0[k], s00), __fmul_rn(xf[k], s01));
-                        const float bot = __fadd_rn(__fmul_rn(wx0[k], s10), __fmul_rn(xf[k], s11));
-                        r[k] = __fadd_rn(__fmul_rn(wy0[k], top), __fmul_rn(yf[k], bot));
+                        if (NN) { // copied value, bit for bit (interpolation.c:869-871)
+                            r[k] = pa[k][zi];
+                        } else {
+                            const float s00 = pa[k][zi], s01 = pa[k][kLvlStride + zi], s10 = pb[k][zi], s11 = pb[k][kLvlStride + zi];
+                            const float top = __fadd_rn(__fmul_rn(wx0[k], s00), __fmul_rn(xf[k], s01));
+                            const float bot = __fadd_rn(__fmul_rn(wx0[k], s10), __fmul_rn(xf[k], s11));
+                            r[k] = __fadd_rn(__fmul_rn(wy0[k], top), __fmul_rn(yf[k], bot));
+                        }
                     }
                     __stcs(o, r[0]);
                     __stcs(o + row8, r[1]);
@@ -340,7 +349,7 @@ bool tile_table_supported(int ix, int iy, int ox, int oy)
     return in_level > 0 && in_level < (1ll << 30) && ox > 0 && oy > 0 && tiles < 2147483647LL;
 }
 
-int tile_table_build(const double* d_px, const double* d_py, int ix, int iy, int ox, int oy, TileTable* tt, cudaStream_t st)
+int tile_table_build(bool nn, const double* d_px, const double* d_py, int ix, int iy, int ox, int oy, TileTable* tt, cudaStream_t st)
 {
     tile_table_free(tt);
     tt->tiles_x = (ox + kTileX - 1) / kTileX;
@@ -349,10 +358,16 @@ int tile_table_build(const double* d_px, const double* d_py, int ix, int iy, int
     FB_CUDA_CHECK(cudaMalloc(&tt->d_cells, sizeof(int) * tiles * kMaxTaps));
     FB_CUDA_CHECK(cudaMalloc(&tt->d_ncells, sizeof(int) * tiles));
     FB_CUDA_CHECK(cudaMalloc(&tt->d_meta, sizeof(uint4) * tiles * kThreads));
-    FB_CUDA_CHECK(cudaMalloc(&tt->d_xf, sizeof(float4) * tiles * kThreads));
-    FB_CUDA_CHECK(cudaMalloc(&tt->d_yf, sizeof(float4) * tiles * kThreads));
-    k_compile_tiles<<<(unsigned)tiles, kThreads, 0, st>>>(d_px, d_py, ox, oy, ix, iy, tt->tiles_x, tt->d_cells, tt->d_ncells, tt->d_meta,
-                                                          tt->d_xf, tt->d_yf);
+    tt->nn = nn;
+    if (nn) {
+        k_compile_tiles<true><<<(unsigned)tiles, kThreads, 0, st>>>(d_px, d_py, ox, oy, ix, iy, tt->tiles_x, tt->d_cells, tt->d_ncells,
+                                                                    tt->d_meta, nullptr, nullptr);
+    } else {
+        FB_CUDA_CHECK(cudaMalloc(&tt->d_xf, sizeof(float4) * tiles * kThreads));
+        FB_CUDA_CHECK(cudaMalloc(&tt->d_yf, sizeof(float4) * tiles * kThreads));
+        k_compile_tiles<false><<<(unsigned)tiles, kThreads, 0, st>>>(d_px, d_py, ox, oy, ix, iy, tt->tiles_x, tt->d_cells, tt->d_ncells,
+                                                                     tt->d_meta, tt->d_xf, tt->d_yf);
+    }
     count_launch();
     FB_CUDA_CHECK(cudaGetLastError());
     return FB_OK;
@@ -379,7 +394,11 @@ int launch_gather_bilinear_staged(const GatherGeom& g, const TileTable& tt, cons
         return FB_OK;
     const unsigned tiles = (unsigned)tt.tiles_x * (unsigned)tt.tiles_y;
     dim3 grid(tiles, z_chunks(tiles, g.nz));
-    k_gather_bilinear_staged<<<grid, kThreads, 0, st>>>(g, tt.tiles_x, tt.d_cells, tt.d_ncells, tt.d_meta, tt.d_xf, tt.d_yf, d_in, d_out);
+    if (tt.nn)
+        k_gather_bilinear_staged<true><<<grid, kThreads, 0, st>>>(g, tt.tiles_x, tt.d_cells, tt.d_ncells, tt.d_meta, nullptr, nullptr, d_in, d_out);
+    else
+        k_gather_bilinear_staged<false><<<grid, kThreads, 0, st>>>(g, tt.tiles_x, tt.d_cells, tt.d_ncells, tt.d_meta, tt.d_xf, tt.d_yf, d_in,
+                                                                   d_out);
     count_launch();
     FB_CUDA_CHECK(cudaGetLastError());
     return FB_OK;

@@ -56,4 +56,19 @@ __device__ __forceinline__ int4 classify_bilinear(double x, double y, int ix, in
     return e;
 }
 
+// Nearest neighbour as a one-tap entry of the same table: {off, 0, 0, NEAR or NAN}; lround semantics of
+// src/interpolation.c:864-868 (half away from zero)
+__device__ __forceinline__ int4 classify_nn(double x, double y, int ix, int iy)
+{
+    int4 e = make_int4(0, 0, 0, FB_BL_NAN);
+    if (fits_int(x) && fits_int(y)) {
+        const long long rx = llround(x), ry = llround(y);
+        if (rx >= 0 && rx < ix && ry >= 0 && ry < iy) {
+            e.x = (int)(ry * ix + rx);
+            e.w = FB_BL_NEAR;
+        }
+    }
+    return e;
+}
+
 } // namespace fb
