@@ -210,7 +210,8 @@ struct fb200_interp {
     int* d_bic_off = nullptr;
     double2* d_bic_frac = nullptr;
     ForwardPlan fwd;
-    TileTable tiles; // staged fast path of the bilinear gather
+    TileTable tiles;       // staged fast path of the bilinear / nearest-neighbour gather
+    BicubicTiles bic_tiles; // staged fast path of the bicubic gather
     bool reduced = false;
     long long xMin = 0, yMin = 0;
     long long coordnn_ties = 0;
@@ -240,6 +241,7 @@ struct fb200_interp {
         d_bic_frac = nullptr;
         forward_free_plan(&fwd);
         tile_table_free(&tiles);
+        bicubic_tiles_free(&bic_tiles);
     }
 };
 
@@ -292,6 +294,11 @@ int compile_tables(fb200_interp* h, cudaStream_t st)
             return FB_ERROR;
         if (launch_compile_bicubic(h->d_px, h->d_py, n, (int)h->inX, (int)h->inY, h->d_bic_off, h->d_bic_frac, st) != FB_OK)
             return FB_ERROR;
+        if (bicubic_tiles_supported((int)h->inX, (int)h->inY, (int)h->outX, (int)h->outY) && !std::getenv("FIMEX_B200_DIRECT_GATHER")) {
+            if (bicubic_tiles_build(h->d_bic_off, h->d_bic_frac, (int)h->inX, (int)h->inY, (int)h->outX, (int)h->outY, &h->bic_tiles, st) !=
+                FB_OK)
+                return FB_ERROR;
+        }
         break;
     default:
         if (dev_alloc(&h->d_nn, h->npts) != FB_OK)
@@ -378,6 +385,8 @@ int run_device(const fb200_interp* h, const float* d_in, size_t nz, float* d_out
             return launch_gather_bilinear_staged(g, h->tiles, d_in, d_out, st);
         return launch_gather_bilinear(g, h->d_bil, d_in, d_out, st);
     case FB_BICUBIC:
+        if (h->bic_tiles.ready())
+            return launch_gather_bicubic_staged(g, h->bic_tiles, h->d_bic_off, h->d_bic_frac, nullptr, d_in, nullptr, d_out, nullptr, st);
         return launch_gather_bicubic(g, h->d_bic_off, h->d_bic_frac, d_in, d_out, st);
     default:
         if (h->tiles.ready())
@@ -395,6 +404,8 @@ int run_vector_device(const fb200_interp* h, const fb200_vector* v, const float*
     case FB_BILINEAR:
         return launch_gather_vector(FB_BILINEAR, g, h->d_bil, nullptr, cs, d_u, d_v, d_uo, d_vo, st);
     case FB_BICUBIC:
+        if (h->bic_tiles.ready())
+            return launch_gather_bicubic_staged(g, h->bic_tiles, h->d_bic_off, h->d_bic_frac, cs, d_u, d_v, d_uo, d_vo, st);
         return launch_gather_vector(FB_BICUBIC, g, h->d_bic_off, h->d_bic_frac, cs, d_u, d_v, d_uo, d_vo, st);
     default:
         return launch_gather_vector(FB_NN, g, h->d_nn, nullptr, cs, d_u, d_v, d_uo, d_vo, st);

@@ -1,0 +1,710 @@
+// fimex_b200/csrc/bicubic_staged.cu -- K5 (bicubic) as a shared-memory staged gather with register reuse of the
+// 4x4 stencil: the fast path of CachedInterpolation::interpolateValues with mifi_get_values_bicubic_f
+// (/root/reference/src/CachedInterpolation.cc:118-147, src/interpolation.c:959-1028), optionally for both
+// components of a vector with the rotation of mifi_vector_reproject_values_by_matrix_f (:790-812) in the epilogue.
+//
+// What bounds bicubic on B200 (ncu, profiles/): not HBM.  The reference's arithmetic is 16 fp64 multiply-adds for the
+// row sums plus 4 for the column sum per output, each multiply and add rounded separately (no FMA on x86-64), with the
+// accumulator re-rounded to fp32 after every row.  Bit-exact replay costs 35 fp64 instructions and 7 fp32<->fp64
+// conversions per output; the fp64 pipe issues 64 lanes/clk/SM and the conversion (XU) pipe 16 lanes/clk/SM.  The
+// direct kernel (gather_kernels.cu) additionally converts its 16 taps per output on the XU pipe, which saturates it
+// (92 % busy, 12 % of the HBM roofline).  So the design goal here is: no per-output tap conversion and as few
+// shared-memory reads per output as possible, leaving the fp64 pipe as the only limiter (~0.55 clk per output and SM).
+//
+//   * a CTA owns a tile of 32 x 28 target points and a chunk of levels;
+//   * the tile's DISTINCT source values ("taps") of a batch of levels are loaded once into registers, converted to
+//     fp64 ONCE (per tap, not per use) and parked in shared memory, double buffered: the global loads of batch b+2 are
+//     in flight while batch b+1 waits in shared memory and batch b is consumed;
+//   * target points are regrouped by source cell: a thread owns a GROUP of up to 4 target points that read the SAME
+//     4x4 stencil, loads each stencil row once (4 x LDS.64) and uses it for its 4 points -- "reuse of the stencil" is
+//     done in registers rather than by warp shuffles, because the points of one cell are not adjacent lanes on a rotated
+//     grid; per-point weights (fp64) stay in registers for the whole chunk;
+//   * results go through a (double-buffered, bank-swizzled) shared-memory output tile so that global stores are full
+//     128-byte rows (st.global.cs) and one barrier per batch suffices.
+//
+// Table (built once per grid on the device by k_compile_bicubic_tiles, two passes: count, then fill):
+//   info  [tile]     int4   {first tap, ntaps (-1: direct fallback), first group, ngroups}
+//   taps  [...]      int    per tile: sorted distinct source offsets y*ix + x
+//   gmeta [group]    uint4  8 x u16: list index of the first tap of each of the 4 stencil rows, then the 4 point slots
+//                           (out_slot(y*32 + x) inside the tile; 896 = padding)
+//   gfrac [group][4] double2 (xfrac, yfrac) of the 4 points, fp64 as in the reference (:970-973)
+// Tiles whose tap list does not fit the staging buffers (over the pole, where one tile sees thousands of source
+// columns) are computed by the same kernel with direct global loads.
+#include "kernels.h"
+#include "interp_math.cuh"
+
+#include <cstdlib>
+#include <vector>
+
+namespace fb {
+
+namespace {
+
+constexpr int kT = 256;                              // threads per CTA
+constexpr int kTX = 32, kTY = 28, kTP = kTX * kTY;   // tile of 896 target points: 224 groups of 4 + padding <= 256
+constexpr int kSortN = 1024;                         // tile points padded to a power of two for the bitonic sort
+constexpr int kDump = kTP;                           // output-tile slot of padding points
+constexpr int kOutRow = kTP + 4;                     // floats per (field, level) of the output tile (multiple of 4)
+constexpr int kOutRows = 8;                          // (field, level) rows of the output tile
+constexpr int kStageElems = 8 * kT;                  // tap values staged per batch: 8 registers per thread
+constexpr int kTapCap = kStageElems;                 // tiles with more distinct taps are computed directly
+constexpr int kFastTaps = kT;                        // at most this many taps: one tap per thread, 8 levels per batch
+constexpr int kStageDoubles = 2 * kFastTaps * 5;     // per buffer: max(256*9, 2*256*5, 2048) = 2560 doubles
+constexpr int kMaxTapKeys = 16384;                   // 16 stencil taps for each of at most 896 distinct cells, padded to 2^k
+constexpr int kNoKey = 0x7fffffff;
+
+// output-tile slot of tile point p = y*32 + x: 4-float column groups are XOR-permuted by the row, so that the points of
+// one source cell (a block of neighbouring rows and columns) spread over the banks; rows stay readable as float4
+__host__ __device__ __forceinline__ int out_slot(int p)
+{
+    return (p & ~31) | ((p & 31) ^ (((p >> 5) & 7) << 2));
+}
+
+// ------------------------------------------------------------------------------------------------ block helpers
+// bitonic sort of n = 2^k keys in shared memory, ascending
+template <class K>
+__device__ __forceinline__ void bitonic_sort(K* s, int n)
+{
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n; i += kT) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const K a = s[i], b = s[p];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) {
+                        s[i] = b;
+                        s[p] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+struct OpAdd {
+    __device__ __forceinline__ int operator()(int a, int b) const { return a + b; }
+};
+struct OpMax {
+    __device__ __forceinline__ int operator()(int a, int b) const { return a > b ? a : b; }
+};
+
+// inclusive scan over kT * N values (thread t owns elements N*t .. N*t+N-1); every thread gets the total
+template <int N, class Op>
+__device__ __forceinline__ int block_scan(int (&v)[N], Op op, int identity, int* s_warp)
+{
+#pragma unroll
+    for (int k = 1; k < N; ++k)
+        v[k] = op(v[k - 1], v[k]);
+    int incl = v[N - 1];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o)
+            incl = op(n, incl);
+    }
+    if (lane == 31)
+        s_warp[w] = incl;
+    __syncthreads();
+    int base = identity, total = identity;
+    for (int k = 0; k < kT / 32; ++k) {
+        if (k < w)
+            base = op(base, s_warp[k]);
+        total = op(total, s_warp[k]);
+    }
+    __syncthreads();
+    int prev = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0)
+        prev = identity;
+    const int ex = op(base, prev);
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+        v[k] = op(ex, v[k]);
+    return total;
+}
+
+// ------------------------------------------------------------------------------------------------ table compiler
+// One CTA per tile.  FILL = false: count taps and groups; FILL = true: write the tables at the offsets in `info`.
+template <bool FILL>
+__global__ void __launch_bounds__(kT) k_compile_bicubic_tiles(const int* __restrict__ off_tab, const double2* __restrict__ frac_tab, int ox,
+                                                             int oy, int ix, int tiles_x, int2* __restrict__ counts,
+                                                             const int4* __restrict__ info, int* __restrict__ taps,
+                                                             uint4* __restrict__ gmeta, double2* __restrict__ gfrac)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long* s_pk = reinterpret_cast<unsigned long long*>(smem_raw); // [1024] (cell << 10 | point), sorted
+    int* s_tk = reinterpret_cast<int*>(smem_raw + sizeof(unsigned long long) * kSortN); // [16384] tap keys
+    int* s_runstart = s_tk + kMaxTapKeys;                                          // [1024]
+    int* s_x = s_runstart + kSortN;                                                // [1024] groups before the element's run
+    int* s_cells = s_x + kSortN;                                                   // [1024] distinct cells
+    int* s_uniq = s_cells + kSortN;                                                // [kTapCap] distinct taps (FILL)
+    __shared__ int s_warp[kT / 32];
+
+    const int tile = blockIdx.x, t = threadIdx.x;
+    int4 inf = make_int4(0, 0, 0, 0);
+    if (FILL) {
+        inf = info[tile];
+        if (inf.y <= 0)
+            return; // direct-fallback tile or a tile without a single valid point
+    }
+    const int tx = tile % tiles_x, ty = tile / tiles_x;
+
+    // A. (cell, point) keys
+#pragma unroll
+    for (int k = 0; k < kSortN / kT; ++k) {
+        const int p = t + k * kT;
+        unsigned long long key = ~0ull;
+        if (p < kTP) {
+            const int gx = tx * kTX + (p & (kTX - 1)), gy = ty * kTY + (p >> 5);
+            if (gx < ox && gy < oy) {
+                const int o = off_tab[(long long)gy * ox + gx];
+                if (o >= 0)
+                    key = ((unsigned long long)(unsigned)o << 10) | (unsigned)p;
+            }
+        }
+        s_pk[p] = key;
+    }
+    __syncthreads();
+    // B. sort by cell (ties by point index: row-major inside the tile)
+    bitonic_sort(s_pk, kSortN);
+
+    // C. runs of equal cells -> groups of up to 4 points
+    int cell[4], runstart[4], isfirst[4], contrib[4];
+    bool valid[4];
+    {
+        const int i0 = 4 * t;
+        unsigned long long prev = i0 > 0 ? s_pk[i0 - 1] : ~0ull;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned long long key = s_pk[i0 + k];
+            valid[k] = key != ~0ull;
+            cell[k] = (int)(key >> 10);
+            const bool first = valid[k] && (i0 + k == 0 || (int)(prev >> 10) != cell[k]);
+            isfirst[k] = first ? 1 : 0;
+            runstart[k] = first ? i0 + k : 0;
+            prev = key;
+        }
+    }
+    block_scan<4>(runstart, OpMax(), 0, s_warp);
+    int ord[4] = {isfirst[0], isfirst[1], isfirst[2], isfirst[3]};
+    const int ncells = block_scan<4>(ord, OpAdd(), 0, s_warp);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = 4 * t + k;
+        s_runstart[i] = runstart[k];
+        if (isfirst[k])
+            s_cells[ord[k] - 1] = cell[k];
+        const unsigned long long next = (i + 1 < kSortN) ? s_pk[i + 1] : ~0ull;
+        const bool last = valid[k] && (next == ~0ull || (int)(next >> 10) != cell[k]);
+        contrib[k] = last ? (i - runstart[k] + 1 + 3) / 4 : 0;
+    }
+    int gincl[4] = {contrib[0], contrib[1], contrib[2], contrib[3]};
+    const int ngroups = block_scan<4>(gincl, OpAdd(), 0, s_warp);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        s_x[4 * t + k] = gincl[k] - contrib[k];
+    __syncthreads();
+
+    // D. tap keys: the 16 taps of every distinct cell, sorted
+    const int nkeys = ncells * 16;
+    int n2 = 32;
+    while (n2 < nkeys)
+        n2 <<= 1;
+    for (int j = t; j < n2; j += kT)
+        s_tk[j] = j < nkeys ? s_cells[j >> 4] + ((j >> 2) & 3) * ix + (j & 3) : kNoKey;
+    __syncthreads();
+    bitonic_sort(s_tk, n2);
+
+    // E. distinct taps
+    const int per = n2 >= kT ? n2 / kT : 1;
+    const int j0 = t * per;
+    int cnt[1] = {0};
+    if (j0 < n2) {
+        for (int k = 0; k < per; ++k) {
+            const int v = s_tk[j0 + k];
+            cnt[0] += (v != kNoKey) && (j0 + k == 0 || s_tk[j0 + k - 1] != v);
+        }
+    }
+    const int mine = cnt[0];
+    const int ntaps = block_scan<1>(cnt, OpAdd(), 0, s_warp);
+    if (!FILL) {
+        if (t == 0)
+            counts[tile] = make_int2(ntaps > kTapCap ? -1 : ntaps, ntaps > kTapCap ? 0 : ngroups);
+        return;
+    }
+    {
+        int pos = cnt[0] - mine;
+        if (j0 < n2) {
+            for (int k = 0; k < per; ++k) {
+                const int v = s_tk[j0 + k];
+                if ((v != kNoKey) && (j0 + k == 0 || s_tk[j0 + k - 1] != v)) {
+                    s_uniq[pos] = v;
+                    taps[(size_t)inf.x + pos] = v;
+                    ++pos;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // F. groups: stencil rows as indices into the tap list, point slots, fractions
+    auto find = [&](int key) {
+        int lo = 0, hi = ntaps - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (s_uniq[mid] < key)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        return lo;
+    };
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (!valid[k])
+            continue;
+        const int i = 4 * t + k;
+        const int rs = s_runstart[i];
+        const int within = i - rs;
+        const size_t gid = (size_t)inf.z + s_x[rs] + (within >> 2);
+        const int slot = within & 3;
+        const int p = (int)(s_pk[i] & 1023u);
+        const int gx = tx * kTX + (p & (kTX - 1)), gy = ty * kTY + (p >> 5);
+        unsigned short* m16 = reinterpret_cast<unsigned short*>(gmeta + gid);
+        m16[4 + slot] = (unsigned short)out_slot(p);
+        gfrac[gid * 4 + slot] = frac_tab[(long long)gy * ox + gx];
+        if (slot == 0) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                m16[r] = (unsigned short)find(cell[k] + r * ix);
+        }
+        if (contrib[k]) { // last point of its cell: pad the group
+            for (int s = slot + 1; s < 4; ++s) {
+                m16[4 + s] = (unsigned short)kDump;
+                gfrac[gid * 4 + s] = make_double2(0., 0.);
+            }
+        }
+    }
+}
+
+constexpr size_t kCompileSmem = sizeof(unsigned long long) * kSortN + sizeof(int) * (kMaxTapKeys + 3 * kSortN + kTapCap);
+
+// ------------------------------------------------------------------------------------------------ gather
+struct Group {
+    double wx[4][4], wy[4][4];
+    int row[4]; // first tap of each stencil row, in doubles from the start of a field's staging area
+    int pt[4];  // output-tile slots
+};
+
+template <int S>
+__device__ __forceinline__ void load_group(Group& gr, const uint4* __restrict__ gmeta, const double2* __restrict__ gfrac, size_t gid)
+{
+    const uint4 m = __ldg(gmeta + gid);
+    gr.row[0] = (int)(m.x & 0xffffu) * S;
+    gr.row[1] = (int)(m.x >> 16) * S;
+    gr.row[2] = (int)(m.y & 0xffffu) * S;
+    gr.row[3] = (int)(m.y >> 16) * S;
+    gr.pt[0] = (int)(m.z & 0xffffu);
+    gr.pt[1] = (int)(m.z >> 16);
+    gr.pt[2] = (int)(m.w & 0xffffu);
+    gr.pt[3] = (int)(m.w >> 16);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const double2 f = __ldg(gfrac + gid * 4 + p);
+        cubic_weights(f.x, gr.wx[p]);
+        cubic_weights(f.y, gr.wy[p]);
+    }
+}
+
+// NL levels of one group: 4 points x NF fields x NL levels = 4*NF*NL independent accumulator chains for the scheduler
+template <int NF, bool ROT, int S, int NL>
+__device__ __forceinline__ void compute_levels(const Group& gr, const double* __restrict__ st, int field_stride, float* __restrict__ s_out,
+                                               int out_field_stride, const double2* __restrict__ s_cs)
+{
+    float a[NL][NF][4];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        const double* sf = st + f * field_stride;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const double* rp = sf + gr.row[r];
+#pragma unroll
+            for (int l = 0; l < NL; ++l) {
+                const double v0 = rp[l], v1 = rp[S + l], v2 = rp[2 * S + l], v3 = rp[3 * S + l];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const double row = bicubic_row(gr.wx[p], v0, v1, v2, v3);
+                    a[l][f][p] = (r == 0) ? bicubic_acc<true>(0.f, row, gr.wy[p][0]) : bicubic_acc<false>(a[l][f][p], row, gr.wy[p][r]);
+                }
+            }
+        }
+    }
+    if (ROT) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const double2 c = s_cs[gr.pt[p]];
+#pragma unroll
+            for (int l = 0; l < NL; ++l)
+                rotate_uv(a[l][0][p], a[l][NF - 1][p], c.x, c.y);
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < NL; ++l)
+#pragma unroll
+        for (int f = 0; f < NF; ++f)
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+                s_out[f * out_field_stride + l * kOutRow + gr.pt[p]] = a[l][f][p];
+}
+
+// Tiles whose taps do not fit the staging buffers: every point reads its 16 taps from global memory (the arithmetic of
+// the direct kernel, gather_kernels.cu); lane = x, so a warp still writes 128 contiguous bytes per level.
+template <int NF, bool ROT>
+__device__ void direct_tile(const GatherGeom& g, int tx, int ty, long long z0, long long z1, const int* __restrict__ off_tab,
+                            const double2* __restrict__ frac_tab, const double2* __restrict__ cs, const float* __restrict__ in0,
+                            const float* __restrict__ in1, float* __restrict__ out0, float* __restrict__ out1)
+{
+    for (int p = threadIdx.x; p < kTP; p += kT) {
+        const int gx = tx * kTX + (p & (kTX - 1)), gy = ty * kTY + (p >> 5);
+        if (gx >= g.ox || gy >= g.oy)
+            continue;
+        const long long q = (long long)gy * g.ox + gx;
+        const int off = __ldg(off_tab + q);
+        float* o0 = out0 + z0 * g.out_level + q;
+        float* o1 = (NF == 2) ? out1 + z0 * g.out_level + q : nullptr;
+        if (off < 0) { // :1022-1026
+            for (long long z = z0; z < z1; ++z) {
+                __stcs(o0, undef_f());
+                o0 += g.out_level;
+                if (NF == 2) {
+                    __stcs(o1, undef_f());
+                    o1 += g.out_level;
+                }
+            }
+            continue;
+        }
+        const double2 f = __ldg(frac_tab + q);
+        double wx[4], wy[4];
+        cubic_weights(f.x, wx);
+        cubic_weights(f.y, wy);
+        double2 rot = make_double2(1., 0.);
+        if (ROT)
+            rot = __ldg(cs + q);
+        const float* p0 = in0 + z0 * g.in_level + off;
+        const float* p1 = (NF == 2) ? in1 + z0 * g.in_level + off : nullptr;
+        for (long long z = z0; z < z1; ++z) {
+            float a = bicubic_eval(p0, g.ix, wx, wy);
+            float b = 0.f;
+            if (NF == 2)
+                b = bicubic_eval(p1, g.ix, wx, wy);
+            if (ROT)
+                rotate_uv(a, b, rot.x, rot.y);
+            __stcs(o0, a);
+            p0 += g.in_level;
+            o0 += g.out_level;
+            if (NF == 2) {
+                __stcs(o1, b);
+                p1 += g.in_level;
+                o1 += g.out_level;
+            }
+        }
+    }
+}
+
+// FAST: at most 256 taps; 8/NF levels per batch; warp w stages (field, level) row w of the batch and later stores
+//       (field, level) row w of the output tile.
+// else: up to 2048/NF taps, one level per batch, every thread stages 8/NF taps per field.
+template <int NF, bool ROT, bool FAST>
+__device__ __forceinline__ void staged_tile(const GatherGeom& g, int tx, int ty, long long z0, long long z1, int4 inf,
+                                            const int* __restrict__ taps, const uint4* __restrict__ gmeta, const double2* __restrict__ gfrac,
+                                            const double2* __restrict__ cs, const float* __restrict__ in0, const float* __restrict__ in1,
+                                            float* __restrict__ out0, float* __restrict__ out1, bool vec_ok, double* s_stage, float* s_out,
+                                            double2* s_cs)
+{
+    constexpr int L = FAST ? 8 / NF : 1;
+    constexpr int S = (L == 1) ? 1 : L + 1; // odd tap stride (in doubles): distinct taps of a warp land in distinct banks
+    constexpr int NREG = 8;
+    static_assert(NF * L <= kOutRows, "output tile");
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int ntaps = inf.y, ngroups = inf.w;
+    const int field_stride = ntaps * S;
+    const int rounds = (ngroups + kT - 1) / kT;
+
+    // output tiles: NaN everywhere; points outside the 4x4 support are in no group and stay NaN (:1022-1026)
+    for (int i = t; i < 2 * kOutRows * kOutRow; i += kT)
+        s_out[i] = undef_f();
+    if (ROT) {
+        for (int p = t; p < kOutRow; p += kT) {
+            double2 c = make_double2(1., 0.);
+            int slot = p;
+            if (p < kTP) {
+                const int gx = tx * kTX + (p & (kTX - 1)), gy = ty * kTY + (p >> 5);
+                if (gx < g.ox && gy < g.oy)
+                    c = __ldg(cs + (long long)gy * g.ox + gx);
+                slot = out_slot(p);
+            }
+            s_cs[slot] = c;
+        }
+    }
+    Group gr;
+    if (rounds == 1 && t < ngroups)
+        load_group<S>(gr, gmeta, gfrac, (size_t)inf.z + t);
+
+    // staging: which (field, level-in-batch, tap) this thread's register j carries
+    const int my_f = FAST ? warp / L : 0, my_zi = FAST ? warp % L : 0; // FAST: one (field, level) row per warp
+    auto tap_of = [&](int j) { return FAST ? lane + 32 * j : t + kT * (j % (NREG / NF)); };
+    auto field_of = [&](int j) { return FAST ? my_f : j / (NREG / NF); };
+    float regs[NREG];
+    auto load = [&](long long z) {
+        if (z + my_zi >= z1)
+            return;
+#pragma unroll
+        for (int j = 0; j < NREG; ++j) {
+            const int r = tap_of(j);
+            if (r < ntaps) {
+                const float* base = (field_of(j) == 0 ? in0 : in1) + (z + my_zi) * g.in_level;
+                regs[j] = __ldg(base + __ldg(taps + inf.x + r));
+            }
+        }
+    };
+    auto park = [&](int buf) { // the ONE fp32 -> fp64 conversion of each tap value
+        double* dst = s_stage + buf * kStageDoubles + my_zi;
+#pragma unroll
+        for (int j = 0; j < NREG; ++j) {
+            const int r = tap_of(j);
+            if (r < ntaps)
+                dst[field_of(j) * field_stride + r * S] = (double)regs[j];
+        }
+    };
+
+    // store phase: warp w writes (field, level) row w of the finished output tile, 7 x 128-bit per lane.  Lane l owns
+    // tile rows (l >> 3) + 4k; the column group alternates between two values with the parity of k (out_slot()).
+    const int st_f = warp / L, st_zi = warp % L;
+    float* const st_out = (NF == 2 && st_f == 1) ? out1 : out0;
+    const int ly0 = lane >> 3;
+    const int gx_even = tx * kTX + (((lane & 7) ^ ly0) << 2), gx_odd = tx * kTX + (((lane & 7) ^ (ly0 + 4)) << 2);
+    const int gy0 = ty * kTY + ly0;
+    const bool whole = vec_ok && (tx + 1) * kTX <= g.ox && (ty + 1) * kTY <= g.oy; // tile entirely inside the grid
+    const long long st_row0 = (long long)gy0 * g.ox;
+    auto store_out = [&](const float* tile, long long z, int nb) {
+        if (warp >= NF * L || st_zi >= nb)
+            return;
+        const float* src = tile + (st_f * L + st_zi) * kOutRow + lane * 4;
+        float* lvl = st_out + (z + st_zi) * g.out_level + st_row0;
+        if (whole) {
+#pragma unroll
+            for (int k = 0; k < kTP / 128; ++k)
+                __stcs(reinterpret_cast<float4*>(lvl + (long long)(4 * k) * g.ox + ((k & 1) ? gx_odd : gx_even)),
+                       *reinterpret_cast<const float4*>(src + 128 * k));
+            return;
+        }
+#pragma unroll
+        for (int k = 0; k < kTP / 128; ++k) {
+            const int gx = (k & 1) ? gx_odd : gx_even;
+            if (gy0 + 4 * k >= g.oy || gx >= g.ox)
+                continue;
+            const float4 v = *reinterpret_cast<const float4*>(src + 128 * k);
+            float* dst = lvl + (long long)(4 * k) * g.ox + gx;
+            if (vec_ok && gx + 3 < g.ox) {
+                __stcs(reinterpret_cast<float4*>(dst), v);
+            } else {
+                __stcs(dst, v.x);
+                if (gx + 1 < g.ox)
+                    __stcs(dst + 1, v.y);
+                if (gx + 2 < g.ox)
+                    __stcs(dst + 2, v.z);
+                if (gx + 3 < g.ox)
+                    __stcs(dst + 3, v.w);
+            }
+        }
+    };
+
+    load(z0);
+    park(0);
+    if (z0 + L < z1)
+        load(z0 + L);
+    __syncthreads();
+    int buf = 0;
+    for (long long z = z0; z < z1; z += L, buf ^= 1) {
+        const int nb = (int)((z1 - z) < L ? (z1 - z) : L);
+        const double* st = s_stage + buf * kStageDoubles;
+        float* tile = s_out + buf * (kOutRows * kOutRow);
+        for (int rd = 0; rd < rounds; ++rd) {
+            const int gi = rd * kT + t;
+            if (gi < ngroups) {
+                if (rounds > 1)
+                    load_group<S>(gr, gmeta, gfrac, (size_t)inf.z + gi);
+                if (L > 1 && nb == L) { // full batch: branch-free, two levels per step
+#pragma unroll 1
+                    for (int zi = 0; zi < L; zi += 2)
+                        compute_levels<NF, ROT, S, (L > 1 ? 2 : 1)>(gr, st + zi, field_stride, tile + zi * kOutRow, L * kOutRow, s_cs);
+                } else {
+#pragma unroll 1
+                    for (int zi = 0; zi < nb; ++zi)
+                        compute_levels<NF, ROT, S, 1>(gr, st + zi, field_stride, tile + zi * kOutRow, L * kOutRow, s_cs);
+                }
+            }
+        }
+        if (z + L < z1) {
+            park(buf ^ 1);
+            if (z + 2 * L < z1)
+                load(z + 2 * L);
+        }
+        __syncthreads(); // this batch's output tile is complete and the next batch is parked; the other output tile (being
+                         // stored by slower warps) is not written before the next barrier
+        store_out(tile, z, nb);
+    }
+}
+
+template <int NF, bool ROT>
+__global__ void __launch_bounds__(kT, 2) k_gather_bicubic_staged(GatherGeom g, int tiles_x, const int4* __restrict__ info,
+                                                                 const int* __restrict__ taps, const uint4* __restrict__ gmeta,
+                                                                 const double2* __restrict__ gfrac, const int* __restrict__ off_tab,
+                                                                 const double2* __restrict__ frac_tab, const double2* __restrict__ cs,
+                                                                 const float* __restrict__ in0, const float* __restrict__ in1,
+                                                                 float* __restrict__ out0, float* __restrict__ out1, int vec_ok, long long per)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_stage = reinterpret_cast<double*>(smem_raw);                                     // [2][kStageDoubles]
+    float* s_out = reinterpret_cast<float*>(smem_raw + sizeof(double) * 2 * kStageDoubles);    // [2][8][kOutRow]
+    double2* s_cs = reinterpret_cast<double2*>(s_out + 2 * kOutRows * kOutRow);                // [kOutRow] (ROT)
+    const int tile = blockIdx.x;
+    const int4 inf = __ldg(info + tile);
+    const int tx = tile % tiles_x, ty = tile / tiles_x;
+    const long long z0 = (long long)blockIdx.y * per;
+    const long long z1 = z0 + per < g.nz ? z0 + per : g.nz;
+    if (z0 >= z1)
+        return;
+    if (inf.y < 0 || NF * inf.y > kStageElems)
+        direct_tile<NF, ROT>(g, tx, ty, z0, z1, off_tab, frac_tab, cs, in0, in1, out0, out1);
+    else if (inf.y <= kFastTaps)
+        staged_tile<NF, ROT, true>(g, tx, ty, z0, z1, inf, taps, gmeta, gfrac, cs, in0, in1, out0, out1, vec_ok != 0, s_stage, s_out, s_cs);
+    else
+        staged_tile<NF, ROT, false>(g, tx, ty, z0, z1, inf, taps, gmeta, gfrac, cs, in0, in1, out0, out1, vec_ok != 0, s_stage, s_out, s_cs);
+}
+
+constexpr size_t kGatherSmem = sizeof(double) * 2 * kStageDoubles + sizeof(float) * 2 * kOutRows * kOutRow;
+constexpr size_t kGatherSmemRot = kGatherSmem + sizeof(double2) * kOutRow;
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------- host side
+void bicubic_tiles_free(BicubicTiles* bt)
+{
+    if (bt->d_info)
+        cudaFree(bt->d_info);
+    if (bt->d_taps)
+        cudaFree(bt->d_taps);
+    if (bt->d_gmeta)
+        cudaFree(bt->d_gmeta);
+    if (bt->d_gfrac)
+        cudaFree(bt->d_gfrac);
+    *bt = BicubicTiles();
+}
+
+bool bicubic_tiles_supported(int ix, int iy, int ox, int oy)
+{
+    const long long in_level = (long long)ix * iy;
+    const long long tiles = (long long)((ox + kTX - 1) / kTX) * ((oy + kTY - 1) / kTY);
+    // cell offsets are packed above 10 bits of point index in a 64-bit key and taps are ints: any int-sized level works
+    return in_level > 0 && in_level < 2147483647LL - 4ll * ix && ox > 0 && oy > 0 && tiles < 2147483647LL;
+}
+
+// synchronises (setup path)
+int bicubic_tiles_build(const int* d_off, const double2* d_frac, int ix, int iy, int ox, int oy, BicubicTiles* bt, cudaStream_t st)
+{
+    bicubic_tiles_free(bt);
+    const int tiles_x = (ox + kTX - 1) / kTX, tiles_y = (oy + kTY - 1) / kTY;
+    const size_t tiles = (size_t)tiles_x * tiles_y;
+    FB_CUDA_CHECK(cudaFuncSetAttribute(k_compile_bicubic_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCompileSmem));
+    FB_CUDA_CHECK(cudaFuncSetAttribute(k_compile_bicubic_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCompileSmem));
+    int2* d_counts = nullptr;
+    FB_CUDA_CHECK(cudaMalloc(&d_counts, sizeof(int2) * tiles));
+    k_compile_bicubic_tiles<false><<<(unsigned)tiles, kT, kCompileSmem, st>>>(d_off, d_frac, ox, oy, ix, tiles_x, d_counts, nullptr, nullptr,
+                                                                             nullptr, nullptr);
+    count_launch();
+    std::vector<int2> counts(tiles);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(counts.data(), d_counts, sizeof(int2) * tiles, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(st);
+    cudaFree(d_counts);
+    FB_CUDA_CHECK(e);
+    std::vector<int4> info(tiles);
+    long long ntaps = 0, ngroups = 0;
+    int ndirect = 0;
+    for (size_t i = 0; i < tiles; ++i) {
+        FB_REQUIRE(ntaps < 2147483647LL - kTapCap && ngroups < 2147483647LL - kTP, "bicubic tile table too large");
+        info[i] = make_int4((int)ntaps, counts[i].x, (int)ngroups, counts[i].y);
+        if (counts[i].x < 0) {
+            ++ndirect;
+            continue;
+        }
+        ntaps += counts[i].x;
+        ngroups += counts[i].y;
+    }
+    bt->tiles_x = tiles_x;
+    bt->tiles_y = tiles_y;
+    bt->n_taps = ntaps;
+    bt->n_groups = ngroups;
+    bt->n_direct = ndirect;
+    FB_CUDA_CHECK(cudaMalloc(&bt->d_info, sizeof(int4) * tiles));
+    FB_CUDA_CHECK(cudaMalloc(&bt->d_taps, sizeof(int) * (size_t)(ntaps > 0 ? ntaps : 1)));
+    FB_CUDA_CHECK(cudaMalloc(&bt->d_gmeta, sizeof(uint4) * (size_t)(ngroups > 0 ? ngroups : 1)));
+    FB_CUDA_CHECK(cudaMalloc(&bt->d_gfrac, sizeof(double2) * 4 * (size_t)(ngroups > 0 ? ngroups : 1)));
+    FB_CUDA_CHECK(cudaMemcpyAsync(bt->d_info, info.data(), sizeof(int4) * tiles, cudaMemcpyHostToDevice, st));
+    k_compile_bicubic_tiles<true><<<(unsigned)tiles, kT, kCompileSmem, st>>>(d_off, d_frac, ox, oy, ix, tiles_x, nullptr, bt->d_info, bt->d_taps,
+                                                                            bt->d_gmeta, bt->d_gfrac);
+    count_launch();
+    FB_CUDA_CHECK(cudaGetLastError());
+    FB_CUDA_CHECK(cudaStreamSynchronize(st)); // `info` (host) is read by the copy above
+    return FB_OK;
+}
+
+// scalar field (d_in1 == d_out1 == nullptr) or the two components of a vector, optionally rotated (d_cs != nullptr)
+int launch_gather_bicubic_staged(const GatherGeom& g, const BicubicTiles& bt, const int* d_off, const double2* d_frac, const double2* d_cs,
+                                 const float* d_in0, const float* d_in1, float* d_out0, float* d_out1, cudaStream_t st)
+{
+    if (g.out_level == 0 || g.nz == 0)
+        return FB_OK;
+    const unsigned tiles = (unsigned)bt.tiles_x * (unsigned)bt.tiles_y;
+    // Level chunks: 64 levels like the other gathers (longer chunks are slower here too: CTAs drift apart in z and the set of
+    // DRAM pages being written grows -- 3288-level chunks cost 20 % more time), always a multiple of the 8-level batch so
+    // that only the last chunk has a partial batch; shorter chunks only to fill the SMs of small grids.
+    long long per = 64;
+    const long long want = 4ll * sm_count();
+    while (per > 8 && tiles * ((g.nz + per - 1) / per) < want)
+        per -= 8;
+    long long gy = (g.nz + per - 1) / per;
+    if (const char* env = std::getenv("FIMEX_B200_ZCHUNK"))
+        if (std::atoll(env) > 0)
+            per = std::atoll(env), gy = (g.nz + per - 1) / per;
+    if (gy > 65535) {
+        gy = 65535;
+        per = (g.nz + gy - 1) / gy;
+    }
+    dim3 grid(tiles, (unsigned)gy);
+    const bool two = d_in1 != nullptr;
+    uintptr_t align = reinterpret_cast<uintptr_t>(d_out0) | (two ? reinterpret_cast<uintptr_t>(d_out1) : 0);
+    const int vec_ok = ((g.ox % 4) == 0 && (align & 15u) == 0) ? 1 : 0;
+#define FB_BIC_LAUNCH(NF, ROT, SMEM)                                                                                                       \
+    do {                                                                                                                                   \
+        FB_CUDA_CHECK(cudaFuncSetAttribute(k_gather_bicubic_staged<NF, ROT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM)));   \
+        k_gather_bicubic_staged<NF, ROT><<<grid, kT, SMEM, st>>>(g, bt.tiles_x, bt.d_info, bt.d_taps, bt.d_gmeta, bt.d_gfrac, d_off, d_frac, \
+                                                                  d_cs, d_in0, d_in1, d_out0, d_out1, vec_ok, per);                         \
+    } while (0)
+    if (!two)
+        FB_BIC_LAUNCH(1, false, kGatherSmem);
+    else if (d_cs)
+        FB_BIC_LAUNCH(2, true, kGatherSmemRot);
+    else
+        FB_BIC_LAUNCH(2, false, kGatherSmem);
+#undef FB_BIC_LAUNCH
+    count_launch();
+    FB_CUDA_CHECK(cudaGetLastError());
+    return FB_OK;
+}
+
+} // namespace fb

@@ -16,6 +16,7 @@
 // equivalents) so that nvcc cannot contract to FMA: results are bit-identical to the reference built for
 // x86-64, which has no FMA either (SURVEY.md 8a trap 7).
 #include "kernels.h"
+#include "interp_math.cuh"
 
 #include <cstdlib>
 
@@ -29,14 +30,6 @@ constexpr int kThreads = 256;
 __device__ __forceinline__ float ldg_f(const float* p)
 {
     return __ldg(p);
-}
-
-// (1-yf) * ((1-xf)*s00 + xf*s01) + yf * ((1-xf)*s10 + xf*s11), interpolation.c:899-900
-__device__ __forceinline__ float bilinear_full(float wx0, float xf, float wy0, float yf, float s00, float s01, float s10, float s11)
-{
-    const float top = __fadd_rn(__fmul_rn(wx0, s00), __fmul_rn(xf, s01));
-    const float bot = __fadd_rn(__fmul_rn(wx0, s10), __fmul_rn(xf, s11));
-    return __fadd_rn(__fmul_rn(wy0, top), __fmul_rn(yf, bot));
 }
 
 __device__ __forceinline__ float bilinear_any(int mode, const float* __restrict__ s, int ix, float wx0, float xf, float wy0, float yf)
@@ -53,16 +46,6 @@ __device__ __forceinline__ float bilinear_any(int mode, const float* __restrict_
     default:
         return undef_f();
     }
-}
-
-// u' = u*c - v*s ; v' = u*s + v*c in fp64, rounded to fp32 (interpolation.c:804-808)
-__device__ __forceinline__ void rotate_uv(float& u, float& v, double c, double s)
-{
-    const double ud = (double)u, vd = (double)v;
-    const double un = __dsub_rn(__dmul_rn(ud, c), __dmul_rn(vd, s));
-    const double vn = __dadd_rn(__dmul_rn(ud, s), __dmul_rn(vd, c));
-    u = __double2float_rn(un);
-    v = __double2float_rn(vn);
 }
 
 template <int VEC>
@@ -235,47 +218,6 @@ __global__ void __launch_bounds__(kThreads) k_gather_bilinear(GatherGeom g, cons
 }
 
 // ------------------------------------------------------------------------------------------------ K5
-// cubic convolution weights for a = -0.5: w[i] = sum_j T[j] * (M[j][i] / 2), accumulated from 0 in j order
-// exactly as interpolation.c:962-968, 981-1000
-__device__ __forceinline__ void cubic_weights(double t, double (&w)[4])
-{
-    const double M[4][4] = {{0., 1., 0., 0.}, {-.5, 0., .5, 0.}, {1., -2.5, 2., -.5}, {-.5, 1.5, -1.5, .5}};
-    double T[4];
-    T[0] = 1.;
-    T[1] = t;
-    T[2] = __dmul_rn(t, t);
-    T[3] = __dmul_rn(T[2], t);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        double acc = 0.;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            acc = __dadd_rn(acc, __dmul_rn(T[j], M[j][i]));
-        w[i] = acc;
-    }
-}
-
-// fp64 row sums, fp32 accumulator re-rounded after each of the four rows (interpolation.c:1002-1021)
-__device__ __forceinline__ float bicubic_eval(const float* __restrict__ s, int ix, const double (&wx)[4], const double (&wy)[4])
-{
-    float v[4][4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-            v[r][c] = ldg_f(s + r * ix + c);
-    float acc = 0.f;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        double row = 0.;
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-            row = __dadd_rn(row, __dmul_rn(wx[c], (double)v[r][c]));
-        acc = __double2float_rn(__dadd_rn((double)acc, __dmul_rn(row, wy[r])));
-    }
-    return acc;
-}
-
 template <int NFIELD, bool ROT>
 __global__ void __launch_bounds__(kThreads) k_gather_bicubic(GatherGeom g, const int* __restrict__ off_tab, const double2* __restrict__ frac,
                                                            const double2* __restrict__ cs, const float* __restrict__ in0,

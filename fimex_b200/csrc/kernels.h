@@ -79,6 +79,25 @@ void tile_table_free(TileTable* tt);
 // staged gather for bilinear and nearest-neighbour tables
 int launch_gather_bilinear_staged(const GatherGeom& g, const TileTable& tt, const float* d_in, float* d_out, cudaStream_t st);
 
+// ---- bicubic_staged.cu (K5 fast path) ------------------------------------------------------------------
+struct BicubicTiles {
+    int tiles_x = 0, tiles_y = 0;
+    int4* d_info = nullptr;     // [tile] {first tap, ntaps (-1: direct fallback), first group, ngroups}
+    int* d_taps = nullptr;      // per tile: sorted distinct source offsets
+    uint4* d_gmeta = nullptr;   // [group] 8 x u16: 4 stencil-row tap indices, 4 point slots
+    double2* d_gfrac = nullptr; // [group][4] (xfrac, yfrac)
+    long long n_taps = 0, n_groups = 0;
+    int n_direct = 0;           // tiles computed with direct global loads (tap list too long to stage)
+    bool ready() const { return d_info != nullptr; }
+};
+bool bicubic_tiles_supported(int ix, int iy, int ox, int oy);
+// d_off / d_frac: the per-point bicubic table of launch_compile_bicubic; synchronises
+int bicubic_tiles_build(const int* d_off, const double2* d_frac, int ix, int iy, int ox, int oy, BicubicTiles* bt, cudaStream_t st);
+void bicubic_tiles_free(BicubicTiles* bt);
+// scalar field (d_in1 == d_out1 == nullptr) or both components of a vector, rotated when d_cs != nullptr
+int launch_gather_bicubic_staged(const GatherGeom& g, const BicubicTiles& bt, const int* d_off, const double2* d_frac, const double2* d_cs,
+                                 const float* d_in0, const float* d_in1, float* d_out0, float* d_out1, cudaStream_t st);
+
 // ---- forward_kernels.cu (K8) ---------------------------------------------------------------------------
 struct ForwardPlan {
     long long n_in = 0, n_cells = 0;

@@ -1,0 +1,2 @@
+python bench.py --method bicubic --times 2 --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/b_small.json 2>gpurun_out/b_small.err && ncu --set full --clock-control none --import-source on -k regex:k_gather_bicubic_staged -s 3 -c 1 -o gpurun_out/prof_bicubic_v2 python bench.py --method bicubic --times 2 --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu.log 2>&1
+echo "full rc=$?"

@@ -241,6 +241,53 @@ def test_cached_interpolation_bit_exact(oracle, method, shape):
     _mask_ub(oracle, method, px, py, inX, inY, got)
 
 
+def _smooth_positions(inX, inY, outX, outY, angle_deg, zoom, seed):
+    """target grid = rotated, finer copy of the source grid (several target points per source cell), slightly warped"""
+    rng = np.random.default_rng(seed)
+    a = np.radians(angle_deg)
+    jj, ii = np.meshgrid(np.arange(outX, dtype=np.float64), np.arange(outY, dtype=np.float64))
+    u, v = (jj - outX / 2) / zoom, (ii - outY / 2) / zoom
+    px = inX / 2 + np.cos(a) * u - np.sin(a) * v + 0.3 * np.sin(v / 7)
+    py = inY / 2 + np.sin(a) * u + np.cos(a) * v + 0.3 * np.cos(u / 5)
+    px, py = px.ravel(), py.ravel()
+    k = rng.integers(0, px.size, 50)
+    px[k] = np.round(px[k])  # exact grid hits: zero weights, NaN taps still poison (trap 1)
+    return px, py
+
+
+@pytest.mark.parametrize("method", [Method.BICUBIC, Method.BILINEAR, Method.NEAREST_NEIGHBOR])
+@pytest.mark.parametrize("inX,inY,inZ,outX,outY,angle,zoom", [
+    (60, 50, 19, 200, 150, 17.0, 5.0),    # fast path: few taps per tile, partial batches (19 = 2*8 + 3), whole tiles
+    (60, 50, 70, 203, 77, -33.0, 6.5),    # outX not a multiple of 4 (scalar stores), partial tiles, two level chunks
+    (300, 40, 9, 256, 96, 3.0, 0.6),      # target coarser than source: hundreds of taps per tile (one-level batches)
+    (1500, 8, 3, 64, 48, 80.0, 0.02),     # thousands of taps per tile: direct fallback inside the staged kernel
+])
+def test_staged_gathers_on_structured_grids(oracle, method, inX, inY, inZ, outX, outY, angle, zoom):
+    """The staged (shared-memory) kernels take their fast paths only on structured grids; random positions
+    (test_cached_interpolation_bit_exact) exercise their many-taps paths."""
+    px, py = _smooth_positions(inX, inY, outX, outY, angle, zoom, 3)
+    rng = np.random.default_rng(8)
+    field = rng.normal(250, 30, (inZ, inY, inX)).astype(np.float32)
+    field[rng.random(field.shape) < 0.01] = np.nan
+    ci = fb.CachedInterpolation("x", "y", method, px, py, inX, inY, outX, outY)
+    got = ci.interpolateValues(field)
+    want = oracle.cached_interpolate(int(method), px, py, inX, inY, outX, outY, field)
+    assert_bit_equal(got, want, f"structured grid, method {method}", nan_payload=(method == Method.NEAREST_NEIGHBOR))
+    # both components of a vector in one pass, with and without the rotation
+    v = rng.normal(0, 8, field.shape).astype(np.float32)
+    phi = rng.uniform(-np.pi, np.pi, outX * outY)
+    matrix = np.stack([np.cos(phi), np.sin(phi), -np.sin(phi), phi], axis=1).ravel()
+    vi = oracle.cached_interpolate(int(method), px, py, inX, inY, outX, outY, v)
+    wu, wv = oracle.vector_reproject_by_matrix(matrix, want, vi, outX, outY, inZ)
+    cvr = fb.CachedVectorReprojection(fb.MIFI_VECTOR_KEEP_SIZE, matrix, outX, outY)
+    gu, gv = ci.interpolateVector(field, v, cvr)
+    assert_bit_equal(gu, wu.reshape(gu.shape), "fused u")
+    assert_bit_equal(gv, wv.reshape(gv.shape), "fused v")
+    pu, pv = ci.interpolateVector(field, v, None)
+    assert_bit_equal(pu, want, "no-rotation u")
+    assert_bit_equal(pv, vi, "no-rotation v")
+
+
 def test_cached_interpolation_device_path_equals_host_path(oracle):
     import torch
     inX, inY, inZ, outX, outY = 120, 90, 40, 300, 200  # 60000 points: the 128-bit store path; 40 levels
