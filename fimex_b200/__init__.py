@@ -13,7 +13,7 @@ The product is ``fimex_b200/lib/libfimex_b200.so`` (hand-written sm_100a CUDA be
 * :mod:`fimex_b200.slab`    -- one-process-per-GPU slab partition of the (time x level) stack with a single
   NCCL broadcast of the cached tables.
 """
-from .capi import (LATITUDE, LONGITUDE, PROJ_AXIS, MIFI_ERROR, MIFI_OK, MIFI_VECTOR_KEEP_SIZE, FimexB200Error, Method, kernel_launches,
+from .capi import (DataType, cdm_type, default_fill_value, LATITUDE, LONGITUDE, PROJ_AXIS, MIFI_ERROR, MIFI_OK, MIFI_VECTOR_KEEP_SIZE, FimexB200Error, Method, kernel_launches,
                    last_error, lib_path, load, mifi_get_values_bicubic_f, mifi_get_values_bilinear_f, mifi_get_values_f,
                    mifi_get_vector_reproject_matrix, mifi_get_vector_reproject_matrix_field, mifi_get_vector_reproject_matrix_points,
                    mifi_interpolate_f, mifi_points2position, mifi_project_axes, mifi_project_values, mifi_string_to_interpolation_method,
@@ -23,7 +23,7 @@ from .cached import CachedForwardInterpolation, CachedInterpolation, CachedVecto
 from .interpolator import Interpolator
 
 __all__ = [
-    "CachedInterpolation", "CachedForwardInterpolation", "CachedVectorReprojection", "Interpolator", "Method", "FimexB200Error",
+    "CachedInterpolation", "CachedForwardInterpolation", "CachedVectorReprojection", "Interpolator", "Method", "DataType", "cdm_type", "default_fill_value", "FimexB200Error",
     "MIFI_OK", "MIFI_ERROR", "PROJ_AXIS", "LONGITUDE", "LATITUDE", "MIFI_VECTOR_KEEP_SIZE", "load", "lib_path", "version", "last_error",
     "set_device", "kernel_launches", "mifi_interpolate_f", "mifi_points2position", "mifi_project_axes", "mifi_project_values",
     "mifi_get_vector_reproject_matrix", "mifi_get_vector_reproject_matrix_field", "mifi_get_vector_reproject_matrix_points",

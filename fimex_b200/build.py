@@ -20,7 +20,7 @@ LIB = os.path.join(LIBDIR, "libfimex_b200.so")
 
 SOURCES = ["api.cu", "setup_kernels.cu", "gather_kernels.cu", "forward_kernels.cu", "coordnn_kernels.cu", "adapter_kernels.cu", "staged_kernels.cu", "bicubic_staged.cu",
            "proj_parse.cpp"]
-HEADERS = ["common.cuh", "proj.cuh", "kernels.h", "tables.cuh", "interp_math.cuh", os.path.join("..", "..", "include", "fimex_b200.h")]
+HEADERS = ["common.cuh", "proj.cuh", "kernels.h", "tables.cuh", "interp_math.cuh", "convert.cuh", os.path.join("..", "..", "include", "fimex_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",

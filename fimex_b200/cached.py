@@ -136,6 +136,34 @@ class CachedInterpolationInterface:
         return out.reshape(-1)[:n].reshape(nz, self.getOutY(), self.getOutX())
 
 
+    # -- the whole slice body of CDMInterpolator::getDataSlice in one call ---------------------------
+    def getDataSlice(self, inData, badValue, outType=None, stream=None):
+        """data2InterpolationArray -> interpolateValues -> interpolationArray2Data (CDMInterpolator.cc:250-258, 284-285):
+        `inData` [inZ][inY][inX] of any CDM numeric type (numpy array or CUDA tensor), `badValue` = CDM::getFillValue of the
+        variable, result [inZ][outY][outX] in `outType` (default: the input's type)."""
+        lib = load()
+        new_size = C.c_size_t()
+        if _is_torch(inData):
+            import torch
+            if not inData.is_cuda or not inData.is_contiguous():
+                raise FimexB200Error("device path needs a contiguous CUDA tensor")
+            out_dtype = outType if outType is not None else inData.dtype
+            n = int(lib.fb200_interp_new_size(self._h, inData.numel()))
+            out = torch.empty(n, dtype=out_dtype, device=inData.device)
+            check(lib.fb200_interp_get_data_slice_device(self._h, int(capi.cdm_type(inData.dtype)), ptr(inData), inData.numel(), float(badValue),
+                                                         int(capi.cdm_type(out_dtype)), ptr(out), C.byref(new_size), _stream_ptr(stream)),
+                  "getDataSlice")
+        else:
+            a = np.ascontiguousarray(inData)
+            out_dtype = np.dtype(outType) if outType is not None else a.dtype
+            n = int(lib.fb200_interp_new_size(self._h, a.size))
+            out = np.empty(n, dtype=out_dtype)
+            check(lib.fb200_interp_get_data_slice(self._h, int(capi.cdm_type(a.dtype)), ptr(a), a.size, float(badValue),
+                                                  int(capi.cdm_type(out_dtype)), ptr(out), C.byref(new_size)), "getDataSlice")
+        nz = n // max(1, self.getOutX() * self.getOutY())
+        return out.reshape(nz, self.getOutY(), self.getOutX())
+
+
 class CachedInterpolation(CachedInterpolationInterface):
     """CachedInterpolation(xDimName, yDimName, funcType, pointsOnXAxis, pointsOnYAxis, inX, inY, outX, outY)
     -- include/fimex/CachedInterpolation.h:126-128"""
@@ -220,6 +248,39 @@ class CachedInterpolation(CachedInterpolationInterface):
             vo = np.empty(n, dtype=np.float32)
             check(lib.fb200_interp_interpolate_vector(self._h, vh, ptr(u), ptr(v), u.size, ptr(uo), ptr(vo), C.byref(new_size)),
                   "interpolateVector")
+        nz = n // max(1, self.getOutX() * self.getOutY())
+        shape = (nz, self.getOutY(), self.getOutX())
+        return uo.reshape(shape), vo.reshape(shape)
+
+
+    def getVectorSlice(self, uIn, vIn, badValueU, badValueV, vectorReprojection=None, outType=None, stream=None):
+        """The vector branch of CDMInterpolator::getDataSlice (:250-285) for both components at once: fill -> NaN,
+        interpolate, rotate, NaN -> fill + cast."""
+        lib = load()
+        new_size = C.c_size_t()
+        vh = vectorReprojection._h if vectorReprojection is not None else None
+        if _is_torch(uIn):
+            import torch
+            if uIn.dtype != vIn.dtype or uIn.numel() != vIn.numel():
+                raise FimexB200Error("u and v differ in type or size")
+            out_dtype = outType if outType is not None else uIn.dtype
+            n = int(lib.fb200_interp_new_size(self._h, uIn.numel()))
+            uo = torch.empty(n, dtype=out_dtype, device=uIn.device)
+            vo = torch.empty(n, dtype=out_dtype, device=uIn.device)
+            check(lib.fb200_interp_get_vector_slice_device(self._h, vh, int(capi.cdm_type(uIn.dtype)), ptr(uIn), ptr(vIn), uIn.numel(),
+                                                           float(badValueU), float(badValueV), int(capi.cdm_type(out_dtype)), ptr(uo), ptr(vo),
+                                                           C.byref(new_size), _stream_ptr(stream)), "getVectorSlice")
+        else:
+            u, v = np.ascontiguousarray(uIn), np.ascontiguousarray(vIn)
+            if u.dtype != v.dtype or u.size != v.size:
+                raise FimexB200Error("u and v differ in type or size")
+            out_dtype = np.dtype(outType) if outType is not None else u.dtype
+            n = int(lib.fb200_interp_new_size(self._h, u.size))
+            uo = np.empty(n, dtype=out_dtype)
+            vo = np.empty(n, dtype=out_dtype)
+            check(lib.fb200_interp_get_vector_slice(self._h, vh, int(capi.cdm_type(u.dtype)), ptr(u), ptr(v), u.size, float(badValueU),
+                                                    float(badValueV), int(capi.cdm_type(out_dtype)), ptr(uo), ptr(vo), C.byref(new_size)),
+                  "getVectorSlice")
         nz = n // max(1, self.getOutX() * self.getOutY())
         shape = (nz, self.getOutY(), self.getOutX())
         return uo.reshape(shape), vo.reshape(shape)

@@ -41,6 +41,44 @@ class Method(enum.IntEnum):
     FORWARD_UNDEF_MIN = 14
 
 
+class DataType(enum.IntEnum):
+    """enum CDMDataType (reference include/fimex/CDMDataType.h:35-49)"""
+    NAT = 0
+    CHAR = 1
+    SHORT = 2
+    INT = 3
+    FLOAT = 4
+    DOUBLE = 5
+    STRING = 6
+    UCHAR = 7
+    USHORT = 8
+    UINT = 9
+    INT64 = 10
+    UINT64 = 11
+
+
+_NP2CDM = {"int8": DataType.CHAR, "int16": DataType.SHORT, "int32": DataType.INT, "float32": DataType.FLOAT, "float64": DataType.DOUBLE,
+           "uint8": DataType.UCHAR, "uint16": DataType.USHORT, "uint32": DataType.UINT, "int64": DataType.INT64, "uint64": DataType.UINT64}
+
+
+def cdm_type(dtype) -> DataType:
+    """numpy / torch dtype -> CDMDataType"""
+    try:
+        if str(dtype).startswith("torch."):
+            dtype = str(dtype)[len("torch."):]
+        return _NP2CDM[str(np.dtype(dtype))]
+    except (KeyError, TypeError):
+        raise FimexB200Error(f"no CDM data type for {dtype}") from None
+
+
+def default_fill_value(dtype) -> float:
+    """defaultFillValue_ (reference src/CDM.cc:490-503, include/fimex/CDMconstants.h:149-158)"""
+    return {DataType.DOUBLE: 9.9692099683868690e+36, DataType.FLOAT: float(np.float32(9.9692099683868690e+36)),
+            DataType.INT64: -9223372036854775806.0, DataType.INT: -2147483647.0, DataType.SHORT: -32767.0, DataType.CHAR: -127.0,
+            DataType.UINT64: 18446744073709551614.0, DataType.UINT: 4294967295.0, DataType.USHORT: 65535.0,
+            DataType.UCHAR: 255.0}[cdm_type(dtype)]
+
+
 class FimexB200Error(RuntimeError):
     """The counterpart of the reference's CDMException for this path."""
 
@@ -120,6 +158,10 @@ def _declare(lib):
         "fb200_vector_destroy": (None, [_vp]),
         "fb200_interp_interpolate_vector": (i, [_vp, _vp, _vp, _vp, sz, _vp, _vp, P(sz)]),
         "fb200_interp_interpolate_vector_device": (i, [_vp, _vp, _vp, _vp, sz, _vp, _vp, P(sz), _vp]),
+        "fb200_interp_get_data_slice": (i, [_vp, i, _vp, sz, C.c_double, i, _vp, P(sz)]),
+        "fb200_interp_get_data_slice_device": (i, [_vp, i, _vp, sz, C.c_double, i, _vp, P(sz), _vp]),
+        "fb200_interp_get_vector_slice": (i, [_vp, _vp, i, _vp, _vp, sz, C.c_double, C.c_double, i, _vp, _vp, P(sz)]),
+        "fb200_interp_get_vector_slice_device": (i, [_vp, _vp, i, _vp, _vp, sz, C.c_double, C.c_double, i, _vp, _vp, P(sz), _vp]),
         "mifi_string_to_interpolation_method": (i, [C.c_char_p]),
         "mifi_interpolate_f": (i, [i, C.c_char_p, _vp, _vp, _vp, i, i, i, i, i, C.c_char_p, _vp, _vp, _vp, i, i, i, i]),
         "mifi_vector_reproject_values_f": (i, [i, C.c_char_p, C.c_char_p, _vp, _vp, _vp, _vp, i, i, i, i, i]),

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -374,29 +375,37 @@ GatherGeom geom_of(const fb200_interp* h, size_t nz)
     return g;
 }
 
-int run_device(const fb200_interp* h, const float* d_in, size_t nz, float* d_out, cudaStream_t st)
+// types and fill values either side of the gather for one slice call (CDMInterpolator::getDataSlice, :250-285)
+struct SliceIO {
+    bool typed = false; // false: CachedInterpolationInterface::interpolateValues itself (float in, float out, NaN = undefined)
+    int in_type = FB_T_FLOAT, out_type = FB_T_FLOAT;
+    double bad[2] = {0., 0.}; // CDM::getFillValue of each field: fill -> NaN on the way in, NaN -> fill on the way out
+};
+
+// the gather itself: float slabs in, plain floats out -- or, where the kernel can, converted while storing (sc)
+int run_gather(const fb200_interp* h, const float* d_in, size_t nz, void* d_out, const SliceConv& sc, cudaStream_t st)
 {
     if (h->forward)
-        return launch_forward(h->method, h->fwd, d_in, d_out, (long long)nz, st);
+        return launch_forward(h->method, h->fwd, d_in, static_cast<float*>(d_out), (long long)nz, st);
     const GatherGeom g = geom_of(h, nz);
     switch (h->method) {
     case FB_BILINEAR:
         if (h->tiles.ready())
-            return launch_gather_bilinear_staged(g, h->tiles, d_in, d_out, st);
-        return launch_gather_bilinear(g, h->d_bil, d_in, d_out, st);
+            return launch_gather_bilinear_staged(g, h->tiles, d_in, d_out, sc, st);
+        return launch_gather_bilinear(g, h->d_bil, d_in, static_cast<float*>(d_out), st);
     case FB_BICUBIC:
         if (h->bic_tiles.ready())
-            return launch_gather_bicubic_staged(g, h->bic_tiles, h->d_bic_off, h->d_bic_frac, nullptr, d_in, nullptr, d_out, nullptr, st);
-        return launch_gather_bicubic(g, h->d_bic_off, h->d_bic_frac, d_in, d_out, st);
+            return launch_gather_bicubic_staged(g, h->bic_tiles, h->d_bic_off, h->d_bic_frac, nullptr, d_in, nullptr, d_out, nullptr, sc, st);
+        return launch_gather_bicubic(g, h->d_bic_off, h->d_bic_frac, d_in, static_cast<float*>(d_out), st);
     default:
         if (h->tiles.ready())
-            return launch_gather_bilinear_staged(g, h->tiles, d_in, d_out, st);
-        return launch_gather_nn(g, h->d_nn, d_in, d_out, st);
+            return launch_gather_bilinear_staged(g, h->tiles, d_in, d_out, sc, st);
+        return launch_gather_nn(g, h->d_nn, d_in, static_cast<float*>(d_out), st);
     }
 }
 
-int run_vector_device(const fb200_interp* h, const fb200_vector* v, const float* d_u, const float* d_v, size_t nz, float* d_uo, float* d_vo,
-                      cudaStream_t st)
+int run_gather_vector(const fb200_interp* h, const fb200_vector* v, const float* d_u, const float* d_v, size_t nz, float* d_uo, float* d_vo,
+                      const SliceConv& sc, cudaStream_t st)
 {
     const GatherGeom g = geom_of(h, nz);
     const double2* cs = v ? v->d_cs : nullptr;
@@ -405,22 +414,84 @@ int run_vector_device(const fb200_interp* h, const fb200_vector* v, const float*
         return launch_gather_vector(FB_BILINEAR, g, h->d_bil, nullptr, cs, d_u, d_v, d_uo, d_vo, st);
     case FB_BICUBIC:
         if (h->bic_tiles.ready())
-            return launch_gather_bicubic_staged(g, h->bic_tiles, h->d_bic_off, h->d_bic_frac, cs, d_u, d_v, d_uo, d_vo, st);
+            return launch_gather_bicubic_staged(g, h->bic_tiles, h->d_bic_off, h->d_bic_frac, cs, d_u, d_v, d_uo, d_vo, sc, st);
         return launch_gather_vector(FB_BICUBIC, g, h->d_bic_off, h->d_bic_frac, cs, d_u, d_v, d_uo, d_vo, st);
     default:
         return launch_gather_vector(FB_NN, g, h->d_nn, nullptr, cs, d_u, d_v, d_uo, d_vo, st);
     }
 }
 
+// One slice on the device: nfields = 1 (scalar) or 2 (u/v with optional rotation).  With io.typed this is
+// data2InterpolationArray -> interpolateValues [-> reprojectValues] -> interpolationArray2Data; the staged gathers do the
+// first and last step inside the gather kernel, everything else goes through a float slab and a conversion pass.
+int run_slice_device(const fb200_interp* h, const fb200_vector* v, int nfields, const void* const* d_in, size_t nz, void* const* d_out,
+                     const SliceIO& io, cudaStream_t st)
+{
+    const size_t in_n = nz * h->inX * h->inY, out_n = nz * h->outX * h->outY;
+    if (nz == 0 || out_n == 0)
+        return FB_OK;
+    const bool staged_scalar = nfields == 1 && !h->forward && (h->method == FB_BICUBIC ? h->bic_tiles.ready() : h->tiles.ready());
+    const bool staged_bicubic_vector = nfields == 2 && h->method == FB_BICUBIC && h->bic_tiles.ready();
+    const bool kernel_fills = staged_scalar || staged_bicubic_vector;
+    Scratch tmp(st);
+    SliceConv sc;
+    const float* fin[2] = {nullptr, nullptr};
+    for (int f = 0; f < nfields; ++f) {
+        const float bad = (float)io.bad[f]; // mifi_bad2nanf takes a float (interpolation.c:1775)
+        const bool has_bad = io.typed && !std::isnan(bad);
+        sc.bad_in[f] = std::numeric_limits<float>::quiet_NaN();
+        if (!io.typed || (io.in_type == FB_T_FLOAT && (!has_bad || kernel_fills))) {
+            fin[f] = static_cast<const float*>(d_in[f]);
+            if (has_bad) {
+                sc.fill_in = true;
+                sc.bad_in[f] = bad;
+            }
+        } else {
+            float* conv = nullptr;
+            if (tmp.get(&conv, in_n) != FB_OK || launch_as_float(io.in_type, d_in[f], (long long)in_n, has_bad, bad, conv, st) != FB_OK)
+                return FB_ERROR;
+            fin[f] = conv;
+        }
+    }
+    if (!io.typed) {
+        if (nfields == 1)
+            return run_gather(h, fin[0], nz, d_out[0], sc, st);
+        return run_gather_vector(h, v, fin[0], fin[1], nz, static_cast<float*>(d_out[0]), static_cast<float*>(d_out[1]), sc, st);
+    }
+    if (staged_scalar && staged_store_supports(io.out_type)) { // the fused form: one pass over the output
+        sc.convert_out = true;
+        sc.out_type = io.out_type;
+        sc.fill_out = io.bad[0];
+        return run_gather(h, fin[0], nz, d_out[0], sc, st);
+    }
+    float* fout[2] = {nullptr, nullptr};
+    for (int f = 0; f < nfields; ++f) {
+        if (io.out_type == FB_T_FLOAT)
+            fout[f] = static_cast<float*>(d_out[f]); // converted in place afterwards
+        else if (tmp.get(&fout[f], out_n) != FB_OK)
+            return FB_ERROR;
+    }
+    const int rc = nfields == 1 ? run_gather(h, fin[0], nz, fout[0], sc, st) : run_gather_vector(h, v, fin[0], fin[1], nz, fout[0], fout[1], sc, st);
+    if (rc != FB_OK)
+        return rc;
+    for (int f = 0; f < nfields; ++f)
+        if (launch_from_float(fout[f], (long long)out_n, io.out_type, io.bad[f], d_out[f], st) != FB_OK)
+            return FB_ERROR;
+    return FB_OK;
+}
+
 // Host-buffer execution: levels are cut into chunks that rotate through three (stream, scratch) slots, so that
 // the H2D copy of chunk k+1, the kernel of chunk k and the D2H copy of chunk k-1 overlap.  `nfields` is 1
 // (scalar) or 2 (u/v).  Every call owns its streams and scratch => re-entrant on a shared handle.
-int run_host(const fb200_interp* h, const fb200_vector* v, int nfields, const float* const* in, float* const* out, size_t nz)
+int run_slice_host(const fb200_interp* h, const fb200_vector* v, int nfields, const void* const* in, void* const* out, size_t nz,
+                   const SliceIO& io)
 {
     const size_t in_level = h->inX * h->inY, out_level = h->outX * h->outY;
     if (nz == 0 || out_level == 0)
         return FB_OK;
-    const size_t bytes_per_level = (in_level + out_level) * sizeof(float) * (size_t)nfields;
+    const size_t in_elem = io.typed ? type_size(io.in_type) : sizeof(float), out_elem = io.typed ? type_size(io.out_type) : sizeof(float);
+    FB_REQUIRE(in_elem > 0 && out_elem > 0, "unsupported data type");
+    const size_t bytes_per_level = (in_level * in_elem + out_level * out_elem) * (size_t)nfields;
     size_t zc = (size_t)(192ull << 20) / (bytes_per_level ? bytes_per_level : 1);
     if (zc < 1)
         zc = 1;
@@ -429,16 +500,16 @@ int run_host(const fb200_interp* h, const fb200_vector* v, int nfields, const fl
     const int nslots = (nz > zc) ? 3 : 1;
     struct Slot {
         cudaStream_t st = nullptr;
-        float* d_in[2] = {nullptr, nullptr};
-        float* d_out[2] = {nullptr, nullptr};
+        void* d_in[2] = {nullptr, nullptr};
+        void* d_out[2] = {nullptr, nullptr};
     } slots[3];
     int rc = FB_OK;
     auto body = [&]() -> int {
         for (int s = 0; s < nslots; ++s) {
             FB_CUDA_CHECK(cudaStreamCreateWithFlags(&slots[s].st, cudaStreamNonBlocking));
             for (int f = 0; f < nfields; ++f) {
-                FB_CUDA_CHECK(cudaMallocAsync(&slots[s].d_in[f], sizeof(float) * ((zc * in_level) > 0 ? zc * in_level : 1), slots[s].st));
-                FB_CUDA_CHECK(cudaMallocAsync(&slots[s].d_out[f], sizeof(float) * zc * out_level, slots[s].st));
+                FB_CUDA_CHECK(cudaMallocAsync(&slots[s].d_in[f], in_elem * ((zc * in_level) > 0 ? zc * in_level : 1), slots[s].st));
+                FB_CUDA_CHECK(cudaMallocAsync(&slots[s].d_out[f], out_elem * zc * out_level, slots[s].st));
             }
         }
         size_t chunk = 0;
@@ -447,18 +518,13 @@ int run_host(const fb200_interp* h, const fb200_vector* v, int nfields, const fl
             const size_t zn = (z0 + zc <= nz) ? zc : nz - z0;
             for (int f = 0; f < nfields; ++f)
                 if (in_level)
-                    FB_CUDA_CHECK(cudaMemcpyAsync(sl.d_in[f], in[f] + z0 * in_level, sizeof(float) * zn * in_level, cudaMemcpyHostToDevice,
-                                                  sl.st));
-            int r;
-            if (nfields == 1)
-                r = run_device(h, sl.d_in[0], zn, sl.d_out[0], sl.st);
-            else
-                r = run_vector_device(h, v, sl.d_in[0], sl.d_in[1], zn, sl.d_out[0], sl.d_out[1], sl.st);
-            if (r != FB_OK)
+                    FB_CUDA_CHECK(cudaMemcpyAsync(sl.d_in[f], static_cast<const char*>(in[f]) + z0 * in_level * in_elem, in_elem * zn * in_level,
+                                                  cudaMemcpyHostToDevice, sl.st));
+            if (run_slice_device(h, v, nfields, sl.d_in, zn, sl.d_out, io, sl.st) != FB_OK)
                 return FB_ERROR;
             for (int f = 0; f < nfields; ++f)
-                FB_CUDA_CHECK(cudaMemcpyAsync(out[f] + z0 * out_level, sl.d_out[f], sizeof(float) * zn * out_level, cudaMemcpyDeviceToHost,
-                                              sl.st));
+                FB_CUDA_CHECK(cudaMemcpyAsync(static_cast<char*>(out[f]) + z0 * out_level * out_elem, sl.d_out[f], out_elem * zn * out_level,
+                                              cudaMemcpyDeviceToHost, sl.st));
         }
         for (int s = 0; s < nslots; ++s)
             FB_CUDA_CHECK(cudaStreamSynchronize(slots[s].st));
@@ -478,6 +544,34 @@ int run_host(const fb200_interp* h, const fb200_vector* v, int nfields, const fl
         cudaStreamDestroy(slots[s].st);
     }
     return rc;
+}
+
+// plain interpolateValues forms of the above
+int run_device(const fb200_interp* h, const float* d_in, size_t nz, float* d_out, cudaStream_t st)
+{
+    const void* in[1] = {d_in};
+    void* out[1] = {d_out};
+    return run_slice_device(h, nullptr, 1, in, nz, out, SliceIO(), st);
+}
+
+int run_vector_device(const fb200_interp* h, const fb200_vector* v, const float* d_u, const float* d_v, size_t nz, float* d_uo, float* d_vo,
+                      cudaStream_t st)
+{
+    const void* in[2] = {d_u, d_v};
+    void* out[2] = {d_uo, d_vo};
+    return run_slice_device(h, v, 2, in, nz, out, SliceIO(), st);
+}
+
+int run_host(const fb200_interp* h, const fb200_vector* v, int nfields, const float* const* in, float* const* out, size_t nz)
+{
+    const void* vin[2] = {in[0], nfields > 1 ? in[1] : nullptr};
+    void* vout[2] = {out[0], nfields > 1 ? out[1] : nullptr};
+    return run_slice_host(h, v, nfields, vin, vout, nz, SliceIO());
+}
+
+bool known_type(int t)
+{
+    return type_size(t) > 0;
 }
 
 int check_interp_call(const fb200_interp* h, size_t size, size_t* nz)
@@ -1129,6 +1223,92 @@ int fb200_interp_interpolate_vector(const fb200_interp* h, const fb200_vector* v
     const float* in[2] = {uIn, vIn};
     float* out[2] = {uOut, vOut};
     return run_host(h, (v && v->d_cs) ? v : nullptr, 2, in, out, nz);
+}
+
+// ---------------------------------------------------------------------------------------- getDataSlice in one call
+static int check_slice_types(int inType, int outType)
+{
+    FB_REQUIRE(known_type(inType), "unsupported input data type " + std::to_string(inType));
+    FB_REQUIRE(known_type(outType), "unsupported output data type " + std::to_string(outType));
+    return FB_OK;
+}
+
+int fb200_interp_get_data_slice_device(const fb200_interp* h, int inType, const void* d_in, size_t size, double badValue, int outType,
+                                       void* d_out, size_t* newSize, void* stream)
+{
+    size_t nz = 0;
+    if (check_interp_call(h, size, &nz) != FB_OK || check_slice_types(inType, outType) != FB_OK)
+        return MIFI_ERROR;
+    if (newSize)
+        *newSize = h->outX * h->outY * nz;
+    FB_REQUIRE(nz == 0 || (d_in && d_out), "null data pointer");
+    SliceIO io;
+    io.typed = true;
+    io.in_type = inType;
+    io.out_type = outType;
+    io.bad[0] = badValue;
+    const void* in[1] = {d_in};
+    void* out[1] = {d_out};
+    return run_slice_device(h, nullptr, 1, in, nz, out, io, as_stream(stream));
+}
+
+int fb200_interp_get_data_slice(const fb200_interp* h, int inType, const void* inData, size_t size, double badValue, int outType,
+                                void* outData, size_t* newSize)
+{
+    size_t nz = 0;
+    if (check_interp_call(h, size, &nz) != FB_OK || check_slice_types(inType, outType) != FB_OK)
+        return MIFI_ERROR;
+    if (newSize)
+        *newSize = h->outX * h->outY * nz;
+    FB_REQUIRE(nz == 0 || (inData && outData), "null data pointer");
+    SliceIO io;
+    io.typed = true;
+    io.in_type = inType;
+    io.out_type = outType;
+    io.bad[0] = badValue;
+    const void* in[1] = {inData};
+    void* out[1] = {outData};
+    return run_slice_host(h, nullptr, 1, in, out, nz, io);
+}
+
+int fb200_interp_get_vector_slice_device(const fb200_interp* h, const fb200_vector* v, int inType, const void* d_u, const void* d_v, size_t size,
+                                         double badU, double badV, int outType, void* d_uo, void* d_vo, size_t* newSize, void* stream)
+{
+    size_t nz = 0;
+    if (check_vector_call(h, v) != FB_OK || check_interp_call(h, size, &nz) != FB_OK || check_slice_types(inType, outType) != FB_OK)
+        return MIFI_ERROR;
+    if (newSize)
+        *newSize = h->outX * h->outY * nz;
+    FB_REQUIRE(nz == 0 || (d_u && d_v && d_uo && d_vo), "null data pointer");
+    SliceIO io;
+    io.typed = true;
+    io.in_type = inType;
+    io.out_type = outType;
+    io.bad[0] = badU;
+    io.bad[1] = badV;
+    const void* in[2] = {d_u, d_v};
+    void* out[2] = {d_uo, d_vo};
+    return run_slice_device(h, (v && v->d_cs) ? v : nullptr, 2, in, nz, out, io, as_stream(stream));
+}
+
+int fb200_interp_get_vector_slice(const fb200_interp* h, const fb200_vector* v, int inType, const void* uIn, const void* vIn, size_t size,
+                                  double badU, double badV, int outType, void* uOut, void* vOut, size_t* newSize)
+{
+    size_t nz = 0;
+    if (check_vector_call(h, v) != FB_OK || check_interp_call(h, size, &nz) != FB_OK || check_slice_types(inType, outType) != FB_OK)
+        return MIFI_ERROR;
+    if (newSize)
+        *newSize = h->outX * h->outY * nz;
+    FB_REQUIRE(nz == 0 || (uIn && vIn && uOut && vOut), "null data pointer");
+    SliceIO io;
+    io.typed = true;
+    io.in_type = inType;
+    io.out_type = outType;
+    io.bad[0] = badU;
+    io.bad[1] = badV;
+    const void* in[2] = {uIn, vIn};
+    void* out[2] = {uOut, vOut};
+    return run_slice_host(h, (v && v->d_cs) ? v : nullptr, 2, in, out, nz, io);
 }
 
 // ---------------------------------------------------------------------------------------- mifi_* drop-ins

@@ -32,6 +32,7 @@
 // columns) are computed by the same kernel with direct global loads.
 #include "kernels.h"
 #include "interp_math.cuh"
+#include "convert.cuh"
 
 #include <cstdlib>
 #include <vector>
@@ -360,10 +361,31 @@ __device__ __forceinline__ void compute_levels(const Group& gr, const double* __
 
 // Tiles whose taps do not fit the staging buffers: every point reads its 16 taps from global memory (the arithmetic of
 // the direct kernel, gather_kernels.cu); lane = x, so a warp still writes 128 contiguous bytes per level.
-template <int NF, bool ROT>
+// bicubic_eval with mifi_bad2nanf applied to the 16 taps
+__device__ __forceinline__ float bicubic_eval_bad(const float* __restrict__ s, int ix, const double (&wx)[4], const double (&wy)[4], float bad)
+{
+    float acc = 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const float* p = s + r * ix;
+        float v[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            v[c] = __ldg(p + c);
+            if (v[c] == bad)
+                v[c] = undef_f();
+        }
+        const double row = bicubic_row(wx, (double)v[0], (double)v[1], (double)v[2], (double)v[3]);
+        acc = (r == 0) ? bicubic_acc<true>(acc, row, wy[0]) : bicubic_acc<false>(acc, row, wy[r]);
+    }
+    return acc;
+}
+
+template <int NF, bool ROT, class Out>
 __device__ void direct_tile(const GatherGeom& g, int tx, int ty, long long z0, long long z1, const int* __restrict__ off_tab,
                             const double2* __restrict__ frac_tab, const double2* __restrict__ cs, const float* __restrict__ in0,
-                            const float* __restrict__ in1, float* __restrict__ out0, float* __restrict__ out1)
+                            const float* __restrict__ in1, typename Out::type* __restrict__ out0, typename Out::type* __restrict__ out1,
+                            const Out& conv, bool fill_in, float bad0, float bad1)
 {
     for (int p = threadIdx.x; p < kTP; p += kT) {
         const int gx = tx * kTX + (p & (kTX - 1)), gy = ty * kTY + (p >> 5);
@@ -371,14 +393,14 @@ __device__ void direct_tile(const GatherGeom& g, int tx, int ty, long long z0, l
             continue;
         const long long q = (long long)gy * g.ox + gx;
         const int off = __ldg(off_tab + q);
-        float* o0 = out0 + z0 * g.out_level + q;
-        float* o1 = (NF == 2) ? out1 + z0 * g.out_level + q : nullptr;
+        typename Out::type* o0 = out0 + z0 * g.out_level + q;
+        typename Out::type* o1 = (NF == 2) ? out1 + z0 * g.out_level + q : nullptr;
         if (off < 0) { // :1022-1026
             for (long long z = z0; z < z1; ++z) {
-                __stcs(o0, undef_f());
+                __stcs(o0, conv(undef_f()));
                 o0 += g.out_level;
                 if (NF == 2) {
-                    __stcs(o1, undef_f());
+                    __stcs(o1, conv(undef_f()));
                     o1 += g.out_level;
                 }
             }
@@ -394,17 +416,17 @@ __device__ void direct_tile(const GatherGeom& g, int tx, int ty, long long z0, l
         const float* p0 = in0 + z0 * g.in_level + off;
         const float* p1 = (NF == 2) ? in1 + z0 * g.in_level + off : nullptr;
         for (long long z = z0; z < z1; ++z) {
-            float a = bicubic_eval(p0, g.ix, wx, wy);
+            float a = fill_in ? bicubic_eval_bad(p0, g.ix, wx, wy, bad0) : bicubic_eval(p0, g.ix, wx, wy);
             float b = 0.f;
             if (NF == 2)
-                b = bicubic_eval(p1, g.ix, wx, wy);
+                b = fill_in ? bicubic_eval_bad(p1, g.ix, wx, wy, bad1) : bicubic_eval(p1, g.ix, wx, wy);
             if (ROT)
                 rotate_uv(a, b, rot.x, rot.y);
-            __stcs(o0, a);
+            __stcs(o0, conv(a));
             p0 += g.in_level;
             o0 += g.out_level;
             if (NF == 2) {
-                __stcs(o1, b);
+                __stcs(o1, conv(b));
                 p1 += g.in_level;
                 o1 += g.out_level;
             }
@@ -415,13 +437,15 @@ __device__ void direct_tile(const GatherGeom& g, int tx, int ty, long long z0, l
 // FAST: at most 256 taps; 8/NF levels per batch; warp w stages (field, level) row w of the batch and later stores
 //       (field, level) row w of the output tile.
 // else: up to 2048/NF taps, one level per batch, every thread stages 8/NF taps per field.
-template <int NF, bool ROT, bool FAST>
+template <int NF, bool ROT, bool FAST, class Out>
 __device__ __forceinline__ void staged_tile(const GatherGeom& g, int tx, int ty, long long z0, long long z1, int4 inf,
                                             const int* __restrict__ taps, const uint4* __restrict__ gmeta, const double2* __restrict__ gfrac,
                                             const double2* __restrict__ cs, const float* __restrict__ in0, const float* __restrict__ in1,
-                                            float* __restrict__ out0, float* __restrict__ out1, bool vec_ok, double* s_stage, float* s_out,
-                                            double2* s_cs)
+                                            typename Out::type* __restrict__ out0, typename Out::type* __restrict__ out1, bool vec_ok,
+                                            double* s_stage, float* s_out, double2* s_cs, const Out& conv, bool fill_in, float bad0,
+                                            float bad1)
 {
+    typedef typename Out::type OutT;
     constexpr int L = FAST ? 8 / NF : 1;
     constexpr int S = (L == 1) ? 1 : L + 1; // odd tap stride (in doubles): distinct taps of a warp land in distinct banks
     constexpr int NREG = 8;
@@ -473,15 +497,19 @@ __device__ __forceinline__ void staged_tile(const GatherGeom& g, int tx, int ty,
 #pragma unroll
         for (int j = 0; j < NREG; ++j) {
             const int r = tap_of(j);
-            if (r < ntaps)
-                dst[field_of(j) * field_stride + r * S] = (double)regs[j];
+            if (r < ntaps) {
+                float v = regs[j];
+                if (fill_in && v == (field_of(j) == 0 ? bad0 : bad1)) // mifi_bad2nanf, once per tap
+                    v = undef_f();
+                dst[field_of(j) * field_stride + r * S] = (double)v;
+            }
         }
     };
 
     // store phase: warp w writes (field, level) row w of the finished output tile, 7 x 128-bit per lane.  Lane l owns
     // tile rows (l >> 3) + 4k; the column group alternates between two values with the parity of k (out_slot()).
     const int st_f = warp / L, st_zi = warp % L;
-    float* const st_out = (NF == 2 && st_f == 1) ? out1 : out0;
+    OutT* const st_out = (NF == 2 && st_f == 1) ? out1 : out0;
     const int ly0 = lane >> 3;
     const int gx_even = tx * kTX + (((lane & 7) ^ ly0) << 2), gx_odd = tx * kTX + (((lane & 7) ^ (ly0 + 4)) << 2);
     const int gy0 = ty * kTY + ly0;
@@ -491,12 +519,13 @@ __device__ __forceinline__ void staged_tile(const GatherGeom& g, int tx, int ty,
         if (warp >= NF * L || st_zi >= nb)
             return;
         const float* src = tile + (st_f * L + st_zi) * kOutRow + lane * 4;
-        float* lvl = st_out + (z + st_zi) * g.out_level + st_row0;
+        OutT* lvl = st_out + (z + st_zi) * g.out_level + st_row0;
         if (whole) {
 #pragma unroll
-            for (int k = 0; k < kTP / 128; ++k)
-                __stcs(reinterpret_cast<float4*>(lvl + (long long)(4 * k) * g.ox + ((k & 1) ? gx_odd : gx_even)),
-                       *reinterpret_cast<const float4*>(src + 128 * k));
+            for (int k = 0; k < kTP / 128; ++k) {
+                const float4 v = *reinterpret_cast<const float4*>(src + 128 * k);
+                store_vec4<OutT>(lvl + (long long)(4 * k) * g.ox + ((k & 1) ? gx_odd : gx_even), conv(v.x), conv(v.y), conv(v.z), conv(v.w));
+            }
             return;
         }
 #pragma unroll
@@ -505,17 +534,17 @@ __device__ __forceinline__ void staged_tile(const GatherGeom& g, int tx, int ty,
             if (gy0 + 4 * k >= g.oy || gx >= g.ox)
                 continue;
             const float4 v = *reinterpret_cast<const float4*>(src + 128 * k);
-            float* dst = lvl + (long long)(4 * k) * g.ox + gx;
+            OutT* dst = lvl + (long long)(4 * k) * g.ox + gx;
             if (vec_ok && gx + 3 < g.ox) {
-                __stcs(reinterpret_cast<float4*>(dst), v);
+                store_vec4<OutT>(dst, conv(v.x), conv(v.y), conv(v.z), conv(v.w));
             } else {
-                __stcs(dst, v.x);
+                __stcs(dst, conv(v.x));
                 if (gx + 1 < g.ox)
-                    __stcs(dst + 1, v.y);
+                    __stcs(dst + 1, conv(v.y));
                 if (gx + 2 < g.ox)
-                    __stcs(dst + 2, v.z);
+                    __stcs(dst + 2, conv(v.z));
                 if (gx + 3 < g.ox)
-                    __stcs(dst + 3, v.w);
+                    __stcs(dst + 3, conv(v.w));
             }
         }
     };
@@ -557,13 +586,14 @@ __device__ __forceinline__ void staged_tile(const GatherGeom& g, int tx, int ty,
     }
 }
 
-template <int NF, bool ROT>
+template <int NF, bool ROT, class Out>
 __global__ void __launch_bounds__(kT, 2) k_gather_bicubic_staged(GatherGeom g, int tiles_x, const int4* __restrict__ info,
                                                                  const int* __restrict__ taps, const uint4* __restrict__ gmeta,
                                                                  const double2* __restrict__ gfrac, const int* __restrict__ off_tab,
                                                                  const double2* __restrict__ frac_tab, const double2* __restrict__ cs,
                                                                  const float* __restrict__ in0, const float* __restrict__ in1,
-                                                                 float* __restrict__ out0, float* __restrict__ out1, int vec_ok, long long per)
+                                                                 typename Out::type* __restrict__ out0, typename Out::type* __restrict__ out1,
+                                                                 int vec_ok, long long per, Out conv, int fill_in, float bad0, float bad1)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* s_stage = reinterpret_cast<double*>(smem_raw);                                     // [2][kStageDoubles]
@@ -577,11 +607,13 @@ __global__ void __launch_bounds__(kT, 2) k_gather_bicubic_staged(GatherGeom g, i
     if (z0 >= z1)
         return;
     if (inf.y < 0 || NF * inf.y > kStageElems)
-        direct_tile<NF, ROT>(g, tx, ty, z0, z1, off_tab, frac_tab, cs, in0, in1, out0, out1);
+        direct_tile<NF, ROT, Out>(g, tx, ty, z0, z1, off_tab, frac_tab, cs, in0, in1, out0, out1, conv, fill_in != 0, bad0, bad1);
     else if (inf.y <= kFastTaps)
-        staged_tile<NF, ROT, true>(g, tx, ty, z0, z1, inf, taps, gmeta, gfrac, cs, in0, in1, out0, out1, vec_ok != 0, s_stage, s_out, s_cs);
+        staged_tile<NF, ROT, true, Out>(g, tx, ty, z0, z1, inf, taps, gmeta, gfrac, cs, in0, in1, out0, out1, vec_ok != 0, s_stage, s_out, s_cs,
+                                        conv, fill_in != 0, bad0, bad1);
     else
-        staged_tile<NF, ROT, false>(g, tx, ty, z0, z1, inf, taps, gmeta, gfrac, cs, in0, in1, out0, out1, vec_ok != 0, s_stage, s_out, s_cs);
+        staged_tile<NF, ROT, false, Out>(g, tx, ty, z0, z1, inf, taps, gmeta, gfrac, cs, in0, in1, out0, out1, vec_ok != 0, s_stage, s_out,
+                                         s_cs, conv, fill_in != 0, bad0, bad1);
 }
 
 constexpr size_t kGatherSmem = sizeof(double) * 2 * kStageDoubles + sizeof(float) * 2 * kOutRows * kOutRow;
@@ -663,9 +695,25 @@ int bicubic_tiles_build(const int* d_off, const double2* d_frac, int ix, int iy,
     return FB_OK;
 }
 
-// scalar field (d_in1 == d_out1 == nullptr) or the two components of a vector, optionally rotated (d_cs != nullptr)
+namespace {
+template <int NF, bool ROT, class Out>
+int launch_bic(dim3 grid, size_t smem, const GatherGeom& g, const BicubicTiles& bt, const int* d_off, const double2* d_frac, const double2* d_cs,
+               const float* d_in0, const float* d_in1, void* d_out0, void* d_out1, int vec_ok, long long per, Out conv, const SliceConv& sc,
+               cudaStream_t st)
+{
+    typedef typename Out::type T;
+    FB_CUDA_CHECK(cudaFuncSetAttribute(k_gather_bicubic_staged<NF, ROT, Out>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_gather_bicubic_staged<NF, ROT, Out><<<grid, kT, smem, st>>>(g, bt.tiles_x, bt.d_info, bt.d_taps, bt.d_gmeta, bt.d_gfrac, d_off, d_frac, d_cs,
+                                                                  d_in0, d_in1, static_cast<T*>(d_out0), static_cast<T*>(d_out1), vec_ok, per,
+                                                                  conv, sc.fill_in ? 1 : 0, sc.bad_in[0], sc.bad_in[1]);
+    return FB_OK;
+}
+} // namespace
+
+// scalar field (d_in1 == d_out1 == nullptr) or the two components of a vector, rotated when d_cs != nullptr.  The scalar
+// form converts to sc.out_type while storing (staged_store_supports()); the vector form writes plain floats.
 int launch_gather_bicubic_staged(const GatherGeom& g, const BicubicTiles& bt, const int* d_off, const double2* d_frac, const double2* d_cs,
-                                 const float* d_in0, const float* d_in1, float* d_out0, float* d_out1, cudaStream_t st)
+                                 const float* d_in0, const float* d_in1, void* d_out0, void* d_out1, const SliceConv& sc, cudaStream_t st)
 {
     if (g.out_level == 0 || g.nz == 0)
         return FB_OK;
@@ -687,21 +735,40 @@ int launch_gather_bicubic_staged(const GatherGeom& g, const BicubicTiles& bt, co
     }
     dim3 grid(tiles, (unsigned)gy);
     const bool two = d_in1 != nullptr;
-    uintptr_t align = reinterpret_cast<uintptr_t>(d_out0) | (two ? reinterpret_cast<uintptr_t>(d_out1) : 0);
-    const int vec_ok = ((g.ox % 4) == 0 && (align & 15u) == 0) ? 1 : 0;
-#define FB_BIC_LAUNCH(NF, ROT, SMEM)                                                                                                       \
-    do {                                                                                                                                   \
-        FB_CUDA_CHECK(cudaFuncSetAttribute(k_gather_bicubic_staged<NF, ROT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM)));   \
-        k_gather_bicubic_staged<NF, ROT><<<grid, kT, SMEM, st>>>(g, bt.tiles_x, bt.d_info, bt.d_taps, bt.d_gmeta, bt.d_gfrac, d_off, d_frac, \
-                                                                  d_cs, d_in0, d_in1, d_out0, d_out1, vec_ok, per);                         \
-    } while (0)
-    if (!two)
-        FB_BIC_LAUNCH(1, false, kGatherSmem);
-    else if (d_cs)
-        FB_BIC_LAUNCH(2, true, kGatherSmemRot);
-    else
-        FB_BIC_LAUNCH(2, false, kGatherSmem);
-#undef FB_BIC_LAUNCH
+    const size_t elem = (two || !sc.convert_out) ? sizeof(float) : type_size(sc.out_type);
+    const uintptr_t align = reinterpret_cast<uintptr_t>(d_out0) | (two ? reinterpret_cast<uintptr_t>(d_out1) : 0);
+    const int vec_ok = ((g.ox % 4) == 0 && (align & (4 * elem - 1)) == 0) ? 1 : 0;
+    int rc = FB_ERROR;
+    if (two) {
+        FB_REQUIRE(!sc.convert_out, "bicubic vector gather writes plain floats");
+        if (d_cs)
+            rc = launch_bic<2, true>(grid, kGatherSmemRot, g, bt, d_off, d_frac, d_cs, d_in0, d_in1, d_out0, d_out1, vec_ok, per, StorePlain(), sc, st);
+        else
+            rc = launch_bic<2, false>(grid, kGatherSmem, g, bt, d_off, d_frac, d_cs, d_in0, d_in1, d_out0, d_out1, vec_ok, per, StorePlain(), sc, st);
+    } else if (!sc.convert_out) {
+        rc = launch_bic<1, false>(grid, kGatherSmem, g, bt, d_off, d_frac, d_cs, d_in0, d_in1, d_out0, d_out1, vec_ok, per, StorePlain(), sc, st);
+    } else {
+        switch (sc.out_type) {
+#define FB_CASE(TAG, T)                                                                                                                    \
+    case TAG:                                                                                                                              \
+        rc = launch_bic<1, false>(grid, kGatherSmem, g, bt, d_off, d_frac, d_cs, d_in0, d_in1, d_out0, d_out1, vec_ok, per,               \
+                                  StoreAs<T>{cast_fill<T>(sc.fill_out)}, sc, st);                                                          \
+        break;
+            FB_CASE(FB_T_FLOAT, float)
+            FB_CASE(FB_T_DOUBLE, double)
+            FB_CASE(FB_T_CHAR, signed char)
+            FB_CASE(FB_T_SHORT, short)
+            FB_CASE(FB_T_INT, int)
+            FB_CASE(FB_T_UCHAR, unsigned char)
+            FB_CASE(FB_T_USHORT, unsigned short)
+            FB_CASE(FB_T_UINT, unsigned int)
+#undef FB_CASE
+        default:
+            FB_REQUIRE(false, "bicubic staged gather: unsupported output type");
+        }
+    }
+    if (rc != FB_OK)
+        return rc;
     count_launch();
     FB_CUDA_CHECK(cudaGetLastError());
     return FB_OK;

@@ -5,6 +5,7 @@
 
 #include "common.cuh"
 #include "proj.cuh"
+#include "convert.cuh"
 
 namespace fb {
 
@@ -76,8 +77,9 @@ struct TileTable {
 bool tile_table_supported(int ix, int iy, int ox, int oy);
 int tile_table_build(bool nn, const double* d_px, const double* d_py, int ix, int iy, int ox, int oy, TileTable* tt, cudaStream_t st);
 void tile_table_free(TileTable* tt);
-// staged gather for bilinear and nearest-neighbour tables
-int launch_gather_bilinear_staged(const GatherGeom& g, const TileTable& tt, const float* d_in, float* d_out, cudaStream_t st);
+// staged gather for bilinear and nearest-neighbour tables; sc: fill -> NaN while staging, NaN -> fill + cast while storing
+int launch_gather_bilinear_staged(const GatherGeom& g, const TileTable& tt, const float* d_in, void* d_out, const SliceConv& sc, cudaStream_t st);
+bool staged_store_supports(int out_type);
 
 // ---- bicubic_staged.cu (K5 fast path) ------------------------------------------------------------------
 struct BicubicTiles {
@@ -94,9 +96,16 @@ bool bicubic_tiles_supported(int ix, int iy, int ox, int oy);
 // d_off / d_frac: the per-point bicubic table of launch_compile_bicubic; synchronises
 int bicubic_tiles_build(const int* d_off, const double2* d_frac, int ix, int iy, int ox, int oy, BicubicTiles* bt, cudaStream_t st);
 void bicubic_tiles_free(BicubicTiles* bt);
-// scalar field (d_in1 == d_out1 == nullptr) or both components of a vector, rotated when d_cs != nullptr
+// scalar field (d_in1 == d_out1 == nullptr; converts like the staged bilinear gather) or both components of a vector
+// (plain float output), rotated when d_cs != nullptr
 int launch_gather_bicubic_staged(const GatherGeom& g, const BicubicTiles& bt, const int* d_off, const double2* d_frac, const double2* d_cs,
-                                 const float* d_in0, const float* d_in1, float* d_out0, float* d_out1, cudaStream_t st);
+                                 const float* d_in0, const float* d_in1, void* d_out0, void* d_out1, const SliceConv& sc, cudaStream_t st);
+
+// ---- adapter_kernels.cu (K10, unfused forms) ---------------------------------------------------------------
+// data2InterpolationArray: any CDM numeric type -> float with badValue -> NaN (CDMInterpolator.cc:115-119)
+int launch_as_float(int in_type, const void* d_in, long long n, bool has_bad, float bad, float* d_out, cudaStream_t st);
+// interpolationArray2Data: NaN -> fill, round + cast (CDMInterpolator.cc:121-124); in place allowed for FB_T_FLOAT
+int launch_from_float(const float* d_in, long long n, int out_type, double fill, void* d_out, cudaStream_t st);
 
 // ---- forward_kernels.cu (K8) ---------------------------------------------------------------------------
 struct ForwardPlan {

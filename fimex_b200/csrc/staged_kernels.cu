@@ -24,6 +24,7 @@
 //   xf/yf [tile][256]   float4 per thread: the reference's float xfrac / yfrac of its 4 points
 #include "kernels.h"
 #include "tables.cuh"
+#include "convert.cuh"
 
 #include <cstdlib>
 
@@ -178,11 +179,15 @@ __device__ __forceinline__ void cp_async_wait_all()
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 }
 
-template <bool NN>
+// Out: StorePlain (interpolateValues' own float output) or StoreAs<T> (interpolationArray2Data fused into the store:
+// NaN -> fill, round + cast to the variable's type).  fill_in: mifi_bad2nanf fused into the staging (values equal to
+// bad_in become NaN before any point reads them).
+template <bool NN, class Out>
 __global__ void __launch_bounds__(kThreads, 3) k_gather_bilinear_staged(GatherGeom g, int tiles_x, const int* __restrict__ taps,
                                                                      const int* __restrict__ ntaps_tab, const uint4* __restrict__ meta,
                                                                      const float4* __restrict__ xf4, const float4* __restrict__ yf4,
-                                                                     const float* __restrict__ in, float* __restrict__ out)
+                                                                     const float* __restrict__ in, typename Out::type* __restrict__ out,
+                                                                     Out conv, int fill_in, float bad_in)
 {
     __shared__ float s_stage[2][kStageFloats]; // double buffer: batch b+1 lands while batch b is consumed
     const int tile = blockIdx.x;
@@ -219,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_gather_bilinear_staged(GatherGe
     const long long per = (g.nz + gridDim.y - 1) / gridDim.y;
     const long long z0 = (long long)blockIdx.y * per;
     const long long z1 = z0 + per < g.nz ? z0 + per : g.nz;
-    float* o = out + z0 * g.out_level + (long long)yw * g.ox + x;
+    typename Out::type* o = out + z0 * g.out_level + (long long)yw * g.ox + x;
     const long long row8 = 8ll * g.ox;
     // Two staging layouts.  fast: tap-major, element (tap r, level zi) at r*9 + zi -- a thread's eight row pointers are then
     // constant for a whole batch and the level is an immediate offset of the shared load (no address arithmetic in the
@@ -260,12 +265,34 @@ __global__ void __launch_bounds__(kThreads, 3) k_gather_bilinear_staged(GatherGe
         cp_async_commit();
     };
 
+    // mifi_bad2nanf on the batch that has just landed: every thread patches the elements it copied itself (its own
+    // cp.async writes are visible to it after the wait), so no extra barrier is needed
+    auto patch = [&](int buf, int nb) {
+        float* dst = s_stage[buf];
+        const float nanv = undef_f();
+        if (fast) {
+            for (int r = t; r < ntaps; r += kThreads) {
+                float* d = dst + r * kLvlStride;
+                for (int zi = 0; zi < nb; ++zi)
+                    if (d[zi] == bad_in)
+                        d[zi] = nanv;
+            }
+        } else {
+            for (int zi = 0; zi < nb; ++zi, dst += ntaps)
+                for (int r = t; r < ntaps; r += kThreads)
+                    if (dst[r] == bad_in)
+                        dst[r] = nanv;
+        }
+    };
+
     if (z0 < z1)
         issue(0, z0, (int)((z1 - z0) < zb ? (z1 - z0) : zb));
     int buf = 0;
     for (long long z = z0; z < z1; z += zb, buf ^= 1) {
         const int nb = (int)((z1 - z) < zb ? (z1 - z) : zb);
         cp_async_wait_all();
+        if (fill_in)
+            patch(buf, nb);
         __syncthreads(); // batch z has landed for every thread, and every thread is done reading the other buffer
         const long long zn = z + zb;
         if (zn < z1)
@@ -296,10 +323,10 @@ __global__ void __launch_bounds__(kThreads, 3) k_gather_bilinear_staged(GatherGe
                             r[k] = __fadd_rn(__fmul_rn(wy0[k], top), __fmul_rn(yf[k], bot));
                         }
                     }
-                    __stcs(o, r[0]);
-                    __stcs(o + row8, r[1]);
-                    __stcs(o + 2 * row8, r[2]);
-                    __stcs(o + 3 * row8, r[3]);
+                    __stcs(o, conv(r[0]));
+                    __stcs(o + row8, conv(r[1]));
+                    __stcs(o + 2 * row8, conv(r[2]));
+                    __stcs(o + 3 * row8, conv(r[3]));
                     o += g.out_level;
                 }
             }
@@ -332,7 +359,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_gather_bilinear_staged(GatherGe
                         break;
                     }
                     if (k < nvalid)
-                        __stcs(o + k * row8, v);
+                        __stcs(o + k * row8, conv(v));
                 }
                 o += g.out_level;
             }
@@ -388,17 +415,71 @@ void tile_table_free(TileTable* tt)
     *tt = TileTable();
 }
 
-int launch_gather_bilinear_staged(const GatherGeom& g, const TileTable& tt, const float* d_in, float* d_out, cudaStream_t st)
+namespace {
+template <bool NN, class Out>
+void launch_staged_as(dim3 grid, const GatherGeom& g, const TileTable& tt, const float* d_in, void* d_out, Out conv, const SliceConv& sc,
+                      cudaStream_t st)
+{
+    k_gather_bilinear_staged<NN, Out><<<grid, kThreads, 0, st>>>(g, tt.tiles_x, tt.d_cells, tt.d_ncells, tt.d_meta, tt.d_xf, tt.d_yf, d_in,
+                                                                static_cast<typename Out::type*>(d_out), conv, sc.fill_in ? 1 : 0,
+                                                                sc.bad_in[0]);
+}
+
+template <bool NN>
+bool launch_staged_typed(dim3 grid, const GatherGeom& g, const TileTable& tt, const float* d_in, void* d_out, const SliceConv& sc,
+                         cudaStream_t st)
+{
+    if (!sc.convert_out) {
+        launch_staged_as<NN>(grid, g, tt, d_in, d_out, StorePlain(), sc, st);
+        return true;
+    }
+    switch (sc.out_type) {
+#define FB_CASE(TAG, T)                                                                                                                    \
+    case TAG:                                                                                                                              \
+        launch_staged_as<NN>(grid, g, tt, d_in, d_out, StoreAs<T>{cast_fill<T>(sc.fill_out)}, sc, st);                                     \
+        return true;
+        FB_CASE(FB_T_FLOAT, float)
+        FB_CASE(FB_T_DOUBLE, double)
+        FB_CASE(FB_T_CHAR, signed char)
+        FB_CASE(FB_T_SHORT, short)
+        FB_CASE(FB_T_INT, int)
+        FB_CASE(FB_T_UCHAR, unsigned char)
+        FB_CASE(FB_T_USHORT, unsigned short)
+        FB_CASE(FB_T_UINT, unsigned int)
+#undef FB_CASE
+    default:
+        return false;
+    }
+}
+} // namespace
+
+// output types the staged kernels convert to while storing (the others go through a float slab and a cast pass)
+bool staged_store_supports(int out_type)
+{
+    switch (out_type) {
+    case FB_T_FLOAT:
+    case FB_T_DOUBLE:
+    case FB_T_CHAR:
+    case FB_T_SHORT:
+    case FB_T_INT:
+    case FB_T_UCHAR:
+    case FB_T_USHORT:
+    case FB_T_UINT:
+        return true;
+    default:
+        return false;
+    }
+}
+
+int launch_gather_bilinear_staged(const GatherGeom& g, const TileTable& tt, const float* d_in, void* d_out, const SliceConv& sc,
+                                  cudaStream_t st)
 {
     if (g.out_level == 0 || g.nz == 0)
         return FB_OK;
     const unsigned tiles = (unsigned)tt.tiles_x * (unsigned)tt.tiles_y;
     dim3 grid(tiles, z_chunks(tiles, g.nz));
-    if (tt.nn)
-        k_gather_bilinear_staged<true><<<grid, kThreads, 0, st>>>(g, tt.tiles_x, tt.d_cells, tt.d_ncells, tt.d_meta, nullptr, nullptr, d_in, d_out);
-    else
-        k_gather_bilinear_staged<false><<<grid, kThreads, 0, st>>>(g, tt.tiles_x, tt.d_cells, tt.d_ncells, tt.d_meta, tt.d_xf, tt.d_yf, d_in,
-                                                                   d_out);
+    const bool ok = tt.nn ? launch_staged_typed<true>(grid, g, tt, d_in, d_out, sc, st) : launch_staged_typed<false>(grid, g, tt, d_in, d_out, sc, st);
+    FB_REQUIRE(ok, "staged gather: unsupported output type");
     count_launch();
     FB_CUDA_CHECK(cudaGetLastError());
     return FB_OK;

@@ -172,45 +172,28 @@ class Interpolator:
                                                                               self.y_axis.size, self.x_dim, self.y_dim)
 
     # ---- per slice ------------------------------------------------------------------------------
-    def getDataSlice(self, data, bad_value=np.nan, counterpart=None, direction="x", out_dtype=None):
+    def getDataSlice(self, data, bad_value=None, counterpart=None, direction="x", counterpart_bad_value=None):
         """CDMInterpolator::getDataSlice for an in-memory slice [.., y, x] of the FULL source grid (:235-287):
         crop to the reduced domain, fill -> NaN, interpolate, [rotate with the counterpart component], NaN -> fill
-        and cast back to the variable's type."""
+        and cast back to the variable's type -- one C-ABI call, the adapters run inside the gather kernel.
+        `bad_value` = CDM::getFillValue(varName): the _FillValue attribute, else the type's default."""
         ci = self.cachedInterpolation
         if ci is None:
             raise FimexB200Error("no cached interpolation: call changeProjection first")
         data = np.asarray(data)
-        dtype = np.dtype(out_dtype) if out_dtype is not None else data.dtype
+        if bad_value is None:
+            bad_value = capi.default_fill_value(data.dtype)
         lead = data.shape[:-2]
-        arr = self._to_interpolation_array(ci.getInputDataSlice(data), bad_value)
+        arr = ci.getInputDataSlice(data)
         if counterpart is not None and self.cachedVectorReprojection is not None:
-            other = self._to_interpolation_array(ci.getInputDataSlice(np.asarray(counterpart)), bad_value)
+            other = ci.getInputDataSlice(np.asarray(counterpart, dtype=data.dtype))
+            cbad = bad_value if counterpart_bad_value is None else counterpart_bad_value
             if "x" in direction:
-                out, _ = ci.interpolateVector(arr, other, self.cachedVectorReprojection)
+                out, _ = ci.getVectorSlice(arr, other, bad_value, cbad, self.cachedVectorReprojection)
             elif "y" in direction:
-                _, out = ci.interpolateVector(other, arr, self.cachedVectorReprojection)
+                _, out = ci.getVectorSlice(other, arr, cbad, bad_value, self.cachedVectorReprojection)
             else:
                 raise FimexB200Error(f"could not find x,y direction for vector, direction: {direction}")
         else:
-            out = ci.interpolateValues(arr)
-        out = self._from_interpolation_array(out, dtype, bad_value)
+            out = ci.getDataSlice(arr, bad_value)
         return out.reshape(lead + (ci.getOutY(), ci.getOutX()))
-
-    @staticmethod
-    def _to_interpolation_array(data, bad_value):
-        # data2InterpolationArray (:115-119): asFloat() then mifi_bad2nanf
-        arr = np.ascontiguousarray(data, dtype=np.float32)
-        if bad_value is not None and not np.isnan(bad_value):
-            arr = capi.mifi_bad2nanf(arr, np.float32(bad_value)).reshape(arr.shape)
-        return arr
-
-    @staticmethod
-    def _from_interpolation_array(out, dtype, bad_value):
-        # interpolationArray2Data (:121-124): NaN -> badValue, scale 1 / offset 0, cast (round for integer types)
-        if dtype == np.float32:
-            if bad_value is not None and not np.isnan(bad_value):
-                out = capi.mifi_nanf2bad(out, np.float32(bad_value)).reshape(out.shape)
-            return out
-        # other variable types need the fused NaN->fill + round + cast store (SURVEY.md 8f rank 1); doing that
-        # arithmetic in numpy here would be a CPU path, so it is refused until the device kernel exists
-        raise FimexB200Error(f"output type {dtype} not supported yet on the device path (float32 only)")

@@ -74,6 +74,22 @@ enum fb200_interpol_method {
 };
 #endif
 
+/* enum CDMDataType, include/fimex/CDMDataType.h:35-49 (same numbering) */
+enum fb200_datatype {
+    FB200_NAT = 0,
+    FB200_CHAR,
+    FB200_SHORT,
+    FB200_INT,
+    FB200_FLOAT,
+    FB200_DOUBLE,
+    FB200_STRING,
+    FB200_UCHAR,
+    FB200_USHORT,
+    FB200_UINT,
+    FB200_INT64,
+    FB200_UINT64
+};
+
 /* ------------------------------------------------------------------------------------------------
  * library state
  * ---------------------------------------------------------------------------------------------- */
@@ -190,6 +206,32 @@ int fb200_interp_interpolate_vector(const fb200_interp* handle, const fb200_vect
                                     size_t size, float* uOut, float* vOut, size_t* newSize);
 int fb200_interp_interpolate_vector_device(const fb200_interp* handle, const fb200_vector* vector, const float* d_uIn, const float* d_vIn,
                                            size_t size, float* d_uOut, float* d_vOut, size_t* newSize, void* cuda_stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (1c) the whole per-slice body of CDMInterpolator::getDataSlice in ONE call (src/CDMInterpolator.cc:250-285)
+ *
+ *   data2InterpolationArray  (:115-119)  Data::asFloat() + mifi_bad2nanf(badValue)      any CDM numeric type in
+ *   interpolateValues        (:258)
+ *   [reprojectValues         (:259-283)  with the counterpart component]
+ *   interpolationArray2Data  (:121-124)  NaN -> badValue, round + cast to the variable's type
+ *
+ * inType / outType: enum fb200_datatype of the input slice and of the variable; badValue: CDM::getFillValue(varName)
+ * (src/CDM.cc:505-522; NaN switches the input pass off, src/interpolation.c:1776).  On the staged gathers (bilinear,
+ * nearest neighbour / coord_nn, bicubic) both adapter passes run INSIDE the gather kernel: the fill -> NaN compare is
+ * applied once per staged source value and the output is written once, in the variable's type (a `short` variable
+ * halves the bytes stored).  Other methods / 64-bit integer outputs take a float slab and one conversion pass.
+ * outData: outX*outY*inZ elements of outType.  The pre/post-processes (fill2d, creepfill2d) are not part of this call.
+ * ---------------------------------------------------------------------------------------------- */
+int fb200_interp_get_data_slice(const fb200_interp* handle, int inType, const void* inData, size_t size, double badValue, int outType,
+                                void* outData, size_t* newSize);
+int fb200_interp_get_data_slice_device(const fb200_interp* handle, int inType, const void* d_inData, size_t size, double badValue,
+                                       int outType, void* d_outData, size_t* newSize, void* cuda_stream);
+/* the vector branch (:259-283): both components, each with its own fill value, rotated (vector may be NULL), converted */
+int fb200_interp_get_vector_slice(const fb200_interp* handle, const fb200_vector* vector, int inType, const void* uIn, const void* vIn,
+                                  size_t size, double badValueU, double badValueV, int outType, void* uOut, void* vOut, size_t* newSize);
+int fb200_interp_get_vector_slice_device(const fb200_interp* handle, const fb200_vector* vector, int inType, const void* d_uIn,
+                                         const void* d_vIn, size_t size, double badValueU, double badValueV, int outType, void* d_uOut,
+                                         void* d_vOut, size_t* newSize, void* cuda_stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (2) the reference's C symbols for this path -- include/fimex/interpolation.h (line of each prototype given)

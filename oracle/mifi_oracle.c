@@ -797,17 +797,56 @@ size_t orc_bad2nan(float* p, size_t n, float bad)
     return 0;
 }
 
-void orc_nan2fill_f32(const float* in, size_t n, double fill, float* out)
-{
-    for (size_t i = 0; i < n; ++i)
-        out[i] = isnan(in[i]) ? (float)fill : (float)(1. * in[i] + 0.);
-}
+/* data2InterpolationArray, src/CDMInterpolator.cc:115-119: Data::asFloat() is a static_cast per element
+ * (src/DataImpl.h:385-389, include/fimex/Utils.h:88-113: no rounding towards a floating-point type), then
+ * mifi_bad2nanf with the fill value narrowed to float (src/interpolation.c:1775-1783). */
+#define ORC_AS_FLOAT(NAME, T)                                                                                  \
+    void orc_as_float_##NAME(const T* in, size_t n, double bad, float* out)                                    \
+    {                                                                                                          \
+        const float b = (float)bad;                                                                            \
+        const float nanv = orc_undef_f();                                                                      \
+        for (size_t i = 0; i < n; ++i) {                                                                       \
+            const float f = (float)in[i];                                                                      \
+            out[i] = (!isnan(b) && f == b) ? nanv : f;                                                         \
+        }                                                                                                      \
+    }
+ORC_AS_FLOAT(i8, signed char)
+ORC_AS_FLOAT(i16, short)
+ORC_AS_FLOAT(i32, int)
+ORC_AS_FLOAT(f32, float)
+ORC_AS_FLOAT(f64, double)
+ORC_AS_FLOAT(u8, unsigned char)
+ORC_AS_FLOAT(u16, unsigned short)
+ORC_AS_FLOAT(u32, unsigned int)
+ORC_AS_FLOAT(i64, long long)
+ORC_AS_FLOAT(u64, unsigned long long)
 
-void orc_nan2fill_i16(const float* in, size_t n, double fill, int16_t* out)
-{
-    for (size_t i = 0; i < n; ++i)
-        out[i] = isnan(in[i]) ? (int16_t)fill : (int16_t)round(1. * in[i] + 0.);
-}
+/* interpolationArray2Data, src/CDMInterpolator.cc:121-124: convertDataType(MIFI_UNDEFINED_F, 1., 0., type, badValue, 1., 0.)
+ * = ScaleValue<float, OUT> (include/fimex/Utils.h:444-464): NaN -> static_cast<OUT>(badValue); otherwise
+ * data_caster<OUT, double>(1. * in + 0.), which rounds through MetNoFimex::round(double) -> int (::lround narrowed to int,
+ * Utils.h:72-75, 98-99) for integer OUT and is a plain static_cast for float / double. */
+#define ORC_FROM_FLOAT_INT(NAME, T)                                                                            \
+    void orc_from_float_##NAME(const float* in, size_t n, double fill, T* out)                                 \
+    {                                                                                                          \
+        for (size_t i = 0; i < n; ++i)                                                                         \
+            out[i] = isnan(in[i]) ? (T)fill : (T)(int)lround(1. * in[i] + 0.);                                 \
+    }
+#define ORC_FROM_FLOAT_FP(NAME, T)                                                                             \
+    void orc_from_float_##NAME(const float* in, size_t n, double fill, T* out)                                 \
+    {                                                                                                          \
+        for (size_t i = 0; i < n; ++i)                                                                         \
+            out[i] = isnan(in[i]) ? (T)fill : (T)(1. * in[i] + 0.);                                            \
+    }
+ORC_FROM_FLOAT_INT(i8, signed char)
+ORC_FROM_FLOAT_INT(i16, short)
+ORC_FROM_FLOAT_INT(i32, int)
+ORC_FROM_FLOAT_FP(f32, float)
+ORC_FROM_FLOAT_FP(f64, double)
+ORC_FROM_FLOAT_INT(u8, unsigned char)
+ORC_FROM_FLOAT_INT(u16, unsigned short)
+ORC_FROM_FLOAT_INT(u32, unsigned int)
+ORC_FROM_FLOAT_INT(i64, long long)
+ORC_FROM_FLOAT_INT(u64, unsigned long long)
 
 /* ------------------------------------------------------------------------------------------------
  * A18  coord_nearestneighbor search, src/CDMInterpolator.cc:1064-1125 (getGridDistance) and

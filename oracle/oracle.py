@@ -282,20 +282,31 @@ class Oracle(_Base):
         f(ap, a.size, bad)
         return a
 
-    def nan2fill(self, data, fill, dtype):
-        a, ap = _f(data)
-        if np.dtype(dtype) == np.float32:
-            out = np.empty(a.size, dtype=np.float32)
-            f = self.lib.orc_nan2fill_f32
-        elif np.dtype(dtype) == np.int16:
-            out = np.empty(a.size, dtype=np.int16)
-            f = self.lib.orc_nan2fill_i16
-        else:
-            raise ValueError(dtype)
+    _TAGS = {"int8": "i8", "int16": "i16", "int32": "i32", "float32": "f32", "float64": "f64", "uint8": "u8", "uint16": "u16",
+             "uint32": "u32", "int64": "i64", "uint64": "u64"}
+
+    def as_float(self, data, bad):
+        """data2InterpolationArray (CDMInterpolator.cc:115-119): any CDM numeric type -> float32 with badValue -> NaN"""
+        a = np.ascontiguousarray(data)
+        out = np.empty(a.shape, dtype=np.float32)
+        f = getattr(self.lib, "orc_as_float_" + self._TAGS[str(a.dtype)])
         f.restype = None
-        f.argtypes = [_fp, C.c_size_t, C.c_double, C.c_void_p]
-        f(ap, a.size, float(fill), out.ctypes.data_as(C.c_void_p))
+        f.argtypes = [C.c_void_p, C.c_size_t, C.c_double, C.c_void_p]
+        f(a.ctypes.data_as(C.c_void_p), a.size, float(bad), out.ctypes.data_as(C.c_void_p))
         return out
+
+    def from_float(self, data, fill, dtype):
+        """interpolationArray2Data (CDMInterpolator.cc:121-124): NaN -> fill, round + cast to `dtype`"""
+        a = np.ascontiguousarray(data, dtype=np.float32)
+        out = np.empty(a.shape, dtype=np.dtype(dtype))
+        f = getattr(self.lib, "orc_from_float_" + self._TAGS[str(np.dtype(dtype))])
+        f.restype = None
+        f.argtypes = [C.c_void_p, C.c_size_t, C.c_double, C.c_void_p]
+        f(a.ctypes.data_as(C.c_void_p), a.size, float(fill), out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def nan2fill(self, data, fill, dtype):
+        return self.from_float(data, fill, dtype).ravel()
 
     def coordnn(self, tlon, tlat, lon2d, lat2d, nx, ny):
         """fastTranslatePointsToClosestInputCell. Returns (px, py, n_exact_ties)."""

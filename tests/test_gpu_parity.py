@@ -591,6 +591,119 @@ def test_interpolator_config1_hirlam12_like(oracle):
 
 
 # =====================================================================================================
+# A1/A2: the whole slice body of getDataSlice in one call -- fill -> NaN while loading, NaN -> fill + round + cast
+# while storing (CDMInterpolator.cc:115-124, 250-285)
+# =====================================================================================================
+# (input type, variable type, fill value; None = the type's NetCDF default as CDM::getFillValue returns it)
+_TYPED = [(np.float32, np.float32, None), (np.int16, np.int16, None), (np.float32, np.int16, -32767.0), (np.int16, np.float32, -32767.0),
+          (np.float64, np.float64, None), (np.int32, np.int32, None), (np.uint8, np.uint8, None), (np.int8, np.int8, None),
+          (np.uint16, np.uint16, None), (np.uint32, np.uint32, 4000000000.0), (np.int64, np.int64, -9999.0), (np.uint64, np.uint64, 12345.0),
+          (np.float32, np.float32, np.nan)]
+
+
+def _typed_field(rng, shape, dtype, fill):
+    dt = np.dtype(dtype)
+    if dt.kind == "f":
+        a = rng.normal(250, 30, shape).astype(dt)
+    else:
+        info = np.iinfo(dt)
+        lo, hi = max(info.min, -30000), min(info.max, 30000)
+        a = rng.integers(lo, hi, shape, endpoint=True).astype(dt)
+    a[rng.random(shape) < 0.03] = dt.type(fill)
+    return a
+
+
+@pytest.mark.parametrize("method", [Method.BILINEAR, Method.NEAREST_NEIGHBOR, Method.BICUBIC, Method.COORD_NN])
+@pytest.mark.parametrize("in_dtype,out_dtype,fill", _TYPED)
+def test_get_data_slice_typed(oracle, method, in_dtype, out_dtype, fill):
+    inX, inY, inZ, outX, outY = 60, 50, 11, 200, 90
+    px, py = _smooth_positions(inX, inY, outX, outY, 17.0, 5.0, 3)
+    rng = np.random.default_rng(int(method) * 100 + np.dtype(in_dtype).itemsize)
+    if fill is None:
+        fill = fb.default_fill_value(in_dtype)
+    data = _typed_field(rng, (inZ, inY, inX), in_dtype, fill)
+    if np.isnan(fill):
+        data[0, 0, 0] = -0.0  # a NaN fill value switches the input pass off; the output pass still turns -0 into +0
+    ci = fb.CachedInterpolation("x", "y", method, px, py, inX, inY, outX, outY)
+    got = ci.getDataSlice(data, fill, out_dtype)
+    assert got.dtype == np.dtype(out_dtype) and got.shape == (inZ, outY, outX)
+    interp = oracle.cached_interpolate(int(method), px, py, inX, inY, outX, outY, oracle.as_float(data, fill))
+    want = oracle.from_float(interp, fill, out_dtype).reshape(got.shape)
+    if np.dtype(out_dtype).kind == "f":
+        bits = np.uint32 if got.itemsize == 4 else np.uint64
+        same = (got.view(bits) == want.view(bits)) | (np.isnan(got) & np.isnan(want))  # NaN only when the fill value is NaN
+        assert same.all()
+    else:
+        assert np.array_equal(got, want)
+    if np.isnan(fill):
+        assert np.isnan(want).any()
+    else:
+        assert (want == np.dtype(out_dtype).type(fill)).any()  # the fill value came through both adapters
+
+
+@pytest.mark.parametrize("method", [Method.BILINEAR, Method.BICUBIC, Method.FORWARD_MEAN])
+def test_get_data_slice_device_and_unfused_paths(oracle, method, monkeypatch):
+    import torch
+    inX, inY, inZ, outX, outY = 60, 50, 70, 203, 77  # outX not a multiple of 4; two level chunks
+    rng = np.random.default_rng(5)
+    fill = -32767.0
+    data = _typed_field(rng, (inZ, inY, inX), np.int16, fill)
+    if method == Method.FORWARD_MEAN:
+        px = rng.uniform(-1, outX, inX * inY)
+        py = rng.uniform(-1, outY, inX * inY)
+        ci = fb.CachedForwardInterpolation("x", "y", method, px, py, inX, inY, outX, outY)
+        interp = oracle.forward_interpolate(int(method), px, py, inX, inY, outX, outY, oracle.as_float(data, fill))
+    else:
+        px, py = _smooth_positions(inX, inY, outX, outY, -33.0, 6.5, 3)
+        ci = fb.CachedInterpolation("x", "y", method, px, py, inX, inY, outX, outY)
+        interp = oracle.cached_interpolate(int(method), px, py, inX, inY, outX, outY, oracle.as_float(data, fill))
+    want = oracle.from_float(interp, fill, np.int16).reshape(inZ, outY, outX)
+    host = ci.getDataSlice(data, fill)
+    assert np.array_equal(host, want)
+    dev = ci.getDataSlice(torch.from_numpy(data).cuda(), fill)
+    assert dev.dtype == torch.int16 and np.array_equal(dev.cpu().numpy(), want)
+    # float in / float out with a fill value: in-kernel compare + in-kernel NaN -> fill
+    fdata = oracle.as_float(data, np.nan)
+    f32fill = fb.default_fill_value(np.float32)
+    fdata[fdata == fill] = f32fill
+    gotf = ci.getDataSlice(torch.from_numpy(fdata).cuda(), f32fill).cpu().numpy()
+    wantf = oracle.from_float(interp, f32fill, np.float32).reshape(gotf.shape)
+    assert np.array_equal(gotf.view(np.uint32), wantf.view(np.uint32))
+    if method != Method.FORWARD_MEAN:  # the same through the direct (unstaged) kernels + conversion passes
+        monkeypatch.setenv("FIMEX_B200_DIRECT_GATHER", "1")
+        cd = fb.CachedInterpolation("x", "y", method, px, py, inX, inY, outX, outY)
+        monkeypatch.delenv("FIMEX_B200_DIRECT_GATHER")
+        assert np.array_equal(cd.getDataSlice(data, fill), want)
+        assert np.array_equal(cd.getDataSlice(fdata, f32fill).view(np.uint32), wantf.view(np.uint32))
+
+
+@pytest.mark.parametrize("method", [Method.BILINEAR, Method.BICUBIC, Method.NEAREST_NEIGHBOR])
+@pytest.mark.parametrize("dtype", [np.float32, np.int16])
+def test_get_vector_slice_typed(oracle, method, dtype):
+    inX, inY, inZ, outX, outY = 60, 50, 9, 200, 90
+    px, py = _smooth_positions(inX, inY, outX, outY, 17.0, 5.0, 3)
+    rng = np.random.default_rng(31)
+    fu, fv = fb.default_fill_value(dtype), (-9999.0 if np.dtype(dtype).kind == "f" else -9999)
+    u = _typed_field(rng, (inZ, inY, inX), dtype, fu)
+    v = _typed_field(rng, (inZ, inY, inX), dtype, fv)
+    phi = rng.uniform(-np.pi, np.pi, outX * outY)
+    matrix = np.stack([np.cos(phi), np.sin(phi), -np.sin(phi), phi], axis=1).ravel()
+    ci = fb.CachedInterpolation("x", "y", method, px, py, inX, inY, outX, outY)
+    cvr = fb.CachedVectorReprojection(fb.MIFI_VECTOR_KEEP_SIZE, matrix, outX, outY)
+    gu, gv = ci.getVectorSlice(u, v, fu, fv, cvr)
+    ui = oracle.cached_interpolate(int(method), px, py, inX, inY, outX, outY, oracle.as_float(u, fu))
+    vi = oracle.cached_interpolate(int(method), px, py, inX, inY, outX, outY, oracle.as_float(v, fv))
+    wu, wv = oracle.vector_reproject_by_matrix(matrix, ui, vi, outX, outY, inZ)
+    wu = oracle.from_float(wu, fu, dtype).reshape(gu.shape)
+    wv = oracle.from_float(wv, fv, dtype).reshape(gv.shape)
+    if np.dtype(dtype).kind == "f":
+        assert np.array_equal(gu.view(np.uint32), wu.view(np.uint32)) and np.array_equal(gv.view(np.uint32), wv.view(np.uint32))
+    else:
+        assert np.array_equal(gu, wu) and np.array_equal(gv, wv)
+    assert (wu == np.dtype(dtype).type(fu)).any() and (wv == np.dtype(dtype).type(fv)).any()
+
+
+# =====================================================================================================
 # full BASELINE size (config 2): properties that need no oracle run over 5e8 values
 # =====================================================================================================
 def test_full_size_bilinear_properties(oracle):

@@ -255,3 +255,57 @@ def test_oracle_cached_loop_equals_reference_kernels(oracle, reference):
         a = oracle.cached_interpolate(m, px, py, inX, inY, outX, outY, field, nthreads=3)
         b = reference.cached_interpolate(m, px, py, inX, inY, outX, outY, field)
         assert_bit_equal(a, b, f"cached loop method {m}")
+
+
+# ---------------------------------------------------------------------------------------------------
+# A2: the type / fill-value adapters either side of the gather (CDMInterpolator.cc:115-124)
+# ---------------------------------------------------------------------------------------------------
+def test_adapters_known_answers(oracle):
+    """ScaleValue<float, OUT>(NaN, 1, 0, fill, 1, 0) (include/fimex/Utils.h:444-464) lives in a C++ template that cannot
+    be compiled here (Boost): its restatement is pinned by the semantics the header spells out -- lround for integer
+    targets (half away from zero), plain casts for floating point, NaN -> fill, '+ 0.' turning -0 into +0."""
+    v = np.array([2.5, -2.5, 0.49999997, -0.5, 1e9, np.nan, -0.0, 3.4e38, 255.5, -1.0], dtype=np.float32)
+    assert oracle.from_float(v[:6], -32767, np.int16).tolist() == [3, -3, 0, -1, np.int16(np.int32(1000000000)), -32767]
+    assert oracle.from_float(v[:4], -127, np.int8).tolist() == [3, -3, 0, -1]
+    assert oracle.from_float(v[[0, 5, 9]], 255, np.uint8).tolist() == [3, 255, 255]  # (unsigned char)(int)-1 == 255
+    assert oracle.from_float(v[[0, 4, 5]], -2147483647, np.int32).tolist() == [3, 1000000000, -2147483647]
+    f = oracle.from_float(v[[5, 6, 7]], 9.96921e36, np.float32)
+    assert f[0] == np.float32(9.96921e36) and f[2] == np.float32(3.4e38)
+    assert f[1] == 0 and not np.signbit(f[1])  # -0 + 0. == +0
+    d = oracle.from_float(v[[0, 5]], 9.96921e36, np.float64)
+    assert d[0] == 2.5 and d[1] == 9.96921e36
+    # asFloat + mifi_bad2nanf: the fill value is compared after narrowing to float; a NaN fill value disables the pass
+    s = np.array([-32767, 0, 5, 32767], dtype=np.int16)
+    a = oracle.as_float(s, -32767)
+    assert np.isnan(a[0]) and a[1:].tolist() == [0.0, 5.0, 32767.0]
+    assert a.view(np.uint32)[0] == 0x7fc00000
+    assert not np.isnan(oracle.as_float(s, np.nan)).any()
+    big = np.array([2**53 + 1, -7], dtype=np.int64)
+    assert oracle.as_float(big, 0).tolist() == [float(np.float32(2**53)), -7.0]
+    dbl = np.array([9.9692099683868690e+36, 1.0000000001], dtype=np.float64)
+    a = oracle.as_float(dbl, 9.9692099683868690e+36)
+    assert np.isnan(a[0]) and a[1] == 1.0
+
+
+def test_adapters_against_reference(oracle, reference):
+    """mifi_bad2nanf / mifi_nanf2bad are part of the reference's src/interpolation.c (:1775-1793): the float forms of the
+    restated adapters must agree with them bit for bit."""
+    import ctypes as C
+    rng = np.random.default_rng(77)
+    v = rng.normal(0, 100, 5000).astype(np.float32)
+    fill = np.float32(9.9692099683868690e+36)
+    v[rng.integers(0, v.size, 200)] = fill
+    v[rng.integers(0, v.size, 50)] = np.nan
+    a = v.copy()
+    f = reference.lib.mifi_bad2nanf
+    f.restype = C.c_size_t
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_float]
+    f(a.ctypes.data, a.ctypes.data + a.nbytes, fill)
+    assert_bit_equal(oracle.as_float(v, float(fill)), a, "bad2nan", nan_payload=False)
+    assert np.array_equal(np.isnan(a), np.isnan(v) | (v == fill))
+    b = a.copy()
+    g = reference.lib.mifi_nanf2bad
+    g.restype = C.c_size_t
+    g.argtypes = [C.c_void_p, C.c_void_p, C.c_float]
+    g(b.ctypes.data, b.ctypes.data + b.nbytes, fill)
+    assert_bit_equal(oracle.from_float(a, float(fill), np.float32), b, "nan2bad")
