@@ -10,6 +10,11 @@ timed region.  N > 1: one process per GPU (torchrun), each owning its own contig
 scaling); rank 0 computes the index tables on its GPU and broadcasts the two fp64 position tables over NCCL.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--method bilinear|nearestneighbor|bicubic]
+                    [--variant plain|fill|short]
+
+--variant (default plain = CachedInterpolation::interpolateValues, the BASELINE workload) selects the whole slice body of
+CDMInterpolator::getDataSlice instead, with its two adapter passes fused into the gather kernel: `fill` = float32 field
+with 1 % fill values (9.96921e+36) in, float32 with fill values out; `short` = a packed int16 variable in and out.
 
 --impl reference times the reference's own CPU implementation of the path (oracle/_ref: the reference's
 interpolation.c compiled unmodified, inside the restated CachedInterpolation loop, OpenMP over all host cores) on a
@@ -239,11 +244,25 @@ def main_b200(args):
     tt = (torch.arange(nlev, device=dev) // NZ).to(torch.float32)[:, None, None]
     d_in = 250 + 30 * torch.sin(la) * torch.cos(2 * lo) + 0.1 * zz + tt
     d_in = (d_in + 0.5 * torch.randn((nlev, inY, inX), generator=g, device=dev, dtype=torch.float32)).contiguous()
-    d_out = torch.empty(nlev * OUT_N * OUT_N, device=dev, dtype=torch.float32)
     values_per_step = nlev * OUT_N * OUT_N
+    in_elem = out_elem = 4
+    fill = None
+    if args.variant == "fill":  # SURVEY.md 8d variant B: 1 % undefined values, marked with the NetCDF default fill value
+        fill = fb.default_fill_value(np.float32)
+        d_in[torch.rand(d_in.shape, generator=g, device=dev) < 0.01] = fill
+    elif args.variant == "short":  # a packed variable: scale 0.01, offset 250 -> int16, fill -32767
+        fill = -32767.0
+        packed = torch.clamp(torch.round((d_in - 250.0) / 0.01), -32000, 32000).to(torch.int16)
+        packed[torch.rand(d_in.shape, generator=g, device=dev) < 0.01] = -32767
+        d_in = packed.contiguous()
+        in_elem = out_elem = 2
+    d_out = torch.empty(nlev * OUT_N * OUT_N, device=dev, dtype=d_in.dtype)
 
     def step():
-        ci.interpolateValues(d_in, out=d_out)
+        if fill is None:
+            ci.interpolateValues(d_in, out=d_out)
+        else:
+            ci.getDataSlice(d_in, fill, out=d_out)
 
     def barrier():
         if world > 1:
@@ -277,15 +296,15 @@ def main_b200(args):
     # ---- roofline of the dominant (only) kernel of the step ------------------------------------------------------
     peak, peak_src = peaks()
     n_out, n_fp = OUT_N * OUT_N, inX * inY
-    alg_bytes = 4 * n_out * nlev + 4 * n_fp * nlev + 16 * n_out  # store + compulsory load + two fp64 positions
+    alg_bytes = out_elem * n_out * nlev + in_elem * n_fp * nlev + 16 * n_out  # store + compulsory load + two fp64 positions
     kernel_ms = float(np.mean(per_launch_ms))
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_src,
-                "kernel": {0: "k_gather_nn", 1: "k_gather_bilinear_staged", 2: "k_gather_bicubic"}[method_id],
+                "kernel": {0: "k_gather_bilinear_staged<NN>", 1: "k_gather_bilinear_staged", 2: "k_gather_bicubic_staged"}[method_id],
                 "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_output_value": alg_bytes / values_per_step,
                 "kernel_ms": kernel_ms,
-                "formula": "4*N_out*Z (store) + 4*N_fp*Z (compulsory load of the cropped footprint) + 16*N_out (two fp64 positions)",
+                "formula": f"{out_elem}*N_out*Z (store) + {in_elem}*N_fp*Z (compulsory load of the cropped footprint) + 16*N_out (two fp64 positions)",
                 "n_out": n_out, "n_fp": n_fp, "levels": nlev}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
@@ -298,27 +317,35 @@ def main_b200(args):
     # ---- e2e: the same workload through the C ABI with HOST buffers (pinned); copies inside the timed region ----
     e2e = None
     if not args.no_e2e:
-        h_in = torch.empty((NZ, inY, inX), dtype=torch.float32, pin_memory=True)
+        h_in = torch.empty((NZ, inY, inX), dtype=d_in.dtype, pin_memory=True)
         h_in.copy_(d_in[:NZ].cpu())
-        h_out = torch.empty(NZ * OUT_N * OUT_N, dtype=torch.float32, pin_memory=True)
+        h_out = torch.empty(NZ * OUT_N * OUT_N, dtype=d_in.dtype, pin_memory=True)
         hin_np, hout_np = h_in.numpy(), h_out.numpy()
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
-        ci.interpolateValues(hin_np, out=hout_np)  # warm-up: scratch pool, page mapping
+
+        def host_call():
+            if fill is None:
+                ci.interpolateValues(hin_np, out=hout_np)
+            else:
+                ci.getDataSlice(hin_np, fill, out=hout_np)
+
+        host_call()  # warm-up: scratch pool, page mapping
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             for _t in range(args.times):  # 24 time steps, one getDataSlice-sized call each (the way a Fimex host calls it)
-                ci.interpolateValues(hin_np, out=hout_np)
+                host_call()
         barrier()
         dt = time.perf_counter() - t0
         tt_ = torch.tensor([dt], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
         dt = float(tt_.item())
-        e2e = {"value": world * values_per_step * e2e_steps / dt, "unit": "values/s", "h2d_bytes_per_step": int(4 * n_fp * nlev),
-               "d2h_bytes_per_step": int(4 * n_out * nlev), "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
-               "how": "fb200_interp_interpolate_values (C ABI) on pinned host buffers, 24 calls of 137 levels per step, "
-                      "H2D + kernel + D2H pipelined in 3 streams inside the call",
+        e2e = {"value": world * values_per_step * e2e_steps / dt, "unit": "values/s", "h2d_bytes_per_step": int(in_elem * n_fp * nlev),
+               "d2h_bytes_per_step": int(out_elem * n_out * nlev), "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
+               "how": ("fb200_interp_interpolate_values" if fill is None else "fb200_interp_get_data_slice") +
+                      " (C ABI) on pinned host buffers, 24 calls of 137 levels per step, H2D + kernel + D2H pipelined in 3 streams "
+                      "inside the call",
                "checksum": float(hout_np[::100003].astype(np.float64).sum())}
 
     # ---- CPU baseline (rank 0, N == 1 only): the reference's kernels on this box's host cores -----------------
@@ -333,11 +360,12 @@ def main_b200(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "values/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.variant != "short" else "f32 (int16 in HBM)",
             "data": "synthetic",
             "config": {"workload": workload_name(method) if args.times == NT else workload_name(method) + f" [REDUCED to {args.times} time steps: profiling only]", "levels_per_gpu": nlev, "source_footprint": [int(inX), int(inY)],
                        "crop_offset": [int(x0), int(y0)], "l2": "inputs+outputs >> L2 (52.6 GB written per step), no flush needed",
-                       "parallelism": f"slab{world}", "setup_s": setup_s},
+                       "parallelism": f"slab{world}", "setup_s": setup_s, "variant": args.variant},
             "hbm_gbs": achieved, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line))
@@ -353,6 +381,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--method", default="bilinear", choices=sorted(METHODS))
+    ap.add_argument("--variant", default="plain", choices=["plain", "fill", "short"],
+                    help="plain: interpolateValues (BASELINE workload); fill / short: the whole getDataSlice body with fused adapters")
     ap.add_argument("--times", type=int, default=NT, help="time steps per GPU slab (24 = the BASELINE workload; fewer only for profiling)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")

@@ -137,7 +137,7 @@ class CachedInterpolationInterface:
 
 
     # -- the whole slice body of CDMInterpolator::getDataSlice in one call ---------------------------
-    def getDataSlice(self, inData, badValue, outType=None, stream=None):
+    def getDataSlice(self, inData, badValue, outType=None, stream=None, out=None):
         """data2InterpolationArray -> interpolateValues -> interpolationArray2Data (CDMInterpolator.cc:250-258, 284-285):
         `inData` [inZ][inY][inX] of any CDM numeric type (numpy array or CUDA tensor), `badValue` = CDM::getFillValue of the
         variable, result [inZ][outY][outX] in `outType` (default: the input's type)."""
@@ -149,7 +149,11 @@ class CachedInterpolationInterface:
                 raise FimexB200Error("device path needs a contiguous CUDA tensor")
             out_dtype = outType if outType is not None else inData.dtype
             n = int(lib.fb200_interp_new_size(self._h, inData.numel()))
-            out = torch.empty(n, dtype=out_dtype, device=inData.device)
+            if out is None:
+                out = torch.empty(n, dtype=out_dtype, device=inData.device)
+            elif out.numel() < n or out.dtype != out_dtype or not out.is_contiguous():
+                raise FimexB200Error("output tensor too small, of the wrong type or not contiguous")
+            out = out.view(-1)[:n]
             check(lib.fb200_interp_get_data_slice_device(self._h, int(capi.cdm_type(inData.dtype)), ptr(inData), inData.numel(), float(badValue),
                                                          int(capi.cdm_type(out_dtype)), ptr(out), C.byref(new_size), _stream_ptr(stream)),
                   "getDataSlice")
@@ -157,7 +161,11 @@ class CachedInterpolationInterface:
             a = np.ascontiguousarray(inData)
             out_dtype = np.dtype(outType) if outType is not None else a.dtype
             n = int(lib.fb200_interp_new_size(self._h, a.size))
-            out = np.empty(n, dtype=out_dtype)
+            if out is None:
+                out = np.empty(n, dtype=out_dtype)
+            elif out.size < n or out.dtype != out_dtype or not out.flags.c_contiguous:
+                raise FimexB200Error("output array too small, of the wrong type or not contiguous")
+            out = out.reshape(-1)[:n]
             check(lib.fb200_interp_get_data_slice(self._h, int(capi.cdm_type(a.dtype)), ptr(a), a.size, float(badValue),
                                                   int(capi.cdm_type(out_dtype)), ptr(out), C.byref(new_size)), "getDataSlice")
         nz = n // max(1, self.getOutX() * self.getOutY())

@@ -33,7 +33,21 @@ namespace fb {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kTileX = 32, kTileY = 32, kTilePts = kTileX * kTileY;  // 1024 points; lane = x, warp w owns rows w, w+8, w+16, w+24
+constexpr int kTilePts = 1024;
+// Tile shapes (1024 target points, 4 per thread).  Measured on B200 (scratch/ubench/store_bw.cu, pure stores, 64-level
+// chunks): tiles whose rows are 128 B wide reach 5.66 TB/s, 256 B rows 6.35 TB/s, 512 B rows written with 128-bit stores
+// 7.1 TB/s -- the wider the contiguous run a CTA writes per row, the fewer DRAM pages are open at once.  The width a
+// bilinear warp can cover is limited by shared-memory banks instead: the 32 lanes of a load should see fewer than 32
+// distinct taps, i.e. span fewer than ~30 source cells.
+//   bilinear: 64 x 16, lane = x, thread t owns (t & 63, (t >> 6) + 4k): a row is written by two neighbouring warps
+//   nearest neighbour: 128 x 8, thread t owns (4 (t & 31) + k, t >> 5): one 128-bit store per thread and level
+template <bool NN>
+struct Tile {
+    static constexpr int X = NN ? 128 : 64, Y = NN ? 8 : 16;
+    // position of point k of thread t inside the tile
+    static __device__ __forceinline__ int px(int t, int k) { return NN ? 4 * (t & 31) + k : (t & 63); }
+    static __device__ __forceinline__ int py(int t, int k) { return NN ? (t >> 5) : (t >> 6) + 4 * k; }
+};
 constexpr int kMaxTaps = 4 * kTilePts;                              // worst case: every point has its own 4 taps
 constexpr int kStageFloats = 4096;                                  // one staging buffer (16 KB), two of them
 constexpr int kMaxBatch = 8;                                        // levels staged per barrier
@@ -53,14 +67,12 @@ __global__ void __launch_bounds__(kThreads) k_compile_tiles(const double* __rest
     const int tile = blockIdx.x;
     const int t = threadIdx.x;
     const int tx = tile % tiles_x, ty = tile / tiles_x;
-    const int x = tx * kTileX + (t & 31);
-    const int yw = ty * kTileY + (t >> 5);
     int off[4], mode[4];
     float xf[4], yf[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         int4 e = make_int4(0, 0, 0, FB_BL_NAN);
-        const int y = yw + 8 * k;
+        const int x = tx * Tile<NN>::X + Tile<NN>::px(t, k), y = ty * Tile<NN>::Y + Tile<NN>::py(t, k);
         if (y < oy && x < ox) {
             const long long i = (long long)y * ox + x;
             e = NN ? classify_nn(px[i], py[i], ix, iy) : classify_bilinear(px[i], py[i], ix, iy);
@@ -187,7 +199,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_gather_bilinear_staged(GatherGe
                                                                      const int* __restrict__ ntaps_tab, const uint4* __restrict__ meta,
                                                                      const float4* __restrict__ xf4, const float4* __restrict__ yf4,
                                                                      const float* __restrict__ in, typename Out::type* __restrict__ out,
-                                                                     Out conv, int fill_in, float bad_in)
+                                                                     Out conv, int fill_in, float bad_in, int vec_ok)
 {
     __shared__ float s_stage[2][kStageFloats]; // double buffer: batch b+1 lands while batch b is consumed
     const int tile = blockIdx.x;
@@ -212,20 +224,21 @@ __global__ void __launch_bounds__(kThreads, 3) k_gather_bilinear_staged(GatherGe
         wy0[k] = __fsub_rn(1.f, yf[k]);
         all_full = all_full && (mode[k] == (NN ? FB_BL_NEAR : FB_BL_FULL));
     }
-    // lane = x inside the tile: a warp reads 32 consecutive target points of one row per shared load (a handful
-    // of neighbouring taps: no bank conflicts) and writes 128 contiguous bytes per store
+    // a warp owns 128 consecutive target points of one row, lane l the points 4l .. 4l+3: neighbouring lanes read the same
+    // or neighbouring taps (broadcast / distinct banks) and the warp writes 512 contiguous bytes per level
     const int tx = tile % tiles_x, ty = tile / tiles_x;
-    const int x = tx * kTileX + (t & 31);
-    const int yw = ty * kTileY + (t >> 5);
-    int nvalid = 0; // rows yw + 8k, k < nvalid, exist (rows are visited in increasing k)
-    if (x < g.ox)
-        nvalid = yw >= g.oy ? 0 : (g.oy - yw + 7) / 8;
+    // points k < nvalid of this thread exist (k runs along x for nearest neighbour, down the rows for bilinear)
+    const int x0 = tx * Tile<NN>::X + Tile<NN>::px(t, 0), y0 = ty * Tile<NN>::Y + Tile<NN>::py(t, 0);
+    int nvalid = 0;
+    if (y0 < g.oy && x0 < g.ox)
+        nvalid = NN ? g.ox - x0 : (g.oy - y0 + 3) / 4;
     nvalid = nvalid > 4 ? 4 : nvalid;
     const long long per = (g.nz + gridDim.y - 1) / gridDim.y;
     const long long z0 = (long long)blockIdx.y * per;
     const long long z1 = z0 + per < g.nz ? z0 + per : g.nz;
-    typename Out::type* o = out + z0 * g.out_level + (long long)yw * g.ox + x;
-    const long long row8 = 8ll * g.ox;
+    // element offset of point 0 inside a level, and from point k to point k+1
+    const unsigned off0 = (unsigned)y0 * (unsigned)g.ox + (unsigned)x0;
+    const unsigned kstep = NN ? 1u : 4u * (unsigned)g.ox;
     // Two staging layouts.  fast: tap-major, element (tap r, level zi) at r*9 + zi -- a thread's eight row pointers are then
     // constant for a whole batch and the level is an immediate offset of the shared load (no address arithmetic in the
     // inner loop; 9 is odd, so any 32 taps with distinct r mod 32 still hit distinct banks).  Tiles with more than 455 taps
@@ -300,6 +313,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_gather_bilinear_staged(GatherGe
         if (nvalid == 0)
             continue;
         const float* lvl = s_stage[buf];
+        typename Out::type* base = out + z * g.out_level; // uniform across the CTA
         if (fast && all_full && nvalid == 4) {
             const float* pa[4];
             const float* pb[4];
@@ -308,27 +322,39 @@ __global__ void __launch_bounds__(kThreads, 3) k_gather_bilinear_staged(GatherGe
                 pa[k] = lvl + ia[k] * kLvlStride;
                 pb[k] = lvl + ib[k] * kLvlStride;
             }
+            auto one_level = [&](int zi) {
+                float r[4];
 #pragma unroll
-            for (int zi = 0; zi < kMaxBatch; ++zi) {
-                if (zi < nb) {
-                    float r[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (NN) { // copied value, bit for bit (interpolation.c:869-871)
-                            r[k] = pa[k][zi];
-                        } else {
-                            const float s00 = pa[k][zi], s01 = pa[k][kLvlStride + zi], s10 = pb[k][zi], s11 = pb[k][kLvlStride + zi];
-                            const float top = __fadd_rn(__fmul_rn(wx0[k], s00), __fmul_rn(xf[k], s01));
-                            const float bot = __fadd_rn(__fmul_rn(wx0[k], s10), __fmul_rn(xf[k], s11));
-                            r[k] = __fadd_rn(__fmul_rn(wy0[k], top), __fmul_rn(yf[k], bot));
-                        }
+                for (int k = 0; k < 4; ++k) {
+                    if (NN) { // copied value, bit for bit (interpolation.c:869-871)
+                        r[k] = pa[k][zi];
+                    } else {
+                        const float s00 = pa[k][zi], s01 = pa[k][kLvlStride + zi], s10 = pb[k][zi], s11 = pb[k][kLvlStride + zi];
+                        const float top = __fadd_rn(__fmul_rn(wx0[k], s00), __fmul_rn(xf[k], s01));
+                        const float bot = __fadd_rn(__fmul_rn(wx0[k], s10), __fmul_rn(xf[k], s11));
+                        r[k] = __fadd_rn(__fmul_rn(wy0[k], top), __fmul_rn(yf[k], bot));
                     }
-                    __stcs(o, conv(r[0]));
-                    __stcs(o + row8, conv(r[1]));
-                    __stcs(o + 2 * row8, conv(r[2]));
-                    __stcs(o + 3 * row8, conv(r[3]));
-                    o += g.out_level;
                 }
+                typename Out::type* dst = base + off0;
+                if (NN && vec_ok) {
+                    store_vec4<typename Out::type>(dst, conv(r[0]), conv(r[1]), conv(r[2]), conv(r[3]));
+                } else {
+                    __stcs(dst, conv(r[0]));
+                    __stcs(dst + kstep, conv(r[1]));
+                    __stcs(dst + 2 * kstep, conv(r[2]));
+                    __stcs(dst + 3 * kstep, conv(r[3]));
+                }
+                base += g.out_level;
+            };
+            if (nb == kMaxBatch) { // full batch: no per-level test
+#pragma unroll
+                for (int zi = 0; zi < kMaxBatch; ++zi)
+                    one_level(zi);
+            } else {
+#pragma unroll
+                for (int zi = 0; zi < kMaxBatch; ++zi)
+                    if (zi < nb)
+                        one_level(zi);
             }
         } else { // grid edge, partial tile or a tile with many taps: per-point mode (interpolation.c:904-953)
             const int sr = fast ? kLvlStride : 1;      // stride between neighbouring taps
@@ -359,9 +385,9 @@ __global__ void __launch_bounds__(kThreads, 3) k_gather_bilinear_staged(GatherGe
                         break;
                     }
                     if (k < nvalid)
-                        __stcs(o + k * row8, conv(v));
+                        __stcs(base + off0 + (unsigned)k * kstep, conv(v));
                 }
-                o += g.out_level;
+                base += g.out_level;
             }
         }
     }
@@ -372,15 +398,16 @@ __global__ void __launch_bounds__(kThreads, 3) k_gather_bilinear_staged(GatherGe
 bool tile_table_supported(int ix, int iy, int ox, int oy)
 {
     const long long in_level = (long long)ix * iy;
-    const long long tiles = (long long)((ox + kTileX - 1) / kTileX) * ((oy + kTileY - 1) / kTileY);
+    const long long tiles = (long long)((ox + 63) / 64) * ((oy + 7) / 8); // at least as many as either tile shape needs
     return in_level > 0 && in_level < (1ll << 30) && ox > 0 && oy > 0 && tiles < 2147483647LL;
 }
 
 int tile_table_build(bool nn, const double* d_px, const double* d_py, int ix, int iy, int ox, int oy, TileTable* tt, cudaStream_t st)
 {
     tile_table_free(tt);
-    tt->tiles_x = (ox + kTileX - 1) / kTileX;
-    tt->tiles_y = (oy + kTileY - 1) / kTileY;
+    const int tile_x = nn ? Tile<true>::X : Tile<false>::X, tile_y = nn ? Tile<true>::Y : Tile<false>::Y;
+    tt->tiles_x = (ox + tile_x - 1) / tile_x;
+    tt->tiles_y = (oy + tile_y - 1) / tile_y;
     const size_t tiles = (size_t)tt->tiles_x * tt->tiles_y;
     FB_CUDA_CHECK(cudaMalloc(&tt->d_cells, sizeof(int) * tiles * kMaxTaps));
     FB_CUDA_CHECK(cudaMalloc(&tt->d_ncells, sizeof(int) * tiles));
@@ -422,7 +449,8 @@ void launch_staged_as(dim3 grid, const GatherGeom& g, const TileTable& tt, const
 {
     k_gather_bilinear_staged<NN, Out><<<grid, kThreads, 0, st>>>(g, tt.tiles_x, tt.d_cells, tt.d_ncells, tt.d_meta, tt.d_xf, tt.d_yf, d_in,
                                                                 static_cast<typename Out::type*>(d_out), conv, sc.fill_in ? 1 : 0,
-                                                                sc.bad_in[0]);
+                                                                sc.bad_in[0],
+                                                                ((g.ox % 4) == 0 && (reinterpret_cast<uintptr_t>(d_out) & (4 * sizeof(typename Out::type) - 1)) == 0) ? 1 : 0);
 }
 
 template <bool NN>

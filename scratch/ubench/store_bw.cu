@@ -1,0 +1,81 @@
+// store-bandwidth ceilings on B200 for the access patterns of the gather kernels (no loads, no math)
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
+
+__global__ void k_linear(float4* out, size_t n4)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+        __stcs(out + i, make_float4(1.f, 2.f, 3.f, 4.f));
+}
+
+// CTA = tile of TX x TY points of a level of ox x oy, 256 threads, lane = x (TX/32 segments per row), chunk of levels
+template <int TX, int TY, int VEC>
+__global__ void k_tiles(float* out, int ox, int oy, int nz, int chunk)
+{
+    const int tiles_x = ox / TX;
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    const int z0 = blockIdx.y * chunk, z1 = min(nz, z0 + chunk);
+    constexpr int per_row = TX / VEC;            // threads per tile row
+    constexpr int rows_per_pass = 256 / per_row; // rows written per pass of the CTA
+    const int lx = (threadIdx.x % per_row) * VEC, ly = threadIdx.x / per_row;
+    const size_t level = (size_t)ox * oy;
+    for (int z = z0; z < z1; ++z) {
+        float* base = out + z * level + (size_t)(ty * TY) * ox + tx * TX + lx;
+#pragma unroll
+        for (int r = ly; r < TY; r += rows_per_pass) {
+            if (VEC == 4)
+                __stcs(reinterpret_cast<float4*>(base + (size_t)r * ox), make_float4(1.f, 2.f, 3.f, (float)z));
+            else
+                __stcs(base + (size_t)r * ox, (float)z);
+        }
+    }
+}
+
+template <class F>
+float time_ms(F f, int reps = 5)
+{
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    f(); f();
+    cudaEventRecord(a);
+    for (int i = 0; i < reps; ++i) f();
+    cudaEventRecord(b);
+    CK(cudaEventSynchronize(b));
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    return ms / reps;
+}
+
+int main()
+{
+    const int ox = 2000 / 128 * 128 + 128 == 2048 ? 2048 : 2048, oy = 2016, nz = 1644; // 2048 x 2016 x 1644 floats = 27 GB
+    const size_t n = (size_t)ox * oy * nz;
+    float* out; CK(cudaMalloc(&out, n * 4));
+    float* in; CK(cudaMalloc(&in, n * 4));
+    const double gb = n * 4 / 1e9;
+    float ms = time_ms([&] { k_linear<<<148 * 16, 256>>>((float4*)out, n / 4); });
+    printf("linear float4 stores        %8.3f ms %8.1f GB/s\n", ms, gb / ms * 1e3);
+    ms = time_ms([&] { CK(cudaMemsetAsync(out, 0, n * 4)); });
+    printf("cudaMemset                  %8.3f ms %8.1f GB/s\n", ms, gb / ms * 1e3);
+    ms = time_ms([&] { CK(cudaMemcpyAsync(out, in, n * 4, cudaMemcpyDeviceToDevice)); });
+    printf("cudaMemcpy D2D (r+w bytes)  %8.3f ms %8.1f GB/s\n", ms, 2 * gb / ms * 1e3);
+    for (int chunk : {64, 16, 256}) {
+        { dim3 g((ox / 32) * (oy / 32), (nz + chunk - 1) / chunk);
+          ms = time_ms([&] { k_tiles<32, 32, 1><<<g, 256>>>(out, ox, oy, nz, chunk); });
+          printf("tiles 32x32  scalar chunk %3d %8.3f ms %8.1f GB/s\n", chunk, ms, gb / ms * 1e3); }
+        { dim3 g((ox / 64) * (oy / 16), (nz + chunk - 1) / chunk);
+          ms = time_ms([&] { k_tiles<64, 16, 1><<<g, 256>>>(out, ox, oy, nz, chunk); });
+          printf("tiles 64x16  scalar chunk %3d %8.3f ms %8.1f GB/s\n", chunk, ms, gb / ms * 1e3); }
+        { dim3 g((ox / 128) * (oy / 8), (nz + chunk - 1) / chunk);
+          ms = time_ms([&] { k_tiles<128, 8, 1><<<g, 256>>>(out, ox, oy, nz, chunk); });
+          printf("tiles 128x8  scalar chunk %3d %8.3f ms %8.1f GB/s\n", chunk, ms, gb / ms * 1e3); }
+        { dim3 g((ox / 128) * (oy / 8), (nz + chunk - 1) / chunk);
+          ms = time_ms([&] { k_tiles<128, 8, 4><<<g, 256>>>(out, ox, oy, nz, chunk); });
+          printf("tiles 128x8  float4 chunk %3d %8.3f ms %8.1f GB/s\n", chunk, ms, gb / ms * 1e3); }
+        { dim3 g((ox / 32) * (oy / 32), (nz + chunk - 1) / chunk);
+          ms = time_ms([&] { k_tiles<32, 32, 4><<<g, 256>>>(out, ox, oy, nz, chunk); });
+          printf("tiles 32x32  float4 chunk %3d %8.3f ms %8.1f GB/s\n", chunk, ms, gb / ms * 1e3); }
+    }
+    return 0;
+}
