@@ -411,12 +411,16 @@ int run_gather_vector(const fb200_interp* h, const fb200_vector* v, const float*
     const double2* cs = v ? v->d_cs : nullptr;
     switch (h->method) {
     case FB_BILINEAR:
+        if (h->tiles.ready())
+            return launch_gather_staged_vector(g, h->tiles, cs, d_u, d_v, d_uo, d_vo, sc, st);
         return launch_gather_vector(FB_BILINEAR, g, h->d_bil, nullptr, cs, d_u, d_v, d_uo, d_vo, st);
     case FB_BICUBIC:
         if (h->bic_tiles.ready())
             return launch_gather_bicubic_staged(g, h->bic_tiles, h->d_bic_off, h->d_bic_frac, cs, d_u, d_v, d_uo, d_vo, sc, st);
         return launch_gather_vector(FB_BICUBIC, g, h->d_bic_off, h->d_bic_frac, cs, d_u, d_v, d_uo, d_vo, st);
     default:
+        if (h->tiles.ready())
+            return launch_gather_staged_vector(g, h->tiles, cs, d_u, d_v, d_uo, d_vo, sc, st);
         return launch_gather_vector(FB_NN, g, h->d_nn, nullptr, cs, d_u, d_v, d_uo, d_vo, st);
     }
 }
@@ -431,8 +435,8 @@ int run_slice_device(const fb200_interp* h, const fb200_vector* v, int nfields, 
     if (nz == 0 || out_n == 0)
         return FB_OK;
     const bool staged_scalar = nfields == 1 && !h->forward && (h->method == FB_BICUBIC ? h->bic_tiles.ready() : h->tiles.ready());
-    const bool staged_bicubic_vector = nfields == 2 && h->method == FB_BICUBIC && h->bic_tiles.ready();
-    const bool kernel_fills = staged_scalar || staged_bicubic_vector;
+    const bool staged_vector = nfields == 2 && !h->forward && (h->method == FB_BICUBIC ? h->bic_tiles.ready() : h->tiles.ready());
+    const bool kernel_fills = staged_scalar || staged_vector;
     Scratch tmp(st);
     SliceConv sc;
     const float* fin[2] = {nullptr, nullptr};

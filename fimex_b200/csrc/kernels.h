@@ -80,6 +80,9 @@ void tile_table_free(TileTable* tt);
 // staged gather for bilinear and nearest-neighbour tables; sc: fill -> NaN while staging, NaN -> fill + cast while storing
 int launch_gather_bilinear_staged(const GatherGeom& g, const TileTable& tt, const float* d_in, void* d_out, const SliceConv& sc, cudaStream_t st);
 bool staged_store_supports(int out_type);
+// both components of a vector through the staged gather (plain float output), rotated when d_cs != nullptr
+int launch_gather_staged_vector(const GatherGeom& g, const TileTable& tt, const double2* d_cs, const float* d_u, const float* d_v, float* d_uo,
+                                float* d_vo, const SliceConv& sc, cudaStream_t st);
 
 // ---- bicubic_staged.cu (K5 fast path) ------------------------------------------------------------------
 struct BicubicTiles {

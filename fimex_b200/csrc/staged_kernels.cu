@@ -25,6 +25,7 @@
 #include "kernels.h"
 #include "tables.cuh"
 #include "convert.cuh"
+#include "interp_math.cuh"
 
 #include <cstdlib>
 
@@ -41,12 +42,16 @@ constexpr int kTilePts = 1024;
 // distinct taps, i.e. span fewer than ~30 source cells.
 //   bilinear: 64 x 16, lane = x, thread t owns (t & 63, (t >> 6) + 4k): a row is written by two neighbouring warps
 //   nearest neighbour: 128 x 8, thread t owns (4 (t & 31) + k, t >> 5): one 128-bit store per thread and level
+#ifndef FB_BL_TILE_X
+#define FB_BL_TILE_X 64 // bilinear tile width: 32 or 64 (experiments: -DFB_BL_TILE_X=32)
+#endif
 template <bool NN>
 struct Tile {
-    static constexpr int X = NN ? 128 : 64, Y = NN ? 8 : 16;
+    static constexpr int X = NN ? 128 : FB_BL_TILE_X, Y = kTilePts / X;
+    static constexpr int RowStep = NN ? 0 : kThreads / X; // bilinear: rows between point k and point k+1 of a thread
     // position of point k of thread t inside the tile
-    static __device__ __forceinline__ int px(int t, int k) { return NN ? 4 * (t & 31) + k : (t & 63); }
-    static __device__ __forceinline__ int py(int t, int k) { return NN ? (t >> 5) : (t >> 6) + 4 * k; }
+    static __device__ __forceinline__ int px(int t, int k) { return NN ? 4 * (t & 31) + k : (t % X); }
+    static __device__ __forceinline__ int py(int t, int k) { return NN ? (t >> 5) : (t / X) + RowStep * k; }
 };
 constexpr int kMaxTaps = 4 * kTilePts;                              // worst case: every point has its own 4 taps
 constexpr int kStageFloats = 4096;                                  // one staging buffer (16 KB), two of them
@@ -193,15 +198,18 @@ __device__ __forceinline__ void cp_async_wait_all()
 
 // Out: StorePlain (interpolateValues' own float output) or StoreAs<T> (interpolationArray2Data fused into the store:
 // NaN -> fill, round + cast to the variable's type).  fill_in: mifi_bad2nanf fused into the staging (values equal to
-// bad_in become NaN before any point reads them).
-template <bool NN, class Out>
-__global__ void __launch_bounds__(kThreads, 3) k_gather_bilinear_staged(GatherGeom g, int tiles_x, const int* __restrict__ taps,
-                                                                     const int* __restrict__ ntaps_tab, const uint4* __restrict__ meta,
-                                                                     const float4* __restrict__ xf4, const float4* __restrict__ yf4,
-                                                                     const float* __restrict__ in, typename Out::type* __restrict__ out,
-                                                                     Out conv, int fill_in, float bad_in, int vec_ok)
+// bad0 / bad1 become NaN before any point reads them).  NF = 2: both components of a vector through one table pass
+// (CDMInterpolator.cc:255-276), ROT: rotated in the epilogue (mifi_vector_reproject_values_by_matrix_f, interpolation.c:790-812).
+template <bool NN, int NF, bool ROT, class Out>
+__global__ void __launch_bounds__(kThreads, NF == 1 ? 3 : 2)
+    k_gather_bilinear_staged(GatherGeom g, int tiles_x, const int* __restrict__ taps, const int* __restrict__ ntaps_tab,
+                             const uint4* __restrict__ meta, const float4* __restrict__ xf4, const float4* __restrict__ yf4,
+                             const float* __restrict__ in0, const float* __restrict__ in1, typename Out::type* __restrict__ out0,
+                             typename Out::type* __restrict__ out1, const double2* __restrict__ cs, Out conv, int fill_in, float bad0,
+                             float bad1, int vec_ok)
 {
-    __shared__ float s_stage[2][kStageFloats]; // double buffer: batch b+1 lands while batch b is consumed
+    extern __shared__ __align__(16) float s_dyn[]; // [2 buffers][NF fields][kStageFloats]: batch b+1 lands while batch b is consumed
+    auto stage = [&](int buf, int f) { return s_dyn + (buf * NF + f) * kStageFloats; };
     const int tile = blockIdx.x;
     const int t = threadIdx.x;
     const int ntaps = __ldg(ntaps_tab + tile);
@@ -224,21 +232,25 @@ __global__ void __launch_bounds__(kThreads, 3) k_gather_bilinear_staged(GatherGe
         wy0[k] = __fsub_rn(1.f, yf[k]);
         all_full = all_full && (mode[k] == (NN ? FB_BL_NEAR : FB_BL_FULL));
     }
-    // a warp owns 128 consecutive target points of one row, lane l the points 4l .. 4l+3: neighbouring lanes read the same
-    // or neighbouring taps (broadcast / distinct banks) and the warp writes 512 contiguous bytes per level
     const int tx = tile % tiles_x, ty = tile / tiles_x;
     // points k < nvalid of this thread exist (k runs along x for nearest neighbour, down the rows for bilinear)
     const int x0 = tx * Tile<NN>::X + Tile<NN>::px(t, 0), y0 = ty * Tile<NN>::Y + Tile<NN>::py(t, 0);
     int nvalid = 0;
     if (y0 < g.oy && x0 < g.ox)
-        nvalid = NN ? g.ox - x0 : (g.oy - y0 + 3) / 4;
+        nvalid = NN ? g.ox - x0 : (g.oy - y0 + Tile<NN>::RowStep - 1) / (NN ? 1 : Tile<NN>::RowStep);
     nvalid = nvalid > 4 ? 4 : nvalid;
     const long long per = (g.nz + gridDim.y - 1) / gridDim.y;
     const long long z0 = (long long)blockIdx.y * per;
     const long long z1 = z0 + per < g.nz ? z0 + per : g.nz;
     // element offset of point 0 inside a level, and from point k to point k+1
     const unsigned off0 = (unsigned)y0 * (unsigned)g.ox + (unsigned)x0;
-    const unsigned kstep = NN ? 1u : 4u * (unsigned)g.ox;
+    const unsigned kstep = NN ? 1u : (unsigned)Tile<NN>::RowStep * (unsigned)g.ox;
+    double2 rot[4];
+    if (ROT) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            rot[k] = k < nvalid ? __ldg(cs + off0 + (unsigned)k * kstep) : make_double2(1., 0.);
+    }
     // Two staging layouts.  fast: tap-major, element (tap r, level zi) at r*9 + zi -- a thread's eight row pointers are then
     // constant for a whole batch and the level is an immediate offset of the shared load (no address arithmetic in the
     // inner loop; 9 is odd, so any 32 taps with distinct r mod 32 still hit distinct banks).  Tiles with more than 455 taps
@@ -249,30 +261,33 @@ __global__ void __launch_bounds__(kThreads, 3) k_gather_bilinear_staged(GatherGe
     const int tap0 = (t < ntaps) ? __ldg(my_taps + t) : -1;
 
     auto issue = [&](int buf, long long z, int nb) {
-        float* dst = s_stage[buf];
-        const float* lv = in + z * g.in_level;
-        if (fast) {
-            if (tap0 >= 0) { // warps past the end of the tap list (most of them: ~50 taps per tile) skip the loop entirely
-                const float* src = lv + tap0;
-                float* d = dst + t * kLvlStride;
 #pragma unroll
-                for (int zi = 0; zi < kMaxBatch; ++zi)
-                    if (zi < nb)
-                        cp_async_f32(d + zi, src + zi * g.in_level);
-            }
-            if (ntaps > kThreads) {
-                for (int r = t + kThreads; r < ntaps; r += kThreads) {
-                    const float* src = lv + __ldg(my_taps + r);
-                    for (int zi = 0; zi < nb; ++zi)
-                        cp_async_f32(dst + r * kLvlStride + zi, src + zi * g.in_level);
+        for (int f = 0; f < NF; ++f) {
+            float* dst = stage(buf, f);
+            const float* lv = (f == 0 ? in0 : in1) + z * g.in_level;
+            if (fast) {
+                if (tap0 >= 0) { // warps past the end of the tap list (most of them: ~50 taps per tile) skip the loop entirely
+                    const float* src = lv + tap0;
+                    float* d = dst + t * kLvlStride;
+#pragma unroll
+                    for (int zi = 0; zi < kMaxBatch; ++zi)
+                        if (zi < nb)
+                            cp_async_f32(d + zi, src + zi * g.in_level);
                 }
-            }
-        } else {
-            for (int zi = 0; zi < nb; ++zi, lv += g.in_level, dst += ntaps) {
-                if (tap0 >= 0)
-                    cp_async_f32(dst + t, lv + tap0);
-                for (int r = t + kThreads; r < ntaps; r += kThreads)
-                    cp_async_f32(dst + r, lv + __ldg(my_taps + r));
+                if (ntaps > kThreads) {
+                    for (int r = t + kThreads; r < ntaps; r += kThreads) {
+                        const float* src = lv + __ldg(my_taps + r);
+                        for (int zi = 0; zi < nb; ++zi)
+                            cp_async_f32(dst + r * kLvlStride + zi, src + zi * g.in_level);
+                    }
+                }
+            } else {
+                for (int zi = 0; zi < nb; ++zi, lv += g.in_level, dst += ntaps) {
+                    if (tap0 >= 0)
+                        cp_async_f32(dst + t, lv + tap0);
+                    for (int r = t + kThreads; r < ntaps; r += kThreads)
+                        cp_async_f32(dst + r, lv + __ldg(my_taps + r));
+                }
             }
         }
         cp_async_commit();
@@ -281,20 +296,24 @@ __global__ void __launch_bounds__(kThreads, 3) k_gather_bilinear_staged(GatherGe
     // mifi_bad2nanf on the batch that has just landed: every thread patches the elements it copied itself (its own
     // cp.async writes are visible to it after the wait), so no extra barrier is needed
     auto patch = [&](int buf, int nb) {
-        float* dst = s_stage[buf];
         const float nanv = undef_f();
-        if (fast) {
-            for (int r = t; r < ntaps; r += kThreads) {
-                float* d = dst + r * kLvlStride;
-                for (int zi = 0; zi < nb; ++zi)
-                    if (d[zi] == bad_in)
-                        d[zi] = nanv;
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            float* dst = stage(buf, f);
+            const float bad = f == 0 ? bad0 : bad1;
+            if (fast) {
+                for (int r = t; r < ntaps; r += kThreads) {
+                    float* d = dst + r * kLvlStride;
+                    for (int zi = 0; zi < nb; ++zi)
+                        if (d[zi] == bad)
+                            d[zi] = nanv;
+                }
+            } else {
+                for (int zi = 0; zi < nb; ++zi, dst += ntaps)
+                    for (int r = t; r < ntaps; r += kThreads)
+                        if (dst[r] == bad)
+                            dst[r] = nanv;
             }
-        } else {
-            for (int zi = 0; zi < nb; ++zi, dst += ntaps)
-                for (int r = t; r < ntaps; r += kThreads)
-                    if (dst[r] == bad_in)
-                        dst[r] = nanv;
         }
     };
 
@@ -312,8 +331,9 @@ __global__ void __launch_bounds__(kThreads, 3) k_gather_bilinear_staged(GatherGe
             issue(buf ^ 1, zn, (int)((z1 - zn) < zb ? (z1 - zn) : zb));
         if (nvalid == 0)
             continue;
-        const float* lvl = s_stage[buf];
-        typename Out::type* base = out + z * g.out_level; // uniform across the CTA
+        const float* lvl = stage(buf, 0);
+        typename Out::type* base0 = out0 + z * g.out_level; // uniform across the CTA
+        typename Out::type* base1 = NF == 2 ? out1 + z * g.out_level : nullptr;
         if (fast && all_full && nvalid == 4) {
             const float* pa[4];
             const float* pb[4];
@@ -323,28 +343,43 @@ __global__ void __launch_bounds__(kThreads, 3) k_gather_bilinear_staged(GatherGe
                 pb[k] = lvl + ib[k] * kLvlStride;
             }
             auto one_level = [&](int zi) {
-                float r[4];
+                float r[NF][4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (NN) { // copied value, bit for bit (interpolation.c:869-871)
-                        r[k] = pa[k][zi];
-                    } else {
-                        const float s00 = pa[k][zi], s01 = pa[k][kLvlStride + zi], s10 = pb[k][zi], s11 = pb[k][kLvlStride + zi];
-                        const float top = __fadd_rn(__fmul_rn(wx0[k], s00), __fmul_rn(xf[k], s01));
-                        const float bot = __fadd_rn(__fmul_rn(wx0[k], s10), __fmul_rn(xf[k], s11));
-                        r[k] = __fadd_rn(__fmul_rn(wy0[k], top), __fmul_rn(yf[k], bot));
+                for (int f = 0; f < NF; ++f) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float* qa = pa[k] + f * kStageFloats;
+                        const float* qb = pb[k] + f * kStageFloats;
+                        if (NN) { // copied value, bit for bit (interpolation.c:869-871)
+                            r[f][k] = qa[zi];
+                        } else {
+                            const float s00 = qa[zi], s01 = qa[kLvlStride + zi], s10 = qb[zi], s11 = qb[kLvlStride + zi];
+                            const float top = __fadd_rn(__fmul_rn(wx0[k], s00), __fmul_rn(xf[k], s01));
+                            const float bot = __fadd_rn(__fmul_rn(wx0[k], s10), __fmul_rn(xf[k], s11));
+                            r[f][k] = __fadd_rn(__fmul_rn(wy0[k], top), __fmul_rn(yf[k], bot));
+                        }
                     }
                 }
-                typename Out::type* dst = base + off0;
-                if (NN && vec_ok) {
-                    store_vec4<typename Out::type>(dst, conv(r[0]), conv(r[1]), conv(r[2]), conv(r[3]));
-                } else {
-                    __stcs(dst, conv(r[0]));
-                    __stcs(dst + kstep, conv(r[1]));
-                    __stcs(dst + 2 * kstep, conv(r[2]));
-                    __stcs(dst + 3 * kstep, conv(r[3]));
+                if (ROT) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        rotate_uv(r[0][k], r[NF - 1][k], rot[k].x, rot[k].y);
                 }
-                base += g.out_level;
+#pragma unroll
+                for (int f = 0; f < NF; ++f) {
+                    typename Out::type* dst = (f == 0 ? base0 : base1) + off0;
+                    if (NN && vec_ok) {
+                        store_vec4<typename Out::type>(dst, conv(r[f][0]), conv(r[f][1]), conv(r[f][2]), conv(r[f][3]));
+                    } else {
+                        __stcs(dst, conv(r[f][0]));
+                        __stcs(dst + kstep, conv(r[f][1]));
+                        __stcs(dst + 2 * kstep, conv(r[f][2]));
+                        __stcs(dst + 3 * kstep, conv(r[f][3]));
+                    }
+                }
+                base0 += g.out_level;
+                if (NF == 2)
+                    base1 += g.out_level;
             };
             if (nb == kMaxBatch) { // full batch: no per-level test
 #pragma unroll
@@ -362,32 +397,43 @@ __global__ void __launch_bounds__(kThreads, 3) k_gather_bilinear_staged(GatherGe
             for (int zi = 0; zi < nb; ++zi, lvl += sz) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    float v = undef_f();
-                    const float* qa = lvl + ia[k] * sr;
-                    const float* qb = lvl + ib[k] * sr;
-                    switch (mode[k]) {
-                    case FB_BL_FULL: {
-                        const float top = __fadd_rn(__fmul_rn(wx0[k], qa[0]), __fmul_rn(xf[k], qa[sr]));
-                        const float bot = __fadd_rn(__fmul_rn(wx0[k], qb[0]), __fmul_rn(xf[k], qb[sr]));
-                        v = __fadd_rn(__fmul_rn(wy0[k], top), __fmul_rn(yf[k], bot));
-                        break;
+                    float v[NF];
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) {
+                        v[f] = undef_f();
+                        const float* qa = lvl + f * kStageFloats + ia[k] * sr;
+                        const float* qb = lvl + f * kStageFloats + ib[k] * sr;
+                        switch (mode[k]) {
+                        case FB_BL_FULL: {
+                            const float top = __fadd_rn(__fmul_rn(wx0[k], qa[0]), __fmul_rn(xf[k], qa[sr]));
+                            const float bot = __fadd_rn(__fmul_rn(wx0[k], qb[0]), __fmul_rn(xf[k], qb[sr]));
+                            v[f] = __fadd_rn(__fmul_rn(wy0[k], top), __fmul_rn(yf[k], bot));
+                            break;
+                        }
+                        case FB_BL_XLIN:
+                            v[f] = __fadd_rn(__fmul_rn(wx0[k], qa[0]), __fmul_rn(xf[k], qa[sr]));
+                            break;
+                        case FB_BL_YLIN:
+                            v[f] = __fadd_rn(__fmul_rn(wy0[k], qa[0]), __fmul_rn(yf[k], qb[0]));
+                            break;
+                        case FB_BL_NEAR:
+                            v[f] = qa[0];
+                            break;
+                        default:
+                            break;
+                        }
                     }
-                    case FB_BL_XLIN:
-                        v = __fadd_rn(__fmul_rn(wx0[k], qa[0]), __fmul_rn(xf[k], qa[sr]));
-                        break;
-                    case FB_BL_YLIN:
-                        v = __fadd_rn(__fmul_rn(wy0[k], qa[0]), __fmul_rn(yf[k], qb[0]));
-                        break;
-                    case FB_BL_NEAR:
-                        v = qa[0];
-                        break;
-                    default:
-                        break;
+                    if (ROT)
+                        rotate_uv(v[0], v[NF - 1], rot[k].x, rot[k].y);
+                    if (k < nvalid) {
+                        __stcs(base0 + off0 + (unsigned)k * kstep, conv(v[0]));
+                        if (NF == 2)
+                            __stcs(base1 + off0 + (unsigned)k * kstep, conv(v[NF - 1]));
                     }
-                    if (k < nvalid)
-                        __stcs(base + off0 + (unsigned)k * kstep, conv(v));
                 }
-                base += g.out_level;
+                base0 += g.out_level;
+                if (NF == 2)
+                    base1 += g.out_level;
             }
         }
     }
@@ -443,14 +489,32 @@ void tile_table_free(TileTable* tt)
 }
 
 namespace {
+constexpr size_t kStageBytes = 2 * kStageFloats * sizeof(float); // per field: two buffers
+
 template <bool NN, class Out>
 void launch_staged_as(dim3 grid, const GatherGeom& g, const TileTable& tt, const float* d_in, void* d_out, Out conv, const SliceConv& sc,
                       cudaStream_t st)
 {
-    k_gather_bilinear_staged<NN, Out><<<grid, kThreads, 0, st>>>(g, tt.tiles_x, tt.d_cells, tt.d_ncells, tt.d_meta, tt.d_xf, tt.d_yf, d_in,
-                                                                static_cast<typename Out::type*>(d_out), conv, sc.fill_in ? 1 : 0,
-                                                                sc.bad_in[0],
-                                                                ((g.ox % 4) == 0 && (reinterpret_cast<uintptr_t>(d_out) & (4 * sizeof(typename Out::type) - 1)) == 0) ? 1 : 0);
+    typedef typename Out::type T;
+    const int vec_ok = ((g.ox % 4) == 0 && (reinterpret_cast<uintptr_t>(d_out) & (4 * sizeof(T) - 1)) == 0) ? 1 : 0;
+    k_gather_bilinear_staged<NN, 1, false, Out><<<grid, kThreads, kStageBytes, st>>>(g, tt.tiles_x, tt.d_cells, tt.d_ncells, tt.d_meta, tt.d_xf,
+                                                                                      tt.d_yf, d_in, nullptr, static_cast<T*>(d_out), nullptr,
+                                                                                      nullptr, conv, sc.fill_in ? 1 : 0, sc.bad_in[0], 0.f, vec_ok);
+}
+
+template <bool NN, bool ROT>
+cudaError_t launch_staged_vector(dim3 grid, const GatherGeom& g, const TileTable& tt, const double2* d_cs, const float* d_u, const float* d_v,
+                                 float* d_uo, float* d_vo, const SliceConv& sc, cudaStream_t st)
+{
+    auto kernel = k_gather_bilinear_staged<NN, 2, ROT, StorePlain>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kStageBytes));
+    if (e != cudaSuccess)
+        return e;
+    const uintptr_t align = reinterpret_cast<uintptr_t>(d_uo) | reinterpret_cast<uintptr_t>(d_vo);
+    const int vec_ok = ((g.ox % 4) == 0 && (align & 15u) == 0) ? 1 : 0;
+    kernel<<<grid, kThreads, 2 * kStageBytes, st>>>(g, tt.tiles_x, tt.d_cells, tt.d_ncells, tt.d_meta, tt.d_xf, tt.d_yf, d_u, d_v, d_uo, d_vo, d_cs,
+                                                    StorePlain(), sc.fill_in ? 1 : 0, sc.bad_in[0], sc.bad_in[1], vec_ok);
+    return cudaSuccess;
 }
 
 template <bool NN>
@@ -508,6 +572,28 @@ int launch_gather_bilinear_staged(const GatherGeom& g, const TileTable& tt, cons
     dim3 grid(tiles, z_chunks(tiles, g.nz));
     const bool ok = tt.nn ? launch_staged_typed<true>(grid, g, tt, d_in, d_out, sc, st) : launch_staged_typed<false>(grid, g, tt, d_in, d_out, sc, st);
     FB_REQUIRE(ok, "staged gather: unsupported output type");
+    count_launch();
+    FB_CUDA_CHECK(cudaGetLastError());
+    return FB_OK;
+}
+
+// both components of a vector through the staged gather (plain float output), rotated when d_cs != nullptr
+int launch_gather_staged_vector(const GatherGeom& g, const TileTable& tt, const double2* d_cs, const float* d_u, const float* d_v, float* d_uo,
+                                float* d_vo, const SliceConv& sc, cudaStream_t st)
+{
+    if (g.out_level == 0 || g.nz == 0)
+        return FB_OK;
+    FB_REQUIRE(!sc.convert_out, "staged vector gather writes plain floats");
+    const unsigned tiles = (unsigned)tt.tiles_x * (unsigned)tt.tiles_y;
+    dim3 grid(tiles, z_chunks(tiles, g.nz));
+    cudaError_t e;
+    if (tt.nn)
+        e = d_cs ? launch_staged_vector<true, true>(grid, g, tt, d_cs, d_u, d_v, d_uo, d_vo, sc, st)
+                 : launch_staged_vector<true, false>(grid, g, tt, d_cs, d_u, d_v, d_uo, d_vo, sc, st);
+    else
+        e = d_cs ? launch_staged_vector<false, true>(grid, g, tt, d_cs, d_u, d_v, d_uo, d_vo, sc, st)
+                 : launch_staged_vector<false, false>(grid, g, tt, d_cs, d_u, d_v, d_uo, d_vo, sc, st);
+    FB_CUDA_CHECK(e);
     count_launch();
     FB_CUDA_CHECK(cudaGetLastError());
     return FB_OK;

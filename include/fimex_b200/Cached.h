@@ -56,6 +56,15 @@ public:
             throw CDMException(std::string("error during interpolation: ") + fb200_last_error());
         return out;
     }
+    /** The whole per-slice body of CDMInterpolator::getDataSlice (src/CDMInterpolator.cc:250-258, 284-285) in one call:
+     *  data2InterpolationArray(inData, badValue) -> interpolateValues -> interpolationArray2Data(type, ..., badValue).
+     *  inType / outType: CDMDataType numbers (fb200_datatype); outData: outX*outY*inZ elements of outType, caller-owned.
+     *  On the staged gathers both adapter passes run inside the gather kernel. */
+    virtual void getDataSlice(int inType, const void* inData, size_t size, double badValue, int outType, void* outData, size_t& newSize) const
+    {
+        if (fb200_interp_get_data_slice(handle_, inType, inData, size, badValue, outType, outData, &newSize) != MIFI_OK)
+            throw CDMException(std::string("error during interpolation: ") + fb200_last_error());
+    }
     virtual size_t getInX() const { return fb200_interp_in_x(handle_); }
     virtual size_t getInY() const { return fb200_interp_in_y(handle_); }
     virtual size_t getOutX() const { return fb200_interp_out_x(handle_); }

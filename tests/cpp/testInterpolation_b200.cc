@@ -236,6 +236,37 @@ static void test_cached_classes()
     CHECK(fout[0] == 1.5f && fout[1] == 5.f && std::isnan(fout[2]));
 }
 
+// the per-slice body of CDMInterpolator::getDataSlice (src/CDMInterpolator.cc:250-285) through the mirror: a packed short
+// variable with _FillValue -32767, nearest neighbour -> short out; the fill value survives both adapters
+static void test_get_data_slice()
+{
+    using namespace MetNoFimexB200;
+    const size_t inX = 4, inY = 3, outX = 3, outY = 2;
+    std::vector<double> px = {0.2, 1.6, 3.0, 0.0, 2.4, 9.0};
+    std::vector<double> py = {0.0, 0.4, 1.6, 2.0, 1.0, 1.0};
+    CachedInterpolation ci("x", "y", FB200_INTERPOL_NEAREST_NEIGHBOR, px, py, inX, inY, outX, outY);
+    std::vector<short> in(inX * inY);
+    for (size_t i = 0; i < in.size(); ++i)
+        in[i] = (short)(10 * i);
+    in[6] = -32767; // (x=2, y=1)
+    std::vector<short> out(outX * outY, 0);
+    size_t newSize = 0;
+    ci.getDataSlice(FB200_SHORT, in.data(), in.size(), -32767., FB200_SHORT, out.data(), newSize);
+    CHECK(newSize == outX * outY);
+    CHECK(out[0] == 0 && out[1] == 20 && out[2] == 110 && out[3] == 80);
+    CHECK(out[4] == -32767); // the undefined source value
+    CHECK(out[5] == -32767); // outside the source grid
+    // bilinear to float: 0.5 * (in[0] + in[1]) and rounding to short (half away from zero): (0 + 10) / 2 = 5
+    std::vector<double> bx = {0.5, 0.25}, by = {0.0, 0.0};
+    CachedInterpolation cb("x", "y", FB200_INTERPOL_BILINEAR, bx, by, inX, inY, 2, 1);
+    std::vector<short> bo(2, 0);
+    cb.getDataSlice(FB200_SHORT, in.data(), in.size(), -32767., FB200_SHORT, bo.data(), newSize);
+    CHECK(bo[0] == 5 && bo[1] == 3); // 2.5 -> 3
+    std::vector<float> bf(2, 0.f);
+    cb.getDataSlice(FB200_SHORT, in.data(), in.size(), -32767., FB200_FLOAT, bf.data(), newSize);
+    CHECK(bf[0] == 5.f && bf[1] == 2.5f);
+}
+
 int main()
 {
     test_mifi_points2position();
@@ -247,6 +278,7 @@ int main()
     test_mifi_vector_reproject_values_rotate(90, 1e-4);
     test_mifi_vector_reproject_values_rotate(180, 1e-5);
     test_cached_classes();
+    test_get_data_slice();
     std::printf("%d checks, %d failures\n", checks, failures);
     return failures == 0 ? 0 : 1;
 }
