@@ -21,4 +21,4 @@ for name, m in (("bilinear", Method.BILINEAR), ("nearestneighbor", Method.NEARES
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 3
         vals = 2 * nz * 4e6
-        print(f"{name:16s} vector rot={rot is not None}: {ms:8.3f} ms  {vals/ms*1e-9*1e3/1e3:8.1f} Gvalues/s  {vals*4.3/ms/1e6:7.0f} GB/s", flush=True)
+        print(f"{name:16s} vector rot={rot is not None}: {ms:8.3f} ms  {vals/ms*1e-6:8.1f} Gvalues/s  {vals*4.3/ms/1e6:7.0f} GB/s", flush=True)
