@@ -189,7 +189,7 @@ def main_reference(args):
         "cpu_baseline": {"value": r["value"], "unit": "values/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "values/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     return 0
 
 
@@ -368,7 +368,7 @@ def main_b200(args):
                        "parallelism": f"slab{world}", "setup_s": setup_s, "variant": args.variant},
             "hbm_gbs": achieved, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)  # flushed before the NCCL teardown: a buffered line is lost if that dies
     if world > 1:
         dist.destroy_process_group()
     return 0
