@@ -209,16 +209,32 @@ class CachedInterpolation(CachedInterpolationInterface):
         return cls._wrap(h, xDimName, yDimName)
 
     @classmethod
+    def fromTemplate(cls, funcType, proj_template, tmplLon, tmplLat, outX, outY, proj_source, in_x_axis, in_y_axis, in_is_degree,
+                     xDimName="x", yDimName="y"):
+        """index tables of changeProjectionByProjectionParametersToLatLonTemplate (CDMInterpolator.cc:1755-1803): the target is a
+        2-D lon/lat template in degrees (or a point list with outY = 1)"""
+        lo, la, ix, iy = f64(tmplLon), f64(tmplLat), f64(in_x_axis), f64(in_y_axis)
+        if lo.size != outX * outY or la.size != outX * outY:
+            raise FimexB200Error("template lon/lat must hold outX*outY values")
+        h = C.c_void_p()
+        check(load().fb200_cached_interpolation_create_from_template(int(funcType), proj_template.encode(), ptr(lo), ptr(la), outX, outY,
+                                                                     proj_source.encode(), ptr(ix), ptr(iy), ix.size, iy.size,
+                                                                     int(in_is_degree), C.byref(h)), "changeProjection (lat/lon template)")
+        return cls._wrap(h, xDimName, yDimName)
+
+    @classmethod
     def fromCoordinates(cls, funcType, proj_target, out_x_axis, out_y_axis, out_x_is_degree, out_y_is_degree, lon2d, lat2d, inX, inY,
-                        xDimName="x", yDimName="y"):
-        """index tables of changeProjectionByCoordinates, coord_nearestneighbor (CDMInterpolator.cc:1387-1412)"""
+                        xDimName="x", yDimName="y", maxDistance=0.0):
+        """index tables of changeProjectionByCoordinates (CDMInterpolator.cc:1387-1412): coord_nearestneighbor, or coord_kdtree
+        with `maxDistance` metres (the reference's setDistanceOfInterest; 0 = derived from the output axes)"""
         ox, oy, lo, la = f64(out_x_axis), f64(out_y_axis), f64(lon2d), f64(lat2d)
         if lo.size != inX * inY or la.size != inX * inY:
             raise FimexB200Error("lon2d/lat2d must hold inX*inY values")
         h = C.c_void_p()
-        check(load().fb200_cached_interpolation_create_from_coordinates(int(funcType), proj_target.encode(), ptr(ox), ptr(oy), ox.size, oy.size,
-                                                                        int(out_x_is_degree), int(out_y_is_degree), ptr(lo), ptr(la), inX, inY,
-                                                                        C.byref(h)), "changeProjectionByCoordinates")
+        check(load().fb200_cached_interpolation_create_from_coordinates_kd(int(funcType), proj_target.encode(), ptr(ox), ptr(oy), ox.size,
+                                                                           oy.size, int(out_x_is_degree), int(out_y_is_degree), ptr(lo),
+                                                                           ptr(la), inX, inY, float(maxDistance), C.byref(h)),
+              "changeProjectionByCoordinates")
         return cls._wrap(h, xDimName, yDimName)
 
     def _npoints(self):
@@ -346,6 +362,17 @@ class CachedVectorReprojection:
                                                          int(out_x_axis_type), int(out_y_axis_type), ox.size, oy.size, C.byref(self._h)),
               "mifi_get_vector_reproject_matrix")
         self.ox, self.oy = ox.size, oy.size
+        return self
+
+    @classmethod
+    def fromPoints(cls, method, proj_input, proj_output, inputIsMetric, lon, lat):
+        """mifi_get_vector_reproject_matrix_points for a point list in degrees (lat/lon-template path, CDMInterpolator.cc:1805-1823)"""
+        lo, la = f64(lon), f64(lat)
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        check(load().fb200_vector_create_from_points(int(method), proj_input.encode(), proj_output.encode(), int(inputIsMetric), ptr(lo),
+                                                     ptr(la), lo.size, C.byref(self._h)), "mifi_get_vector_reproject_matrix_points")
+        self.ox, self.oy = lo.size, 1
         return self
 
     def close(self):

@@ -134,7 +134,11 @@ def _declare(lib):
         "fb200_cached_interpolation_create_device": (i, [i, _vp, _vp, sz, sz, sz, sz, P(_vp)]),
         "fb200_cached_interpolation_create_from_projection": (i, [i, C.c_char_p, _vp, _vp, sz, sz, i, i, C.c_char_p, _vp, _vp, sz, sz, i,
                                                                   P(_vp)]),
+        "fb200_cached_interpolation_create_from_template": (i, [i, C.c_char_p, _vp, _vp, sz, sz, C.c_char_p, _vp, _vp, sz, sz, i, P(_vp)]),
+        "fb200_vector_create_from_points": (i, [i, C.c_char_p, C.c_char_p, i, _vp, _vp, i, P(_vp)]),
         "fb200_cached_interpolation_create_from_coordinates": (i, [i, C.c_char_p, _vp, _vp, sz, sz, i, i, _vp, _vp, sz, sz, P(_vp)]),
+        "fb200_cached_interpolation_create_from_coordinates_kd": (i, [i, C.c_char_p, _vp, _vp, sz, sz, i, i, _vp, _vp, sz, sz, C.c_double,
+                                                                     P(_vp)]),
         "fb200_cached_forward_interpolation_create": (i, [i, _vp, _vp, sz, sz, sz, sz, P(_vp)]),
         "fb200_cached_forward_interpolation_create_from_coordinates": (i, [i, C.c_char_p, _vp, _vp, sz, sz, i, i, _vp, _vp, sz, sz, P(_vp)]),
         "fb200_interp_create_reduced_domain": (i, [_vp, P(i), P(ll), P(ll)]),

@@ -5,6 +5,7 @@
 
 #include "kernels.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdlib>
@@ -850,14 +851,71 @@ int fb200_cached_interpolation_create_from_projection(int funcType, const char* 
     return MIFI_OK;
 }
 
-int fb200_cached_interpolation_create_from_coordinates(int funcType, const char* proj_target, const double* out_x_axis,
-                                                       const double* out_y_axis, size_t outX, size_t outY, int out_x_is_degree,
-                                                       int out_y_is_degree, const double* lon2d, const double* lat2d, size_t inX, size_t inY,
-                                                       fb200_interp** handle)
+int fb200_cached_interpolation_create_from_template(int funcType, const char* proj_template, const double* tmplLon, const double* tmplLat,
+                                                    size_t outX, size_t outY, const char* proj_source, const double* in_x_axis,
+                                                    const double* in_y_axis, size_t inX, size_t inY, int in_is_degree, fb200_interp** handle)
 {
     FB_REQUIRE(handle != nullptr, "null handle pointer");
     *handle = nullptr;
-    FB_REQUIRE(funcType == FB_COORD_NN, "changeProjectionByCoordinates: only coord_nearestneighbor is implemented on the device");
+    FB_REQUIRE(funcType == FB_NN || funcType == FB_BILINEAR || funcType == FB_BICUBIC,
+               "changeProjectionByProjectionParametersToLatLonTemplate: method must be nearestneighbor, bilinear or bicubic");
+    FB_REQUIRE(tmplLon && tmplLat && in_x_axis && in_y_axis, "null argument");
+    ProjDef ptmpl, psrc;
+    if (parse_pair(proj_template, proj_source, &ptmpl, &psrc) != FB_OK)
+        return MIFI_ERROR;
+    std::unique_ptr<fb200_interp> h;
+    if (new_interp(funcType, false, inX, inY, outX, outY, &h) != FB_OK)
+        return MIFI_ERROR;
+    cudaStream_t st = cudaStreamPerThread;
+    const std::vector<double> lon = axis_in_radians(tmplLon, h->npts, true); // template data is in degrees (:1760-1763)
+    const std::vector<double> lat = axis_in_radians(tmplLat, h->npts, true);
+    const std::vector<double> ixa = axis_in_radians(in_x_axis, inX, in_is_degree != 0); // :1781-1786
+    const std::vector<double> iya = axis_in_radians(in_y_axis, inY, in_is_degree != 0);
+    if (h->npts) {
+        Scratch tmp(st);
+        int* d_status = nullptr;
+        if (tmp.get(&d_status, 1) != FB_OK)
+            return MIFI_ERROR;
+        FB_CUDA_CHECK(cudaMemsetAsync(d_status, 0, sizeof(int), st));
+        FB_CUDA_CHECK(cudaMemcpyAsync(h->d_px, lon.data(), sizeof(double) * h->npts, cudaMemcpyHostToDevice, st));
+        FB_CUDA_CHECK(cudaMemcpyAsync(h->d_py, lat.data(), sizeof(double) * h->npts, cudaMemcpyHostToDevice, st));
+        if (launch_project_values(ptmpl, psrc, h->d_px, h->d_py, (long long)h->npts, d_status, st) != FB_OK) // :1770
+            return MIFI_ERROR;
+        if (check_status(d_status, st, "mifi_project_values") != FB_OK)
+            return MIFI_ERROR;
+        if (points2position_device(h->d_py, (long long)h->npts, iya, in_is_degree ? FB_AXIS_LATITUDE : FB_AXIS_PROJ, st) != FB_OK) // :1789
+            return MIFI_ERROR;
+        if (points2position_device(h->d_px, (long long)h->npts, ixa, in_is_degree ? FB_AXIS_LONGITUDE : FB_AXIS_PROJ, st) != FB_OK) // :1790
+            return MIFI_ERROR;
+    }
+    if (compile_tables(h.get(), st) != FB_OK)
+        return MIFI_ERROR;
+    *handle = h.release();
+    return MIFI_OK;
+}
+
+// getMaxDistanceOfInterest (src/CDMInterpolator.cc:304-326): the largest step of either output axis, in metres; axes whose
+// unit is a degree are multiplied by the earth radius AS GIVEN (the reference passes the unconverted axis values)
+static double max_distance_of_interest(const double* xa, size_t nx, const double* ya, size_t ny, bool is_metric)
+{
+    const double factor = is_metric ? 1. : 6371000.;
+    double mx = 0., my = 0.;
+    for (size_t i = 0; i + 1 < nx; ++i)
+        mx = std::max(factor * std::fabs(xa[i + 1] - xa[i]), mx);
+    for (size_t j = 0; j + 1 < ny; ++j)
+        my = std::max(factor * std::fabs(ya[j + 1] - ya[j]), my);
+    return std::max(mx, my);
+}
+
+int fb200_cached_interpolation_create_from_coordinates_kd(int funcType, const char* proj_target, const double* out_x_axis,
+                                                          const double* out_y_axis, size_t outX, size_t outY, int out_x_is_degree,
+                                                          int out_y_is_degree, const double* lon2d, const double* lat2d, size_t inX,
+                                                          size_t inY, double maxDistance, fb200_interp** handle)
+{
+    FB_REQUIRE(handle != nullptr, "null handle pointer");
+    *handle = nullptr;
+    FB_REQUIRE(funcType == FB_COORD_NN || funcType == FB_COORD_NN_KD,
+               "unkown interpolation method for coordinates: " + std::to_string(funcType)); // CDMInterpolator.cc:1410
     FB_REQUIRE(out_x_axis && out_y_axis && lon2d && lat2d, "null argument");
     ProjDef ptgt, pll;
     if (parse_pair(proj_target, kWgs84LatLon, &ptgt, &pll) != FB_OK)
@@ -873,13 +931,30 @@ int fb200_cached_interpolation_create_from_coordinates(int funcType, const char*
     if (h->npts) {
         if (project_axes_device(ptgt, pll, oxa, oya, h->d_px, h->d_py, st, "mifi_project_axes") != FB_OK)
             return MIFI_ERROR;
-        if (coordnn_search(h->d_px, h->d_py, (long long)h->npts, lon.data(), lat.data(), inX, inY, &h->coordnn_ties, st) != FB_OK)
-            return MIFI_ERROR;
+        if (funcType == FB_COORD_NN) {
+            if (coordnn_search(h->d_px, h->d_py, (long long)h->npts, lon.data(), lat.data(), inX, inY, &h->coordnn_ties, st) != FB_OK)
+                return MIFI_ERROR;
+        } else {
+            // isMetric follows the x axis' unit only (:1389-1393); p_->maxDistance > 0 overrides (:306)
+            const double dist = maxDistance > 0. ? maxDistance : max_distance_of_interest(out_x_axis, outX, out_y_axis, outY, out_x_is_degree == 0);
+            FB_REQUIRE(dist > 0., "coord_kdtree: maximum distance of interest is 0 (single-point axes); set one explicitly");
+            if (coordkd_search(h->d_px, h->d_py, (long long)h->npts, lon.data(), lat.data(), inX, inY, dist, &h->coordnn_ties, st) != FB_OK)
+                return MIFI_ERROR;
+        }
     }
     if (compile_tables(h.get(), st) != FB_OK)
         return MIFI_ERROR;
     *handle = h.release();
     return MIFI_OK;
+}
+
+int fb200_cached_interpolation_create_from_coordinates(int funcType, const char* proj_target, const double* out_x_axis,
+                                                       const double* out_y_axis, size_t outX, size_t outY, int out_x_is_degree,
+                                                       int out_y_is_degree, const double* lon2d, const double* lat2d, size_t inX, size_t inY,
+                                                       fb200_interp** handle)
+{
+    return fb200_cached_interpolation_create_from_coordinates_kd(funcType, proj_target, out_x_axis, out_y_axis, outX, outY, out_x_is_degree,
+                                                                 out_y_is_degree, lon2d, lat2d, inX, inY, 0., handle);
 }
 
 int fb200_cached_forward_interpolation_create_from_coordinates(int funcType, const char* proj_target, const double* out_x_axis,
@@ -1106,6 +1181,33 @@ int fb200_vector_create_from_projection(int method, const char* proj_input, cons
     if (dev_alloc(&v->d_matrix, 4 * on) != FB_OK || dev_alloc(&v->d_cs, on) != FB_OK)
         return MIFI_ERROR;
     if (build_matrix_device(MI_AXES, proj_input, proj_output, out_x_axis, out_y_axis, xt, yt, ox, oy, 0, v->d_matrix, st) != FB_OK)
+        return MIFI_ERROR;
+    if (launch_matrix_to_cossin(v->d_matrix, (long long)on, v->d_cs, st) != FB_OK)
+        return MIFI_ERROR;
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    *handle = v.release();
+    return MIFI_OK;
+}
+
+int fb200_vector_create_from_points(int method, const char* proj_input, const char* proj_output, int inputIsMetric, const double* lon,
+                                    const double* lat, int on, fb200_vector** handle)
+{
+    FB_REQUIRE(handle != nullptr, "null handle pointer");
+    *handle = nullptr;
+    FB_REQUIRE(on > 0 && lon && lat, "empty point list");
+    if (use_device(default_device()) != FB_OK)
+        return MIFI_ERROR;
+    std::unique_ptr<fb200_vector> v(new fb200_vector());
+    v->method = method;
+    v->ox = on; // CachedVectorReprojection(MIFI_VECTOR_KEEP_SIZE, matrix, outSize, 1), CDMInterpolator.cc:1823
+    v->oy = 1;
+    v->device = default_device();
+    cudaStream_t st = cudaStreamPerThread;
+    if (dev_alloc(&v->d_matrix, 4 * (size_t)on) != FB_OK || dev_alloc(&v->d_cs, (size_t)on) != FB_OK)
+        return MIFI_ERROR;
+    const std::vector<double> lo = axis_in_radians(lon, (size_t)on, true); // template data is in degrees (:1810-1813)
+    const std::vector<double> la = axis_in_radians(lat, (size_t)on, true);
+    if (build_matrix_device(MI_POINTS, proj_input, proj_output, lo.data(), la.data(), 0, 0, on, 1, inputIsMetric, v->d_matrix, st) != FB_OK)
         return MIFI_ERROR;
     if (launch_matrix_to_cossin(v->d_matrix, (long long)on, v->d_cs, st) != FB_OK)
         return MIFI_ERROR;

@@ -44,6 +44,11 @@ int launch_matrix_to_cossin(const double* d_matrix, long long n, double2* d_cs, 
 int coordnn_search(double* d_px, double* d_py, long long n, const double* h_lon, const double* h_lat, size_t nx, size_t ny,
                    long long* ties, cudaStream_t st);
 
+// coord_kdtree search (flannTranslatePointsToClosestInputCell, CDMInterpolator.cc:991-1062): exact nearest source point by
+// squared chord distance inside (max_dist_m / R)^2, else (-1000, -1000)
+int coordkd_search(double* d_px, double* d_py, long long n, const double* h_lon, const double* h_lat, size_t nx, size_t ny, double max_dist_m,
+                   long long* ties, cudaStream_t st);
+
 // ---- gather_kernels.cu (K3, K4, K5, K6) -------------------------------------------------------------
 struct GatherGeom {
     int ix, iy, ox, oy;

@@ -109,6 +109,7 @@ class Interpolator:
         self.cachedInterpolation = None
         self.cachedVectorReprojection = None
         self.method = Method.UNKNOWN
+        self.distanceOfInterest = 0.0  # CDMInterpolator::setDistanceOfInterest (metres; <= 0: derived from the output axes)
 
     # ---- setup --------------------------------------------------------------------------------
     def changeProjection(self, method, proj_input, out_x_axis, out_y_axis, out_x_axis_unit="m", out_y_axis_unit="m"):
@@ -156,12 +157,11 @@ class Interpolator:
 
     def _by_coordinates(self, method, proj_input, out_x, out_y, xunit, yunit):
         # :1336-1420
-        if method != Method.COORD_NN:
-            raise FimexB200Error("coord_kdtree is not part of this path; use coord_nearestneighbor")
         lon2d, lat2d = self._source_lonlat()
         self.cachedInterpolation = CachedInterpolation.fromCoordinates(method, proj_input, out_x, out_y, bool(_DEGREE.match(xunit)),
                                                                        bool(_DEGREE.match(yunit)), lon2d, lat2d, self.x_axis.size,
-                                                                       self.y_axis.size, self.x_dim, self.y_dim)
+                                                                       self.y_axis.size, self.x_dim, self.y_dim,
+                                                                       maxDistance=self.distanceOfInterest)
         # no reduced domain, no vector rotation on this path (:1417-1419)
 
     def _by_forward_interpolation(self, method, proj_input, out_x, out_y, xunit, yunit):

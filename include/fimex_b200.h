@@ -132,6 +132,14 @@ int fb200_cached_interpolation_create_from_projection(int funcType, const char* 
                                                       const double* in_y_axis, size_t inX, size_t inY, int in_is_degree,
                                                       fb200_interp** handle);
 
+/* The table-producing part of CDMInterpolator::changeProjectionByProjectionParametersToLatLonTemplate
+ * (src/CDMInterpolator.cc:1755-1803): the target is a 2-D lon/lat template (DEGREES, outX*outY values each, any curvilinear
+ * grid or a 1-D point list with outY = 1) in CRS proj_template (normally MIFI_WGS84_LATLON_PROJ4): deg -> rad,
+ * mifi_project_values(template -> source) (:1770), mifi_points2position on both source axes (:1789-1790), CachedInterpolation. */
+int fb200_cached_interpolation_create_from_template(int funcType, const char* proj_template, const double* tmplLon, const double* tmplLat,
+                                                    size_t outX, size_t outY, const char* proj_source, const double* in_x_axis,
+                                                    const double* in_y_axis, size_t inX, size_t inY, int in_is_degree, fb200_interp** handle);
+
 /* The table-producing part of CDMInterpolator::changeProjectionByCoordinates for MIFI_INTERPOL_COORD_NN
  * (src/CDMInterpolator.cc:1387-1412 with fastTranslatePointsToClosestInputCell :1141-1220): target axes ->
  * WGS84 lat/lon -> nearest source cell by great-circle distance.  lon2d/lat2d: source coordinates in
@@ -140,6 +148,16 @@ int fb200_cached_interpolation_create_from_coordinates(int funcType, const char*
                                                        const double* out_y_axis, size_t outX, size_t outY, int out_x_is_degree,
                                                        int out_y_is_degree, const double* lon2d, const double* lat2d, size_t inX,
                                                        size_t inY, fb200_interp** handle);
+
+/* The same for MIFI_INTERPOL_COORD_NN_KD (coord_kdtree; flannTranslatePointsToClosestInputCell, src/CDMInterpolator.cc:991-1062):
+ * the source point with the smallest squared chord distance on the unit sphere inside (maxDistance / 6371000)^2, else
+ * (-1000, -1000).  maxDistance (metres) > 0 is the reference's setDistanceOfInterest; <= 0 derives it from the output
+ * axes like getMaxDistanceOfInterest (:304-326).  funcType COORD_NN is accepted too (maxDistance is ignored then), and
+ * fb200_cached_interpolation_create_from_coordinates accepts COORD_NN_KD with the derived distance. */
+int fb200_cached_interpolation_create_from_coordinates_kd(int funcType, const char* proj_target, const double* out_x_axis,
+                                                          const double* out_y_axis, size_t outX, size_t outY, int out_x_is_degree,
+                                                          int out_y_is_degree, const double* lon2d, const double* lat2d, size_t inX,
+                                                          size_t inY, double maxDistance, fb200_interp** handle);
 
 /* CachedForwardInterpolation::CachedForwardInterpolation(..., funcType, pOnX, pOnY, inX, inY, outX, outY) --
  * src/CachedForwardInterpolation.h:51-53, src/CachedForwardInterpolation.cc:62-90.  funcType: FORWARD_*.
@@ -192,6 +210,11 @@ int fb200_vector_create(int method, const double* matrix, int ox, int oy, fb200_
 int fb200_vector_create_from_projection(int method, const char* proj_input, const char* proj_output, const double* out_x_axis,
                                         const double* out_y_axis, int out_x_axis_type, int out_y_axis_type, int ox, int oy,
                                         fb200_vector** handle);
+/* mifi_get_vector_reproject_matrix_points (src/interpolation.c:719-788) on the device for a list of `on` points given as
+ * lon/lat in DEGREES, as the lat/lon-template path builds it (src/CDMInterpolator.cc:1805-1823: proj_output =
+ * MIFI_WGS84_LATLON_PROJ4, inputIsMetric = !isDegree(source)); the handle has ox = on, oy = 1 */
+int fb200_vector_create_from_points(int method, const char* proj_input, const char* proj_output, int inputIsMetric, const double* lon,
+                                    const double* lat, int on, fb200_vector** handle);
 /* reprojectValues(uValues, vValues, size): rotate in place -- src/CachedVectorReprojection.cc:35-44 */
 int fb200_vector_reproject_values(const fb200_vector* handle, float* uValues, float* vValues, size_t size);
 int fb200_vector_reproject_values_device(const fb200_vector* handle, float* d_uValues, float* d_vValues, size_t size, void* cuda_stream);

@@ -990,6 +990,77 @@ long orc_coordnn(double* px, double* py, size_t n, const double* lon, const doub
 }
 
 /* lonLatVals2Matrix :1226-1239 */
+/* coord_kdtree: flannTranslatePointsToClosestInputCell, src/CDMInterpolator.cc:991-1062.  nanoflann (vendored in the reference,
+ * include/nanoflann/nanoflann.hpp) only prunes the search: radiusSearch(sorted) returns the matches with
+ * dist < radius (RadiusResultSet::addPoint, :150-153) ordered by distance, and the reference takes the first, i.e. the exact
+ * nearest neighbour by PointCloud::kdtree_distance = d0*d0 + d1*d1 + d2*d2 (CDMInterpolator.cc:967-973).  Brute force here.
+ * Equal distances are ordered by std::sort (unspecified); the lowest source position wins here and the count is returned.
+ * Pinned against the reference's nanoflann itself (oracle/ref_kd_driver.cc, tests/test_oracle_golden.py).  Declared deviation:
+ * source points with NaN coordinates are skipped; in the reference they enter the tree as NaN points and corrupt its
+ * bounding boxes (many targets then lose their match). */
+long orc_coordkd(double* px, double* py, size_t n, const double* lon, const double* lat, size_t nx, size_t ny, double max_dist_m)
+{
+    const size_t ns = nx * ny;
+    double* c = (double*)malloc(sizeof(double) * 3 * ns);
+    for (size_t ix = 0; ix < nx; ++ix) {
+        for (size_t iy = 0; iy < ny; ++iy) {
+            const size_t pos = ix + iy * nx;
+            if (!(isnan(lat[pos]) || isnan(lon[pos]))) {
+                const double sinLat = sin(lat[pos]), cosLat = cos(lat[pos]), sinLon = sin(lon[pos]), cosLon = cos(lon[pos]);
+                c[3 * pos] = cosLat * cosLon;
+                c[3 * pos + 1] = cosLat * sinLon;
+                c[3 * pos + 2] = sinLat;
+            } else {
+                c[3 * pos] = c[3 * pos + 1] = c[3 * pos + 2] = NAN;
+            }
+        }
+    }
+    double maxDist = max_dist_m / 6371000.;
+    const double search_radius = maxDist * maxDist;
+    long ties = 0;
+#pragma omp parallel for reduction(+ : ties)
+    for (size_t i = 0; i < n; ++i) {
+        const double sinLat = sin(py[i]), cosLat = cos(py[i]), sinLon = sin(px[i]), cosLon = cos(px[i]);
+        const double q[3] = {cosLat * cosLon, cosLat * sinLon, sinLat};
+        double best = search_radius;
+        long bestpos = -1;
+        int tie = 0;
+        for (size_t p = 0; p < ns; ++p) {
+            const double d0 = q[0] - c[3 * p], d1 = q[1] - c[3 * p + 1], d2 = q[2] - c[3 * p + 2];
+            const double dist = d0 * d0 + d1 * d1 + d2 * d2;
+            if (dist < best) {
+                best = dist;
+                bestpos = (long)p;
+                tie = 0;
+            } else if (dist == best && bestpos >= 0) {
+                tie = 1;
+            }
+        }
+        if (bestpos >= 0) {
+            px[i] = (double)(bestpos % (long)nx);
+            py[i] = (double)(bestpos / (long)nx);
+        } else {
+            px[i] = -1000;
+            py[i] = -1000;
+        }
+        ties += tie;
+    }
+    free(c);
+    return ties;
+}
+
+/* getMaxDistanceOfInterest, src/CDMInterpolator.cc:304-326 (axis values as given, times the earth radius unless metric) */
+double orc_max_distance_of_interest(const double* xa, size_t nx, const double* ya, size_t ny, int is_metric)
+{
+    const double factor = is_metric ? 1. : 6371000.;
+    double maxX = 0, maxY = 0;
+    for (size_t i = 0; i + 1 < nx; ++i)
+        maxX = fmax(factor * fabs(xa[i + 1] - xa[i]), maxX);
+    for (size_t j = 0; j + 1 < ny; ++j)
+        maxY = fmax(factor * fabs(ya[j + 1] - ya[j]), maxY);
+    return fmax(maxX, maxY);
+}
+
 void orc_lonlat_to_matrix(const double* lonv, const double* latv, size_t nlon, size_t nlat, double* lon2d, double* lat2d)
 {
     for (size_t ix = 0; ix < nlon; ++ix)

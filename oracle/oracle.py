@@ -320,6 +320,26 @@ class Oracle(_Base):
         ties = f(pxp, pyp, pxa.size, lop, lap, nx, ny)
         return pxa, pya, ties
 
+    def coordkd(self, tlon, tlat, lon2d, lat2d, nx, ny, max_dist_m):
+        """coord_kdtree search: target lon/lat (rad) -> source (ix, iy) as doubles, (-1000, -1000) if nothing is inside the radius"""
+        px, pxp = _d(np.array(tlon, dtype=np.float64, copy=True))
+        py, pyp = _d(np.array(tlat, dtype=np.float64, copy=True))
+        lo, lop = _d(lon2d)
+        la, lap = _d(lat2d)
+        f = self.lib.orc_coordkd
+        f.restype = C.c_long
+        f.argtypes = [_dp, _dp, C.c_size_t, _dp, _dp, C.c_size_t, C.c_size_t, C.c_double]
+        ties = f(pxp, pyp, px.size, lop, lap, nx, ny, float(max_dist_m))
+        return px, py, int(ties)
+
+    def max_distance_of_interest(self, xa, ya, is_metric):
+        x, xp = _d(xa)
+        y, yp = _d(ya)
+        f = self.lib.orc_max_distance_of_interest
+        f.restype = C.c_double
+        f.argtypes = [_dp, C.c_size_t, _dp, C.c_size_t, C.c_int]
+        return float(f(xp, x.size, yp, y.size, int(is_metric)))
+
     def grid_distance(self, lon2d, lat2d, nx, ny):
         lo, lop = _d(lon2d)
         la, lap = _d(lat2d)

@@ -554,6 +554,69 @@ def test_coord_nearestneighbor_against_oracle(oracle):
     assert gx[0] == 0 and gy[0] == 0 and gx[1] == -1 and gy[1] == -1
 
 
+def test_latlon_template_against_oracle(oracle):
+    """changeProjectionByProjectionParametersToLatLonTemplate (CDMInterpolator.cc:1755-1823): a curvilinear lon/lat template
+    (and a 1-D point list) as the target: project_values + points2position on the device, matrix from points"""
+    lon, lat, _ = _config2_like(40)
+    rng = np.random.default_rng(4)
+    ny, nx = 30, 50
+    jj, ii = np.meshgrid(np.arange(nx), np.arange(ny))
+    tlon = (-20 + 0.6 * jj + 0.1 * ii + 0.3 * np.sin(ii / 5.0)).ravel()
+    tlat = (50 + 0.4 * ii - 0.05 * jj + 0.2 * np.cos(jj / 7.0)).ravel()
+    field = rng.normal(250, 30, (3, lat.size, lon.size)).astype(np.float32)
+    for method in (Method.BILINEAR, Method.NEAREST_NEIGHBOR, Method.BICUBIC):
+        ci = fb.CachedInterpolation.fromTemplate(method, WGS84, tlon, tlat, nx, ny, SRC_LL, lon, lat, True)
+        gx, gy = ci.points()
+        rc, x, y = oracle.project_values(WGS84, SRC_LL, np.radians(tlon), np.radians(tlat))
+        assert rc == 1
+        wy = oracle.points2position(y, np.radians(lat), 2)
+        wx = oracle.points2position(x, np.radians(lon), 1)
+        assert np.abs(gx - wx).max() < 1e-8 and np.abs(gy - wy).max() < 1e-8  # 1e-9 degree = 4e-9 cells here
+        got = ci.interpolateValues(field)
+        assert_bit_equal(got, oracle.cached_interpolate(int(method), gx, gy, lon.size, lat.size, nx, ny, field), f"template {method}",
+                         nan_payload=(method == Method.NEAREST_NEIGHBOR))
+        assert ci.createReducedDomain()
+    # cross-section style: a list of points (outY = 1)
+    ci = fb.CachedInterpolation.fromTemplate(Method.BILINEAR, WGS84, tlon[:77], tlat[:77], 77, 1, SRC_LL, lon, lat, True)
+    assert ci.interpolateValues(field).shape == (3, 1, 77)
+    # rotation matrix for the template points: source rotated pole -> geographic, angles against the oracle
+    rlon = rng.uniform(-10, 10, 200)
+    rlat = rng.uniform(-10, 10, 200)
+    cvr = fb.CachedVectorReprojection.fromPoints(fb.MIFI_VECTOR_KEEP_SIZE, ROTPOLE, WGS84, 0, rlon, rlat)
+    rc, m = oracle.vector_matrix_points(ROTPOLE, WGS84, 0, np.radians(rlon), np.radians(rlat))
+    assert rc == 1
+    g = cvr.getMatrix()
+    assert np.abs(g[0::4] - m[0::4]).max() < 1e-7 and np.abs(g[1::4] - m[1::4]).max() < 1e-7
+
+
+def test_coord_kdtree_against_oracle(oracle):
+    """coord_kdtree (MIFI_INTERPOL_COORD_NN_KD, CDMInterpolator.cc:991-1062, 1406-1408): nearest source point by squared chord
+    distance inside the distance of interest, else (-1000, -1000) -> NaN"""
+    lon = np.arange(0, 360, 1.5)
+    lat = 90 - np.arange(0, 180.1, 1.5)
+    ax = (np.arange(60) - 29.5) * 0.7
+    lon2d, lat2d = oracle.lonlat_to_matrix(np.radians(lon), np.radians(lat))
+    rc, tx, ty = oracle.project_axes(ROTPOLE, WGS84, np.radians(ax), np.radians(ax))
+    assert rc == 1
+    for max_dist in (0.0, 60e3, 2000e3):
+        # 0: derived from the axes like getMaxDistanceOfInterest -- degrees times the earth radius, as the reference does
+        dist = max_dist if max_dist > 0 else oracle.max_distance_of_interest(ax, ax, False)
+        wx, wy, ties = oracle.coordkd(tx, ty, lon2d, lat2d, lon.size, lat.size, dist)
+        ci = fb.CachedInterpolation.fromCoordinates(Method.COORD_NN_KD, ROTPOLE, ax, ax, True, True, np.degrees(lon2d), np.degrees(lat2d),
+                                                    lon.size, lat.size, maxDistance=max_dist)
+        gx, gy = ci.points()
+        differ = int(((gx != wx) | (gy != wy)).sum())
+        assert differ <= max(2, ties), (max_dist, differ, ties)  # only (near-)equidistant candidates may resolve differently
+        if max_dist == 60e3:
+            assert (wx == -1000).any() and (wx >= 0).any()  # 1.5-degree cells: most targets are further than 60 km from a centre
+        field = np.random.default_rng(1).normal(0, 1, (2, lat.size, lon.size)).astype(np.float32)
+        assert_bit_equal(ci.interpolateValues(field), oracle.cached_interpolate(4, gx, gy, lon.size, lat.size, ax.size, ax.size, field),
+                         "coord_kdtree gather", nan_payload=True)
+    with pytest.raises(fb.FimexB200Error):
+        fb.CachedInterpolation.fromCoordinates(Method.BILINEAR, ROTPOLE, ax, ax, True, True, np.degrees(lon2d), np.degrees(lat2d), lon.size,
+                                               lat.size)
+
+
 def test_interpolator_config1_hirlam12_like(oracle):
     # BASELINE config 1: test/hirlam12.nc geometry (Xc = 5.0..6.6 step 0.1, Yc = 61.5..62.6, 2 levels x 2 times) bilinear
     # to a 0.5-degree lat/long grid via the option strings of the fimex CLI (src/binSrc/fimex.cc:1008-1034)

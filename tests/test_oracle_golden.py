@@ -309,3 +309,41 @@ def test_adapters_against_reference(oracle, reference):
     g.argtypes = [C.c_void_p, C.c_void_p, C.c_float]
     g(b.ctypes.data, b.ctypes.data + b.nbytes, fill)
     assert_bit_equal(oracle.from_float(a, float(fill), np.float32), b, "nan2bad")
+
+
+# ---------------------------------------------------------------------------------------------------
+# coord_kdtree: the restated search against the reference's own nanoflann kd-tree
+# ---------------------------------------------------------------------------------------------------
+def test_coordkd_against_reference_nanoflann(oracle):
+    """flannTranslatePointsToClosestInputCell (CDMInterpolator.cc:991-1062): the reference's vendored nanoflann header,
+    compiled from where it lies behind the reference's call sequence (oracle/ref_kd_driver.cc), against the brute-force
+    restatement.  A kd-tree only prunes: both must name the same nearest source point."""
+    import ctypes as C
+    import os
+    from oracle import oracle as orc
+    so = os.path.join(os.path.dirname(orc.REF_SO), "libkd_ref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libkd_ref.so not built (no /root/reference on this machine)")
+    lib = C.CDLL(so)
+    rng = np.random.default_rng(42)
+    nx, ny = 90, 61
+    lon = np.radians(np.arange(nx) * 4.0)
+    lat = np.radians(90 - np.arange(ny) * 3.0)
+    lon2d, lat2d = oracle.lonlat_to_matrix(lon, lat)
+    # (undefined source coordinates are a declared deviation: the reference leaves them in the cloud as NaN points, which
+    # corrupts the tree's bounding boxes -- half of the targets lose their match; the restatement and the GPU skip them)
+    tlon = rng.uniform(-np.pi, np.pi, 4000)
+    tlat = rng.uniform(-np.pi / 2, np.pi / 2, 4000)
+    for max_dist in (150e3, 400e3, 3000e3):
+        wx, wy, ties = oracle.coordkd(tlon, tlat, lon2d, lat2d, nx, ny, max_dist)
+        rx, ry = tlon.copy(), tlat.copy()
+        dp = C.POINTER(C.c_double)
+        lib.ref_coordkd.argtypes = [dp, dp, C.c_size_t, dp, dp, C.c_size_t, C.c_size_t, C.c_double]
+        lib.ref_coordkd(rx.ctypes.data_as(dp), ry.ctypes.data_as(dp), rx.size, lon2d.ctypes.data_as(dp), lat2d.ctypes.data_as(dp), nx, ny,
+                        max_dist)
+        differ = int(((rx != wx) | (ry != wy)).sum())
+        assert differ <= ties, (max_dist, differ, ties)  # equal distances (the pole row) are ordered by an unstable sort
+        assert (wx == -1000).any() == (max_dist < 400e3)
+    # getMaxDistanceOfInterest (:304-326): degrees are multiplied by the earth radius as given
+    assert oracle.max_distance_of_interest([0, 0.5, 1.0], [10, 10.25], False) == 6371000 * 0.5
+    assert oracle.max_distance_of_interest([0, 2500, 5000], [0, 1000], True) == 2500
