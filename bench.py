@@ -189,7 +189,7 @@ def main_reference(args):
         "cpu_baseline": {"value": r["value"], "unit": "values/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "values/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -214,7 +214,6 @@ def main_b200(args):
     fb.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout for the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     method = args.method
     method_id = METHODS[method]
@@ -368,13 +367,34 @@ def main_b200(args):
                        "parallelism": f"slab{world}", "setup_s": setup_s, "variant": args.variant},
             "hbm_gbs": achieved, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)  # flushed before the NCCL teardown: a buffered line is lost if that dies
+        emit(line)  # written straight to the real stdout before the NCCL teardown: a buffered line is lost if that dies
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Keep file descriptor 1 for the ONE JSON line: everything else that writes to stdout from here on (the NCCL version
+    banner, library chatter of any rank) goes to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    fd = _REAL_STDOUT if _REAL_STDOUT is not None else 1
+    while data:
+        data = data[os.write(fd, data):]
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -18,7 +18,8 @@ from .capi import (DataType, cdm_type, default_fill_value, LATITUDE, LONGITUDE, 
                    mifi_get_vector_reproject_matrix, mifi_get_vector_reproject_matrix_field, mifi_get_vector_reproject_matrix_points,
                    mifi_interpolate_f, mifi_points2position, mifi_project_axes, mifi_project_values, mifi_string_to_interpolation_method,
                    mifi_vector_reproject_direction_by_matrix_f, mifi_vector_reproject_values_by_matrix_f, mifi_vector_reproject_values_f,
-                   mifi_bad2nanf, mifi_nanf2bad, set_device, version)
+                   mifi_bad2nanf, mifi_nanf2bad, mifi_fill2d_f, mifi_creepfill2d_f, fill2d_device, creepfill2d_device, set_device,
+                   version)
 from .cached import CachedForwardInterpolation, CachedInterpolation, CachedVectorReprojection
 from .interpolator import Interpolator
 
@@ -29,5 +30,5 @@ __all__ = [
     "mifi_get_vector_reproject_matrix", "mifi_get_vector_reproject_matrix_field", "mifi_get_vector_reproject_matrix_points",
     "mifi_vector_reproject_values_by_matrix_f", "mifi_vector_reproject_direction_by_matrix_f", "mifi_vector_reproject_values_f",
     "mifi_get_values_f", "mifi_get_values_bilinear_f", "mifi_get_values_bicubic_f", "mifi_string_to_interpolation_method",
-    "mifi_bad2nanf", "mifi_nanf2bad",
+    "mifi_bad2nanf", "mifi_nanf2bad", "mifi_fill2d_f", "mifi_creepfill2d_f", "fill2d_device", "creepfill2d_device",
 ]

@@ -182,6 +182,11 @@ def _declare(lib):
         "mifi_project_axes": (i, [C.c_char_p, C.c_char_p, _vp, _vp, i, i, _vp, _vp]),
         "mifi_bad2nanf": (sz, [_vp, _vp, C.c_float]),
         "mifi_nanf2bad": (sz, [_vp, _vp, C.c_float]),
+        "mifi_fill2d_f": (i, [sz, sz, _vp, C.c_float, C.c_float, sz, P(sz)]),
+        "mifi_creepfill2d_f": (i, [sz, sz, _vp, C.c_ushort, C.c_char, P(sz)]),
+        "mifi_creepfillval2d_f": (i, [sz, sz, _vp, C.c_float, C.c_ushort, C.c_char, P(sz)]),
+        "fb200_fill2d_device": (i, [_vp, sz, sz, sz, C.c_float, C.c_float, sz, _vp]),
+        "fb200_creepfill2d_device": (i, [_vp, sz, sz, sz, i, C.c_float, C.c_ushort, C.c_char, _vp]),
         "mifi_setNumThreads": (i, [i]),
     }
     for name, (res, args) in sig.items():
@@ -337,3 +342,42 @@ def mifi_nanf2bad(data, bad):
     a = f32(data, copy=True)
     load().mifi_nanf2bad(C.c_void_p(a.ctypes.data), C.c_void_p(a.ctypes.data + a.nbytes), C.c_float(bad))
     return a
+
+
+# ------------------------------------------------------------------------------------------------ 2-D pre/post-processes
+def mifi_fill2d_f(field, relaxCrit, corrEff, maxLoop):
+    """one level [ny][nx] of host data; returns (rc, filled copy, nChanged)"""
+    a = f32(field, copy=True)
+    ny, nx = a.shape[-2:]
+    n = C.c_size_t(0)
+    rc = load().mifi_fill2d_f(nx, ny, ptr(a), relaxCrit, corrEff, int(maxLoop), C.byref(n))
+    return rc, a, n.value
+
+
+def mifi_creepfill2d_f(field, repeat, setWeight, defaultVal=None):
+    """mifi_creepfill2d_f, or mifi_creepfillval2d_f when defaultVal is given; one level [ny][nx] of host data"""
+    a = f32(field, copy=True)
+    ny, nx = a.shape[-2:]
+    n = C.c_size_t(0)
+    w = bytes([int(setWeight) & 0xff])
+    if defaultVal is None:
+        rc = load().mifi_creepfill2d_f(nx, ny, ptr(a), int(repeat), w, C.byref(n))
+    else:
+        rc = load().mifi_creepfillval2d_f(nx, ny, ptr(a), float(defaultVal), int(repeat), w, C.byref(n))
+    return rc, a, n.value
+
+
+def fill2d_device(field, relaxCrit, corrEff, maxLoop, stream=None):
+    """all levels of a CUDA tensor [..., ny, nx] in place (processArray_, CDMInterpolator.cc:136-159)"""
+    ny, nx = field.shape[-2:]
+    nz = field.numel() // max(1, nx * ny)
+    check(load().fb200_fill2d_device(ptr(field), nx, ny, nz, relaxCrit, corrEff, int(maxLoop), stream), "fill2d")
+    return field
+
+
+def creepfill2d_device(field, repeat, setWeight, defaultVal=None, stream=None):
+    ny, nx = field.shape[-2:]
+    nz = field.numel() // max(1, nx * ny)
+    check(load().fb200_creepfill2d_device(ptr(field), nx, ny, nz, int(defaultVal is not None), 0.0 if defaultVal is None else float(defaultVal),
+                                          int(repeat), bytes([int(setWeight) & 0xff]), stream), "creepfill2d")
+    return field

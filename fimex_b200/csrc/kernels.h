@@ -115,6 +115,13 @@ int launch_as_float(int in_type, const void* d_in, long long n, bool has_bad, fl
 // interpolationArray2Data: NaN -> fill, round + cast (CDMInterpolator.cc:121-124); in place allowed for FB_T_FLOAT
 int launch_from_float(const float* d_in, long long n, int out_type, double fill, void* d_out, cudaStream_t st);
 
+// ---- fill_kernels.cu (2-D pre/post-processes: fill2d, creepfill2d) -----------------------------------------------
+// nz levels of nx x ny in place; d_nchanged (nz counters, may be null) receives the NaN count of every level
+int launch_fill2d(float* d_field, size_t nx, size_t ny, size_t nz, float relaxCrit, float corrEff, size_t maxLoop,
+                  unsigned long long* d_nchanged, cudaStream_t st);
+int launch_creepfill2d(float* d_field, size_t nx, size_t ny, size_t nz, bool use_mean, float defaultVal, unsigned short repeat,
+                       signed char setWeight, unsigned long long* d_nchanged, cudaStream_t st);
+
 // ---- forward_kernels.cu (K8) ---------------------------------------------------------------------------
 struct ForwardPlan {
     long long n_in = 0, n_cells = 0;

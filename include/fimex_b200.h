@@ -297,6 +297,18 @@ int mifi_project_axes(const char* proj_input, const char* proj_output, const dou
 size_t mifi_bad2nanf(float* posPtr, float* endPtr, float badVal);
 size_t mifi_nanf2bad(float* posPtr, float* endPtr, float badVal);
 
+/* The 2-D pre/post-processes of getDataSlice (--interpolate.preprocess / postprocess, src/CDMInterpolator.cc:126-159, 256, 284;
+ * include/fimex/interpolation.h:520-560): same prototypes as the reference, one level of host data per call.  nx, ny >= 2. */
+int mifi_fill2d_f(size_t nx, size_t ny, float* field, float relaxCrit, float corrEff, size_t maxLoop, size_t* nChanged);
+int mifi_creepfill2d_f(size_t nx, size_t ny, float* field, unsigned short repeat, char setWeight, size_t* nChanged);
+int mifi_creepfillval2d_f(size_t nx, size_t ny, float* field, float defaultVal, unsigned short repeat, char setWeight, size_t* nChanged);
+/* the same for nz levels resident on the device, in place (processArray_, src/CDMInterpolator.cc:136-159): one CTA per level
+ * walks the anti-diagonals of the lexicographic Gauss-Seidel sweeps, so results are bit-identical to the reference.
+ * useDefaultVal != 0: creepfillval2d(defaultVal), else creepfill2d (mean of the defined values as first guess). */
+int fb200_fill2d_device(float* d_field, size_t nx, size_t ny, size_t nz, float relaxCrit, float corrEff, size_t maxLoop, void* cuda_stream);
+int fb200_creepfill2d_device(float* d_field, size_t nx, size_t ny, size_t nz, int useDefaultVal, float defaultVal, unsigned short repeat,
+                             char setWeight, void* cuda_stream);
+
 /* ThreadPool.c's knob (src/ThreadPool.c:33-46): kept as a symbol, has no effect on this path */
 int mifi_setNumThreads(int n);
 

@@ -849,6 +849,166 @@ ORC_FROM_FLOAT_INT(i64, long long)
 ORC_FROM_FLOAT_INT(u64, unsigned long long)
 
 /* ------------------------------------------------------------------------------------------------
+ * 8f rank 3: the 2-D pre/post-processes.  mifi_fill2d_f (src/interpolation.c:1246-1376): undefined cells get the mean of the
+ * defined ones, then lexicographic Gauss-Seidel relaxation of the Laplace equation on those cells (weight 1 on undefined
+ * cells, times corrEff in the interior), a convergence test every 10th sweep, one-sided relaxation of the border after each
+ * sweep.  mifi_creepfill(val)2d_f (:1378-1525): undefined cells creep in from defined neighbours, `repeat` times per cell.
+ * Restated sweep by sweep; pinned bit for bit against the compiled reference (tests/test_oracle_golden.py).
+ * ---------------------------------------------------------------------------------------------- */
+int orc_fill2d(size_t nx, size_t ny, float* field, float relaxCrit, float corrEff, size_t maxLoop, size_t* nChanged)
+{
+    const size_t n = nx * ny;
+    if (n == 0)
+        return ORC_OK;
+    double sum = 0;
+    size_t nundef = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (isnan(field[i]))
+            ++nundef;
+        else
+            sum += field[i];
+    }
+    *nChanged = nundef;
+    const size_t ndef = n - nundef;
+    if (ndef == 0 || nundef == 0)
+        return ORC_OK;
+    float* w = (float*)malloc(n * sizeof(float));
+    const double average = sum / ndef;
+    double dev = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (isnan(field[i])) {
+            w[i] = 1.f;
+            field[i] = average;
+        } else {
+            dev += fabs(field[i] - average);
+            w[i] = 0.f;
+        }
+    }
+    dev /= ndef;
+    const double crit = relaxCrit * dev;
+    const size_t xl = nx - 1, yl = ny - 1; /* last column / row */
+    for (size_t y = 1; y < yl; ++y)
+        for (size_t x = 1; x < xl; ++x)
+            w[y * nx + x] *= corrEff;
+    for (size_t loop = 0; loop < maxLoop; ++loop) {
+        int bad = 0;
+        const int test = (loop < (maxLoop - 5)) && (loop % 10 == 0);
+        const float crtest = crit * corrEff;
+        for (size_t y = 1; y < yl; ++y) {
+            for (size_t x = 1; x < xl; ++x) {
+                float* f = field + y * nx + x;
+                const float e = (f[1] + f[-1] + f[nx] + f[-(long)nx]) * 0.25 - *f;
+                const float ew = e * w[y * nx + x];
+                *f += ew;
+                if (test && fabs(ew) > crtest)
+                    bad = 1;
+            }
+        }
+        if (test && !bad)
+            break;
+        for (size_t y = 1; y < yl; ++y) {
+            float* r = field + y * nx;
+            r[0] += (r[1] - r[0]) * w[y * nx];
+            r[xl] += (r[xl - 1] - r[xl]) * w[y * nx + xl];
+        }
+        for (size_t x = 0; x < nx; ++x) {
+            field[x] += (field[nx + x] - field[x]) * w[x];
+            field[yl * nx + x] += (field[(yl - 1) * nx + x] - field[yl * nx + x]) * w[yl * nx + x];
+        }
+    }
+    free(w);
+    return ORC_OK;
+}
+
+/* use_mean != 0: mifi_creepfill2d_f (first guess = float mean of the defined values); else mifi_creepfillval2d_f */
+int orc_creepfill2d(size_t nx, size_t ny, float* field, int use_mean, float defaultVal, unsigned short repeat, char setWeight,
+                    size_t* nChanged)
+{
+    const size_t n = nx * ny;
+    if (n == 0)
+        return ORC_OK;
+    double sum = 0;
+    size_t nundef = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (isnan(field[i]))
+            ++nundef;
+        else
+            sum += field[i];
+    }
+    *nChanged = nundef;
+    const size_t ndef = n - nundef;
+    if (ndef == 0 || nundef == 0)
+        return ORC_OK;
+    float guess = defaultVal;
+    if (use_mean)
+        guess = sum / ndef;
+    char* w = (char*)malloc(n);
+    unsigned short* r = (unsigned short*)malloc(n * sizeof(unsigned short));
+    for (size_t i = 0; i < n; ++i) {
+        if (isnan(field[i])) {
+            w[i] = 0;
+            r[i] = 0;
+            field[i] = guess;
+        } else {
+            w[i] = setWeight;
+            r[i] = repeat;
+        }
+    }
+    const size_t xl = nx - 1, yl = ny - 1;
+    size_t changed = 1, loops = 0;
+    while (changed > 0 && loops < ndef) {
+        changed = 0;
+        ++loops;
+        for (size_t y = 1; y < yl; ++y) {
+            for (size_t x = 1; x < xl; ++x) {
+                const size_t p = y * nx + x;
+                if (r[p] >= repeat)
+                    continue;
+                const size_t wsum = w[p + 1] + w[p - 1] + w[p + nx] + w[p - nx];
+                if (wsum == 0)
+                    continue;
+                field[p] += w[p + 1] * field[p + 1] + w[p - 1] * field[p - 1] + w[p + nx] * field[p + nx] + w[p - nx] * field[p - nx];
+                field[p] /= (1 + wsum);
+                w[p] = 1;
+                r[p]++;
+                ++changed;
+            }
+        }
+    }
+    for (size_t k = 0; k < repeat; ++k) {
+        for (size_t y = 1; y < yl; ++y) {
+            const size_t a = y * nx, b = y * nx + xl;
+            if (r[a] < repeat) {
+                field[a] += field[a + 1] * w[a + 1];
+                field[a] /= (1 + w[a + 1]);
+                w[a] = 1;
+            }
+            if (r[b] < repeat) {
+                field[b] += field[b - 1] * w[b - 1];
+                field[b] /= (1 + w[b - 1]);
+                w[b] = 1;
+            }
+        }
+        for (size_t x = 0; x < nx; ++x) {
+            const size_t a = x, b = yl * nx + x;
+            if (r[a] < repeat) {
+                field[a] += field[a + nx] * w[a + nx];
+                field[a] /= (1 + w[a + nx]);
+                w[a] = 1;
+            }
+            if (r[b] < repeat) {
+                field[b] += field[b - nx] * w[b - nx];
+                field[b] /= (1 + w[b - nx]);
+                w[b] = 1;
+            }
+        }
+    }
+    free(r);
+    free(w);
+    return ORC_OK;
+}
+
+/* ------------------------------------------------------------------------------------------------
  * A18  coord_nearestneighbor search, src/CDMInterpolator.cc:1064-1125 (getGridDistance) and
  * :1141-1220 (fastTranslatePointsToClosestInputCell).  The reference sorts with std::sort (unstable);
  * the order among equal latitudes is libstdc++-specific and only matters for exact cos_d ties.  Here a

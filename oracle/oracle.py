@@ -320,6 +320,48 @@ class Oracle(_Base):
         ties = f(pxp, pyp, pxa.size, lop, lap, nx, ny)
         return pxa, pya, ties
 
+    def fill2d(self, field, relaxCrit, corrEff, maxLoop, lib=None, name="orc_fill2d"):
+        """mifi_fill2d_f on every level of field[..., ny, nx]; returns (filled copy, NaN count per level)"""
+        a = np.array(field, dtype=np.float32, copy=True, order="C")
+        ny, nx = a.shape[-2:]
+        f = getattr(lib or self.lib, name)
+        f.restype = C.c_int
+        f.argtypes = [C.c_size_t, C.c_size_t, _fp, C.c_float, C.c_float, C.c_size_t, C.POINTER(C.c_size_t)]
+        counts = []
+        flat = a.reshape(-1, ny, nx)
+        for z in range(flat.shape[0]):
+            n = C.c_size_t(0)
+            f(nx, ny, flat[z].ctypes.data_as(_fp), relaxCrit, corrEff, maxLoop, C.byref(n))
+            counts.append(n.value)
+        return a, counts
+
+    def creepfill2d(self, field, repeat, setWeight, defaultVal=None, lib=None, prefix="orc"):
+        """mifi_creepfill2d_f (defaultVal None) / mifi_creepfillval2d_f on every level of field[..., ny, nx]"""
+        a = np.array(field, dtype=np.float32, copy=True, order="C")
+        ny, nx = a.shape[-2:]
+        flat = a.reshape(-1, ny, nx)
+        counts = []
+        for z in range(flat.shape[0]):
+            n = C.c_size_t(0)
+            p = flat[z].ctypes.data_as(_fp)
+            if prefix == "orc":
+                f = self.lib.orc_creepfill2d
+                f.restype = C.c_int
+                f.argtypes = [C.c_size_t, C.c_size_t, _fp, C.c_int, C.c_float, C.c_ushort, C.c_char, C.POINTER(C.c_size_t)]
+                f(nx, ny, p, int(defaultVal is None), 0.0 if defaultVal is None else defaultVal, repeat, bytes([setWeight & 0xff]), C.byref(n))
+            elif defaultVal is None:
+                f = lib.mifi_creepfill2d_f
+                f.restype = C.c_int
+                f.argtypes = [C.c_size_t, C.c_size_t, _fp, C.c_ushort, C.c_char, C.POINTER(C.c_size_t)]
+                f(nx, ny, p, repeat, bytes([setWeight & 0xff]), C.byref(n))
+            else:
+                f = lib.mifi_creepfillval2d_f
+                f.restype = C.c_int
+                f.argtypes = [C.c_size_t, C.c_size_t, _fp, C.c_float, C.c_ushort, C.c_char, C.POINTER(C.c_size_t)]
+                f(nx, ny, p, defaultVal, repeat, bytes([setWeight & 0xff]), C.byref(n))
+            counts.append(n.value)
+        return a, counts
+
     def coordkd(self, tlon, tlat, lon2d, lat2d, nx, ny, max_dist_m):
         """coord_kdtree search: target lon/lat (rad) -> source (ix, iy) as doubles, (-1000, -1000) if nothing is inside the radius"""
         px, pxp = _d(np.array(tlon, dtype=np.float64, copy=True))

@@ -805,3 +805,59 @@ def test_full_size_bilinear_properties(oracle):
     assert_bit_equal(got, want, "full-size sample vs oracle")
     # (4) checksum of checksums: per-level sums of the output equal the sums of per-row sums (layout sanity)
     assert torch.allclose(oa.sum(dim=(1, 2), dtype=torch.float64), oa.sum(dim=2, dtype=torch.float64).sum(dim=1))
+
+
+# =====================================================================================================
+# 8f rank 3: fill2d / creepfill2d pre/post-processes on the device (anti-diagonal wavefronts of the reference's sweeps)
+# =====================================================================================================
+def _holey(rng, shape, frac=0.1):
+    ny, nx = shape[-2:]
+    yy, xx = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+    f = (280 + 10 * np.sin(xx / 7.0) * np.cos(yy / 5.0) + rng.normal(0, 0.5, shape)).astype(np.float32)
+    f[rng.random(shape) < frac] = np.nan
+    if ny > 12 and nx > 20:
+        f[..., 3:9, 4:15] = np.nan
+        f[..., 0, :5] = np.nan
+        f[..., -1, -3:] = np.nan
+        f[..., 5:8, 0] = np.nan
+    return f
+
+
+@pytest.mark.parametrize("shape", [(3, 20, 31), (2, 77, 130), (1, 2, 2), (2, 2, 9), (2, 9, 2), (1, 3, 3), (1, 600, 3)])
+def test_fill2d_creepfill2d_bit_exact(oracle, shape):
+    import torch
+    rng = np.random.default_rng(sum(shape))
+    f = _holey(rng, shape, 0.3 if min(shape[-2:]) < 10 else 0.1)
+    for args in ((0.01, 1.6, 100), (1e-6, 1.0, 7), (0.5, 1.9, 3), (0.01, 1.6, 0)):
+        want, counts = oracle.fill2d(f, *args)
+        dev = fb.fill2d_device(torch.from_numpy(f.copy()).cuda(), *args).cpu().numpy()
+        assert np.array_equal(dev.view(np.uint32), want.view(np.uint32)), ("fill2d", args)
+        rc, one, n = fb.mifi_fill2d_f(f[0], *args)  # the reference's own host-pointer prototype
+        assert rc == fb.MIFI_OK and n == counts[0] and np.array_equal(one.view(np.uint32), want[0].view(np.uint32))
+    for repeat, weight, dv in ((20, 2, None), (3, 1, None), (5, 2, 0.0), (1, 3, -7.5), (0, 2, None)):
+        want, counts = oracle.creepfill2d(f, repeat, weight, dv)
+        dev = fb.creepfill2d_device(torch.from_numpy(f.copy()).cuda(), repeat, weight, dv).cpu().numpy()
+        assert np.array_equal(dev.view(np.uint32), want.view(np.uint32)), ("creepfill2d", repeat, weight, dv)
+        rc, one, n = fb.mifi_creepfill2d_f(f[0], repeat, weight, dv)
+        assert rc == fb.MIFI_OK and n == counts[0] and np.array_equal(one.view(np.uint32), want[0].view(np.uint32))
+    # nothing to fill / nothing defined: untouched
+    full = np.ones(shape, dtype=np.float32)
+    assert np.array_equal(fb.fill2d_device(torch.from_numpy(full.copy()).cuda(), 0.01, 1.6, 100).cpu().numpy(), full)
+    allnan = torch.full(shape, float("nan"), device="cuda")
+    assert torch.isnan(fb.creepfill2d_device(allnan, 20, 2)).all()
+
+
+def test_fill2d_as_preprocess_at_source_size(oracle):
+    """the cropped ERA5 footprint of config 2 (1440 x 202), a handful of levels: timing + parity of one level"""
+    import torch
+    rng = np.random.default_rng(3)
+    f = _holey(rng, (8, 202, 1440), 0.05)
+    d = torch.from_numpy(f.copy()).cuda()
+    fb.fill2d_device(d, 0.01, 1.6, 100)
+    torch.cuda.synchronize()
+    want, _ = oracle.fill2d(f[:1], 0.01, 1.6, 100)
+    assert np.array_equal(d[:1].cpu().numpy().view(np.uint32), want.view(np.uint32))
+    d2 = torch.from_numpy(f.copy()).cuda()
+    fb.creepfill2d_device(d2, 20, 2)
+    want, _ = oracle.creepfill2d(f[:1], 20, 2)
+    assert np.array_equal(d2[:1].cpu().numpy().view(np.uint32), want.view(np.uint32))

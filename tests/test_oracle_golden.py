@@ -347,3 +347,43 @@ def test_coordkd_against_reference_nanoflann(oracle):
     # getMaxDistanceOfInterest (:304-326): degrees are multiplied by the earth radius as given
     assert oracle.max_distance_of_interest([0, 0.5, 1.0], [10, 10.25], False) == 6371000 * 0.5
     assert oracle.max_distance_of_interest([0, 2500, 5000], [0, 1000], True) == 2500
+
+
+# ---------------------------------------------------------------------------------------------------
+# fill2d / creepfill2d: the restated sweeps against the compiled reference
+# ---------------------------------------------------------------------------------------------------
+def _holey_field(rng, shape, frac):
+    ny, nx = shape[-2:]
+    yy, xx = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+    f = (280 + 10 * np.sin(xx / 7.0) * np.cos(yy / 5.0) + rng.normal(0, 0.5, shape)).astype(np.float32)
+    f[rng.random(shape) < frac] = np.nan
+    f[..., 3:9, 4:15] = np.nan  # a block hole, and holes on the border
+    f[..., 0, :5] = np.nan
+    f[..., -1, -3:] = np.nan
+    f[..., 5:8, 0] = np.nan
+    return f
+
+
+@pytest.mark.parametrize("shape", [(3, 20, 31), (1, 2, 2), (2, 2, 9), (2, 9, 2), (1, 3, 3)])
+def test_fill2d_and_creepfill2d_against_reference(oracle, reference, shape):
+    """interpolation.c:1246-1537 compiled unmodified vs oracle/mifi_oracle.c, bit for bit, including the convergence exit,
+    maxLoop < 5 (the size_t wrap of `maxLoop - 5`), degenerate 2-wide grids and levels with nothing to fill"""
+    rng = np.random.default_rng(sum(shape))
+    f = _holey_field(rng, shape, 0.1) if min(shape[-2:]) > 9 else rng.normal(5, 1, shape).astype(np.float32)
+    if min(shape[-2:]) <= 9:
+        f.reshape(-1)[::3] = np.nan
+    for args in ((0.01, 1.6, 100), (1e-6, 1.0, 7), (0.5, 1.9, 3), (0.01, 1.6, 0)):
+        got, n1 = oracle.fill2d(f, *args)
+        want, n2 = oracle.fill2d(f, *args, lib=reference.lib, name="mifi_fill2d_f")
+        assert n1 == n2
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), args
+        assert not np.isnan(got).any()
+    for repeat, weight, dv in ((20, 2, None), (3, 1, None), (5, 2, 0.0), (1, 3, -7.5), (0, 2, None)):
+        got, n1 = oracle.creepfill2d(f, repeat, weight, dv)
+        want, n2 = oracle.creepfill2d(f, repeat, weight, dv, lib=reference.lib, prefix="ref")
+        assert n1 == n2
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (repeat, weight, dv)
+    full = np.ones(shape, dtype=np.float32)
+    assert np.array_equal(oracle.fill2d(full, 0.01, 1.6, 100)[0], full)
+    allnan = np.full(shape, np.nan, dtype=np.float32)
+    assert np.isnan(oracle.creepfill2d(allnan, 20, 2)[0]).all()
