@@ -861,3 +861,35 @@ def test_fill2d_as_preprocess_at_source_size(oracle):
     fb.creepfill2d_device(d2, 20, 2)
     want, _ = oracle.creepfill2d(f[:1], 20, 2)
     assert np.array_equal(d2[:1].cpu().numpy().view(np.uint32), want.view(np.uint32))
+
+
+def test_concurrent_calls_on_one_handle(oracle):
+    """interpolateValues / getDataSlice / reprojectValues are const in the reference and are called concurrently from the
+    writer's OpenMP tasks on ONE object (src/NetCDF_CDMWriter.cc:749-753): eight host threads share a handle here (ctypes
+    releases the GIL during the call), each with its own data, host-buffer path (per-call streams and scratch)."""
+    import threading
+    inX, inY, inZ, outX, outY = 60, 50, 40, 203, 160
+    px, py = _smooth_positions(inX, inY, outX, outY, 17.0, 5.0, 3)
+    rng = np.random.default_rng(77)
+    fields = [rng.normal(250, 30, (inZ, inY, inX)).astype(np.float32) for _ in range(8)]
+    for method in (Method.BILINEAR, Method.BICUBIC):
+        ci = fb.CachedInterpolation("x", "y", method, px, py, inX, inY, outX, outY)
+        want = [oracle.cached_interpolate(int(method), px, py, inX, inY, outX, outY, f) for f in fields]
+        got = [None] * len(fields)
+        errors = []
+
+        def work(i):
+            try:
+                for _ in range(3):
+                    got[i] = ci.interpolateValues(fields[i]) if i % 2 == 0 else ci.getDataSlice(fields[i], np.nan)
+            except Exception as e:  # pragma: no cover
+                errors.append(e)
+
+        threads = [threading.Thread(target=work, args=(i,)) for i in range(len(fields))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert not errors, errors
+        for i in range(len(fields)):
+            assert_bit_equal(got[i], want[i], f"thread {i}, method {method}")
