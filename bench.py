@@ -305,6 +305,9 @@ def main_b200(args):
                 "kernel_ms": kernel_ms,
                 "formula": f"{out_elem}*N_out*Z (store) + {in_elem}*N_fp*Z (compulsory load of the cropped footprint) + 16*N_out (two fp64 positions)",
                 "n_out": n_out, "n_fp": n_fp, "levels": nlev}
+    if method_id == 2:
+        roofline["note"] = ("bit-exact bicubic needs 35 fp64 instructions per output (separately rounded multiplies and adds, as the "
+                            "reference on x86-64): the fp64 pipe (64 lanes/clk/SM) caps it at about 0.35 of the HBM roofline; see DESIGN.md section 4")
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:

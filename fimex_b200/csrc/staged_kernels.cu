@@ -42,6 +42,9 @@ constexpr int kTilePts = 1024;
 // distinct taps, i.e. span fewer than ~30 source cells.
 //   bilinear: 64 x 16, lane = x, thread t owns (t & 63, (t >> 6) + 4k): a row is written by two neighbouring warps
 //   nearest neighbour: 128 x 8, thread t owns (4 (t & 31) + k, t >> 5): one 128-bit store per thread and level
+#ifndef FB_NN_CTAS
+#define FB_NN_CTAS 3 // resident CTAs per SM the nearest-neighbour kernel is compiled for (experiments: -DFB_NN_CTAS=4)
+#endif
 #ifndef FB_BL_TILE_X
 #define FB_BL_TILE_X 64 // bilinear tile width: 32 or 64 (experiments: -DFB_BL_TILE_X=32)
 #endif
@@ -201,7 +204,7 @@ __device__ __forceinline__ void cp_async_wait_all()
 // bad0 / bad1 become NaN before any point reads them).  NF = 2: both components of a vector through one table pass
 // (CDMInterpolator.cc:255-276), ROT: rotated in the epilogue (mifi_vector_reproject_values_by_matrix_f, interpolation.c:790-812).
 template <bool NN, int NF, bool ROT, class Out>
-__global__ void __launch_bounds__(kThreads, NF == 1 ? 3 : 2)
+__global__ void __launch_bounds__(kThreads, NF == 1 ? (NN ? FB_NN_CTAS : 3) : 2)
     k_gather_bilinear_staged(GatherGeom g, int tiles_x, const int* __restrict__ taps, const int* __restrict__ ntaps_tab,
                              const uint4* __restrict__ meta, const float4* __restrict__ xf4, const float4* __restrict__ yf4,
                              const float* __restrict__ in0, const float* __restrict__ in1, typename Out::type* __restrict__ out0,
