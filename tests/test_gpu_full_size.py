@@ -211,3 +211,45 @@ def test_config5_swath_forward_full_size(oracle, method):
     alg = 8 * n_in + 8 * n_cells  # values + perm + offsets + store
     _log(f"5 {method.name.lower()} 10M swath -> 3000x6000", ms=ms, points_per_s=n_in / (ms * 1e-3), gbs=alg / (ms * 1e-3) / 1e9, setup_s=setup,
          filled_fraction=float(filled))
+
+
+def test_config2_get_data_slice_and_vector_full_size(oracle):
+    """config 2 geometry (2000 x 2000 rotated pole, 137 levels) through the fused slice calls: a packed int16 variable in and
+    out (fb200_interp_get_data_slice) and an x/y wind pair with rotation through the staged bilinear gather
+    (fb200_interp_interpolate_vector); samples against the oracle, exact"""
+    import torch
+    ax = (np.arange(2000) - 999.5) * 0.0225
+    ci = fb.CachedInterpolation.fromProjection(Method.BILINEAR, ROTPOLE, ax, ax, True, True, SRC_LL, LON, LAT, True)
+    assert ci.createReducedDomain()
+    cvr = fb.CachedVectorReprojection.fromProjection(fb.MIFI_VECTOR_KEEP_SIZE, SRC_LL, ROTPOLE, ax, ax, fb.LONGITUDE, fb.LATITUDE)
+    inX, inY = ci.getInX(), ci.getInY()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    packed = torch.randint(-3000, 3000, (NZ, inY, inX), generator=g, device="cuda", dtype=torch.int16)
+    packed[torch.rand((NZ, inY, inX), generator=g, device="cuda") < 0.01] = -32767
+    out = ci.getDataSlice(packed, -32767.0)
+    ms16 = _time_device(lambda: ci.getDataSlice(packed, -32767.0, out=out.view(-1)))
+    assert out.dtype == torch.int16 and out.shape == (NZ, 2000, 2000)
+    frac_fill = (out[0] == -32767).float().mean().item()
+    assert 0.02 < frac_fill < 0.06  # about 4 taps x 1 % of the points see an undefined tap
+    gx, gy = ci.points()
+    rng = np.random.default_rng(3)
+    sample = rng.integers(0, 4_000_000, 3000)
+    hp = packed[:8].cpu().numpy()
+    want = oracle.from_float(oracle.cached_interpolate(1, gx[sample], gy[sample], inX, inY, sample.size, 1, oracle.as_float(hp, -32767.0)),
+                             -32767.0, np.int16)
+    idx = torch.from_numpy(sample).cuda()
+    assert np.array_equal(out.view(NZ, -1)[:8, idx].cpu().numpy().ravel(), want.ravel())
+    # x/y wind pair
+    u = torch.randn((NZ, inY, inX), generator=g, device="cuda") * 10
+    v = torch.randn((NZ, inY, inX), generator=g, device="cuda") * 10
+    uo, vo = ci.interpolateVector(u, v, cvr)
+    msv = _time_device(lambda: ci.interpolateVector(u, v, cvr), reps=2)
+    m = cvr.getMatrix().reshape(-1, 4)[sample].ravel()
+    hu, hv = u[:8].cpu().numpy(), v[:8].cpu().numpy()
+    wu = oracle.cached_interpolate(1, gx[sample], gy[sample], inX, inY, sample.size, 1, hu)
+    wv = oracle.cached_interpolate(1, gx[sample], gy[sample], inX, inY, sample.size, 1, hv)
+    wu, wv = oracle.vector_reproject_by_matrix(m, wu, wv, sample.size, 1, 8)
+    assert_bit_equal(uo.view(NZ, -1)[:8, idx].cpu().numpy().ravel(), wu.ravel(), "config 2 u sample")
+    assert_bit_equal(vo.view(NZ, -1)[:8, idx].cpu().numpy().ravel(), wv.ravel(), "config 2 v sample")
+    _log("2 getDataSlice int16 2000x2000x137", ms=ms16, values_per_s=NZ * 4e6 / (ms16 * 1e-3), fill_fraction=frac_fill)
+    _log("2 bilinear u/v + rotation 2000x2000x137", ms=msv, pairs_per_s=NZ * 4e6 / (msv * 1e-3))
