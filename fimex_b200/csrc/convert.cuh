@@ -68,13 +68,6 @@ struct is_fp<double> {
     static constexpr bool value = true;
 };
 
-// MetNoFimex::round for magnitudes of 2^31 and more (never a sane data value): out of line, so that the store path of
-// the gathers stays short
-static __device__ __noinline__ int lround_slow(float v)
-{
-    return (int)llroundf(v);
-}
-
 // The value the gather produced, stored as is: CachedInterpolationInterface::interpolateValues' own output
 // (NaN = MIFI_UNDEFINED_F stays NaN)
 struct StorePlain {
@@ -93,15 +86,12 @@ struct StoreAs {
             return isnan(v) ? fill : (OUT)__fadd_rn(v, 0.f); // == (float)(1.*in + 0.): only -0 changes (to +0)
         if (is_fp<OUT>::value)
             return isnan(v) ? fill : (OUT)__dadd_rn((double)v, 0.); // 1.*in + 0. in fp64
-        // lround (half away from zero) in long, narrowed to int by MetNoFimex::round, then to OUT; branch-free for
-        // |v| < 2^31: trunc, then one step away from zero when the (exact) remainder is >= 0.5.  Values beyond the
-        // range of long are undefined in the reference.
-        const float t = truncf(v);
-        int r = __float2int_rz(t);
-        r += (fabsf(__fsub_rn(v, t)) >= 0.5f) ? ((v < 0.f) ? -1 : 1) : 0;
-        if (fabsf(v) >= 2147483520.f) // false for NaN
-            r = lround_slow(v);
-        return isnan(v) ? fill : (OUT)r;
+        // lround (half away from zero) in long, narrowed to int by MetNoFimex::round, then to OUT.  In fp64 |v| + 0.5 is exact
+        // for every float, so truncating v + copysign(0.5, v) IS lround(v): four branch-free instructions (F2F, LOP3, DADD,
+        // F2I.S64) for all |v| < 2^63; values beyond the range of long are undefined in the reference.
+        const double half = __hiloint2double(0x3FE00000 | (int)(__float_as_uint(v) & 0x80000000u), 0);
+        const long long r = __double2ll_rz(__dadd_rn((double)v, half));
+        return isnan(v) ? fill : (OUT)(int)r;
     }
 };
 
