@@ -30,6 +30,24 @@ struct Stats {
 };
 
 // NaN count and the sequential double sum of the defined values in row-major order (interpolation.c:1252-1264, :1492-1503)
+// sequential sum of |v - average| over the defined values of a chunk in shared memory, continuing `dev` (interpolation.c:1296)
+__device__ __forceinline__ double chunk_deviation(const float* s_buf, int m, double average, double dev)
+{
+    int i = 0;
+    for (; i + 8 <= m; i += 8) {
+        const float4 a = *reinterpret_cast<const float4*>(s_buf + i), b = *reinterpret_cast<const float4*>(s_buf + i + 4);
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (!isnan(v[k]))
+                dev = __dadd_rn(dev, fabs(__dsub_rn((double)v[k], average)));
+    }
+    for (; i < m; ++i)
+        if (!isnan(s_buf[i]))
+            dev = __dadd_rn(dev, fabs(__dsub_rn((double)s_buf[i], average)));
+    return dev;
+}
+
 __device__ Stats level_sum(const float* __restrict__ f, size_t n, float* s_buf)
 {
     __shared__ Stats s_st;
@@ -43,10 +61,22 @@ __device__ Stats level_sum(const float* __restrict__ f, size_t n, float* s_buf)
         for (int i = threadIdx.x; i < m; i += kT)
             s_buf[i] = f[c0 + i];
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (threadIdx.x == 0) { // the serial chain is one DADD per value; loads, conversions and NaN tests run ahead of it
             double sum = s_st.sum;
             unsigned long long nn = s_st.n_nan;
-            for (int i = 0; i < m; ++i) {
+            int i = 0;
+            for (; i + 8 <= m; i += 8) {
+                const float4 a = *reinterpret_cast<const float4*>(s_buf + i), b = *reinterpret_cast<const float4*>(s_buf + i + 4);
+                const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (isnan(v[k]))
+                        ++nn;
+                    else
+                        sum = __dadd_rn(sum, (double)v[k]);
+                }
+            }
+            for (; i < m; ++i) {
                 const float v = s_buf[i];
                 if (isnan(v))
                     ++nn;
@@ -65,7 +95,7 @@ __device__ Stats level_sum(const float* __restrict__ f, size_t n, float* s_buf)
 __global__ void __launch_bounds__(kT) k_fill2d(float* __restrict__ field, float* __restrict__ wfield, int nx, int ny, float relaxCrit,
                                                float corrEff, unsigned long long maxLoop, unsigned long long* __restrict__ n_changed)
 {
-    __shared__ float s_buf[kChunk];
+    __shared__ __align__(16) float s_buf[kChunk];
     __shared__ double s_dev;
     __shared__ int s_bad;
     const size_t n = (size_t)nx * ny;
@@ -96,15 +126,8 @@ __global__ void __launch_bounds__(kT) k_fill2d(float* __restrict__ field, float*
             }
         }
         __syncthreads();
-        if (t == 0) {
-            double dev = s_dev;
-            for (int i = 0; i < m; ++i) {
-                const float v = s_buf[i];
-                if (!isnan(v))
-                    dev = __dadd_rn(dev, fabs(__dsub_rn((double)v, average)));
-            }
-            s_dev = dev;
-        }
+        if (t == 0)
+            s_dev = chunk_deviation(s_buf, m, average, s_dev);
     }
     __syncthreads();
     const double stddev = __ddiv_rn(s_dev, (double)nUnchanged);
@@ -164,13 +187,238 @@ __global__ void __launch_bounds__(kT) k_fill2d(float* __restrict__ field, float*
     }
 }
 
+// ------------------------------------------------------------------------------------------------------- fill2d, skewed
+// The same sweeps with CONSECUTIVE SWEEPS PIPELINED.  Cell (x, y) of sweep n depends on (x-1, y), (x, y-1) of sweep n and on
+// (x+1, y), (x, y+1), (x, y) of sweep n-1, so every cell with the same time tau = 2n + x + y is independent: up to B sweeps run
+// one behind the other, two diagonals apart, and a level needs (nx + ny + 2B) barriers per B sweeps instead of B (nx + ny).
+// The 2B + 6 diagonals in flight live in a shared-memory ring (values and weights), so a cell is read from and written to
+// global memory once per block of sweeps instead of once per sweep.  The one-sided border relaxation after sweep n
+// (interpolation.c:1354-1363) is scheduled into the same time line (each border cell right after the interior cell it reads);
+// the last sweep of a block gets its borders from a plain pass over global memory, because a block ends where the reference
+// tests convergence (every 10th sweep) and returns BEFORE that sweep's border pass.
+template <int NR>
+__global__ void __launch_bounds__(kT) k_fill2d_skewed(float* __restrict__ field, float* __restrict__ wfield, int nx, int ny, int by_y,
+                                                      int lp, float relaxCrit, float corrEff, unsigned long long maxLoop,
+                                                      unsigned long long* __restrict__ n_changed)
+{
+    constexpr int B = NR == 32 ? 10 : 5; // sweeps in flight: 2B + 5 <= NR live diagonals
+    extern __shared__ __align__(16) float s_ring[]; // [NR][lp] values, then [NR][lp] weights
+    __shared__ __align__(16) float s_buf[kChunk];
+    __shared__ double s_dev;
+    __shared__ int s_bad;
+    float* rf = s_ring;
+    float* rw = s_ring + NR * lp;
+    const size_t n = (size_t)nx * ny;
+    float* f = field + blockIdx.x * n;
+    float* w = wfield + blockIdx.x * n;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    constexpr int nwarps = kT / 32;
+    const Stats st = level_sum(f, n, s_buf);
+    if (t == 0 && n_changed)
+        n_changed[blockIdx.x] = st.n_nan;
+    const unsigned long long nUnchanged = n - st.n_nan;
+    if (nUnchanged == 0 || st.n_nan == 0)
+        return; // nothing to do (:1266-1268)
+    const double average = __ddiv_rn(st.sum, (double)nUnchanged);
+    if (t == 0)
+        s_dev = 0.;
+    for (size_t c0 = 0; c0 < n; c0 += kChunk) { // first guess, weights, sequential mean deviation (:1286-1302)
+        const int m = (int)(n - c0 < (size_t)kChunk ? n - c0 : (size_t)kChunk);
+        __syncthreads();
+        for (int i = t; i < m; i += kT) {
+            const float v = f[c0 + i];
+            s_buf[i] = v;
+            const size_t p = c0 + i;
+            const int x = (int)(p % nx), y = (int)(p / nx);
+            const bool interior = x >= 1 && x < nx - 1 && y >= 1 && y < ny - 1;
+            if (isnan(v)) {
+                w[p] = interior ? __fmul_rn(1.f, corrEff) : 1.f; // :1314-1318
+                f[p] = (float)average;
+            } else {
+                w[p] = interior ? __fmul_rn(0.f, corrEff) : 0.f;
+            }
+        }
+        __syncthreads();
+        if (t == 0)
+            s_dev = chunk_deviation(s_buf, m, average, s_dev);
+    }
+    __syncthreads();
+    const double crit = __dmul_rn((double)relaxCrit, __ddiv_rn(s_dev, (double)nUnchanged));
+    const float crtest = (float)__dmul_rn(crit, (double)corrEff); // :1332
+    const int dmax = nx + ny - 2;
+    auto slot = [&](int x, int y) { return ((x + y) & (NR - 1)) * lp + (by_y ? y : x); };
+    auto load_diag = [&](int d) {
+        if (d < 0 || d > dmax)
+            return;
+        const int xlo = d - (ny - 1) > 0 ? d - (ny - 1) : 0, xhi = d < nx - 1 ? d : nx - 1;
+        for (int x = xlo + t; x <= xhi; x += kT) {
+            const int y = d - x;
+            const size_t p = (size_t)y * nx + x;
+            rf[slot(x, y)] = f[p];
+            rw[slot(x, y)] = w[p];
+        }
+    };
+    // the diagonal that enters the ring comes through registers, fetched two steps before it is needed: a step must not wait
+    // for a global-memory round trip (kPF values per thread cover diagonals of up to kPF * 512 cells)
+    constexpr int kPF = 4;
+    float pf[2][kPF], pw[2][kPF];
+    auto fetch = [&](int d, float (&vf)[kPF], float (&vw)[kPF]) {
+        if (d < 0 || d > dmax)
+            return;
+        const int xlo = d - (ny - 1) > 0 ? d - (ny - 1) : 0, xhi = d < nx - 1 ? d : nx - 1;
+#pragma unroll
+        for (int k = 0; k < kPF; ++k) {
+            const int x = xlo + t + k * kT;
+            if (x <= xhi) {
+                const size_t p = (size_t)(d - x) * nx + x;
+                vf[k] = f[p];
+                vw[k] = w[p];
+            }
+        }
+    };
+    auto commit = [&](int d, const float (&vf)[kPF], const float (&vw)[kPF]) {
+        if (d < 0 || d > dmax)
+            return;
+        const int xlo = d - (ny - 1) > 0 ? d - (ny - 1) : 0, xhi = d < nx - 1 ? d : nx - 1;
+#pragma unroll
+        for (int k = 0; k < kPF; ++k) {
+            const int x = xlo + t + k * kT;
+            if (x <= xhi) {
+                rf[slot(x, d - x)] = vf[k];
+                rw[slot(x, d - x)] = vw[k];
+            }
+        }
+    };
+    auto store_diag = [&](int d) {
+        if (d < 0 || d > dmax)
+            return;
+        const int xlo = d - (ny - 1) > 0 ? d - (ny - 1) : 0, xhi = d < nx - 1 ? d : nx - 1;
+        for (int x = xlo + t; x <= xhi; x += kT)
+            f[(size_t)(d - x) * nx + x] = rf[slot(x, d - x)];
+    };
+    // one-sided relaxation of a border cell towards its inner neighbour (:1354-1363)
+    auto border = [&](int x, int y, int xi, int yi) {
+        const float a = rf[slot(x, y)];
+        rf[slot(x, y)] = __fadd_rn(a, __fmul_rn(__fsub_rn(rf[slot(xi, yi)], a), rw[slot(x, y)]));
+    };
+    unsigned long long loop = 0;
+    while (loop < maxLoop) {
+        // a block of sweeps: up to B, ending at the first sweep the reference tests (:1329-1330, size_t arithmetic)
+        int nb = 0;
+        bool test_last = false;
+        while (nb < B && loop + nb < maxLoop) {
+            const unsigned long long k = loop + nb;
+            ++nb;
+            if ((k < (maxLoop - 5ull)) && (k % 10ull == 0)) {
+                test_last = true;
+                break;
+            }
+        }
+        if (t == 0)
+            s_bad = 0;
+        int bad = 0;
+        load_diag(0);
+        load_diag(1);
+        fetch(2, pf[0], pw[0]);
+        fetch(3, pf[1], pw[1]);
+        __syncthreads();
+        const int tau_end = dmax + 2 * (nb - 1) + 4;
+        for (int tau = 0; tau <= tau_end; ++tau) {
+            if (tau & 1) { // diagonal tau + 2 enters the ring; diagonal tau + 4 starts its way from global memory
+                commit(tau + 2, pf[1], pw[1]);
+                fetch(tau + 4, pf[1], pw[1]);
+            } else {
+                commit(tau + 2, pf[0], pw[0]);
+                fetch(tau + 4, pf[0], pw[0]);
+            }
+            int base = 0;
+            for (int j = 0; j < nb; ++j) {
+                const int d = tau - 2 * j;
+                const int ylo = d - (nx - 2) > 1 ? d - (nx - 2) : 1;
+                const int yhi = d - 1 < ny - 2 ? d - 1 : ny - 2;
+                const int cnt = yhi >= ylo ? yhi - ylo + 1 : 0;
+                const int nchunk = (cnt + 31) >> 5;
+                int k = (warp - base % nwarps + nwarps) % nwarps;
+                for (; k < nchunk; k += nwarps) {
+                    const int y = ylo + 32 * k + lane;
+                    if (y <= yhi) {
+                        const int x = d - y;
+                        const int me = slot(x, y);
+                        const float c = rf[me];
+                        const float s4 = __fadd_rn(__fadd_rn(__fadd_rn(rf[slot(x + 1, y)], rf[slot(x - 1, y)]), rf[slot(x, y + 1)]),
+                                                   rf[slot(x, y - 1)]);
+                        const float e = (float)__dsub_rn(__dmul_rn((double)s4, 0.25), (double)c);
+                        const float ew = __fmul_rn(e, rw[me]);
+                        rf[me] = __fadd_rn(c, ew);
+                        if (test_last && j == nb - 1 && fabs((double)ew) > (double)crtest)
+                            bad = 1;
+                    }
+                }
+                base += nchunk;
+            }
+            // border cells of every sweep but the block's last, each right after the interior cell it reads
+            if (t < 6 * (nb - 1)) {
+                const int j = t / 6, kind = t - 6 * j;
+                const int d = tau - 2 * j;
+                if (kind == 0) { // right column: (nx-1, y) from (nx-2, y)
+                    const int y = d - (nx - 1);
+                    if (y >= 1 && y <= ny - 2)
+                        border(nx - 1, y, nx - 2, y);
+                } else if (kind == 1) { // bottom row: (x, ny-1) from (x, ny-2), x >= 1 (the right corner reads the right column)
+                    const int x = d - (ny - 1);
+                    if (x >= 1 && x <= nx - 1)
+                        border(x, ny - 1, x, ny - 2);
+                } else if (kind == 2) { // left column: (0, y) from (1, y), two steps behind its diagonal
+                    const int y = d - 2;
+                    if (y >= 1 && y <= ny - 2)
+                        border(0, y, 1, y);
+                } else if (kind == 3) { // top row: (x, 0) from (x, 1), x >= 1
+                    const int x = d - 2;
+                    if (x >= 1 && x <= nx - 1)
+                        border(x, 0, x, 1);
+                } else if (kind == 4) { // corner (0, 0) from the left column's (0, 1)
+                    if (d == 4)
+                        border(0, 0, 0, 1);
+                } else { // corner (0, ny-1) from the left column's (0, ny-2)
+                    if (d == ny + 1)
+                        border(0, ny - 1, 0, ny - 2);
+                }
+            }
+            store_diag(tau - 2 * (nb - 1) - 5);
+            __syncthreads();
+        }
+        for (int d = tau_end - 2 * (nb - 1) - 4; d <= dmax; ++d)
+            store_diag(d);
+        if (bad)
+            s_bad = 1;
+        __syncthreads();
+        loop += nb;
+        if (test_last && s_bad == 0)
+            return; // convergence (:1334-1352)
+        // the border pass of the block's last sweep, on global memory (:1354-1363)
+        const int nxm1 = nx - 1, nym1 = ny - 1;
+        for (int y = 1 + t; y < nym1; y += kT) {
+            const size_t r = (size_t)y * nx;
+            f[r] = __fadd_rn(f[r], __fmul_rn(__fsub_rn(f[r + 1], f[r]), w[r]));
+            f[r + nxm1] = __fadd_rn(f[r + nxm1], __fmul_rn(__fsub_rn(f[r + nxm1 - 1], f[r + nxm1]), w[r + nxm1]));
+        }
+        __syncthreads();
+        for (int x = t; x < nx; x += kT) {
+            const size_t top = (size_t)x, bot = (size_t)nym1 * nx + x;
+            f[top] = __fadd_rn(f[top], __fmul_rn(__fsub_rn(f[top + nx], f[top]), w[top]));
+            f[bot] = __fadd_rn(f[bot], __fmul_rn(__fsub_rn(f[bot - nx], f[bot]), w[bot]));
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------- creepfill2d
 // use_mean: mifi_creepfill2d_f (first guess = mean of the defined values, :1486-1507); else mifi_creepfillval2d_f (:1509-1525)
 __global__ void __launch_bounds__(kT) k_creepfill2d(float* __restrict__ field, signed char* __restrict__ wfield,
                                                     unsigned short* __restrict__ rfield, int nx, int ny, int use_mean, float defaultVal,
                                                     unsigned short repeat, signed char setWeight, unsigned long long* __restrict__ n_changed)
 {
-    __shared__ float s_buf[kChunk];
+    __shared__ __align__(16) float s_buf[kChunk];
     __shared__ unsigned long long s_changed;
     const size_t n = (size_t)nx * ny;
     float* f = field + blockIdx.x * n;
@@ -278,7 +526,29 @@ int launch_fill2d(float* d_field, size_t nx, size_t ny, size_t nz, float relaxCr
     FB_REQUIRE(nx >= 2 && ny >= 2 && nx < 2147483647u && ny < 2147483647u, "fill2d needs at least 2 x 2 points per level");
     float* d_w = nullptr;
     FB_CUDA_CHECK(cudaMallocAsync(&d_w, sizeof(float) * nx * ny * nz, st));
-    k_fill2d<<<(unsigned)nz, kT, 0, st>>>(d_field, d_w, (int)nx, (int)ny, relaxCrit, corrEff, (unsigned long long)maxLoop, d_nchanged);
+    // skewed (pipelined) sweeps when the diagonals in flight fit in shared memory: 32 diagonals (10 sweeps) or 16 (5 sweeps)
+    const int by_y = ny <= nx ? 1 : 0;
+    const int lp = (int)(by_y ? ny : nx) + 1;
+    const size_t smem32 = sizeof(float) * 2 * 32 * (size_t)lp, smem16 = smem32 / 2;
+    const size_t smem_max = 200 * 1024;
+    cudaError_t ea = cudaSuccess;
+    if (nx >= 3 && ny >= 3 && smem32 <= smem_max && !std::getenv("FIMEX_B200_FILL_SIMPLE")) {
+        ea = cudaFuncSetAttribute(k_fill2d_skewed<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
+        if (ea == cudaSuccess)
+            k_fill2d_skewed<32><<<(unsigned)nz, kT, smem32, st>>>(d_field, d_w, (int)nx, (int)ny, by_y, lp, relaxCrit, corrEff,
+                                                                 (unsigned long long)maxLoop, d_nchanged);
+    } else if (nx >= 3 && ny >= 3 && smem16 <= smem_max && !std::getenv("FIMEX_B200_FILL_SIMPLE")) {
+        ea = cudaFuncSetAttribute(k_fill2d_skewed<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
+        if (ea == cudaSuccess)
+            k_fill2d_skewed<16><<<(unsigned)nz, kT, smem16, st>>>(d_field, d_w, (int)nx, (int)ny, by_y, lp, relaxCrit, corrEff,
+                                                                 (unsigned long long)maxLoop, d_nchanged);
+    } else {
+        k_fill2d<<<(unsigned)nz, kT, 0, st>>>(d_field, d_w, (int)nx, (int)ny, relaxCrit, corrEff, (unsigned long long)maxLoop, d_nchanged);
+    }
+    if (ea != cudaSuccess) {
+        cudaFreeAsync(d_w, st);
+        FB_CUDA_CHECK(ea);
+    }
     count_launch();
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(d_w, st);
