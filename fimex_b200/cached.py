@@ -136,6 +136,13 @@ class CachedInterpolationInterface:
         return out.reshape(-1)[:n].reshape(nz, self.getOutY(), self.getOutX())
 
 
+    def addPreprocess(self, procString: str):
+        """CDMInterpolator::addPreprocess with the --interpolate.preprocess option string, e.g. "fill2d(0.01,1.6,100)" """
+        check(load().fb200_interp_add_preprocess(self._h, procString.encode()), "addPreprocess")
+
+    def addPostprocess(self, procString: str):
+        check(load().fb200_interp_add_postprocess(self._h, procString.encode()), "addPostprocess")
+
     # -- the whole slice body of CDMInterpolator::getDataSlice in one call ---------------------------
     def getDataSlice(self, inData, badValue, outType=None, stream=None, out=None):
         """data2InterpolationArray -> interpolateValues -> interpolationArray2Data (CDMInterpolator.cc:250-258, 284-285):

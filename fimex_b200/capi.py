@@ -162,6 +162,8 @@ def _declare(lib):
         "fb200_vector_destroy": (None, [_vp]),
         "fb200_interp_interpolate_vector": (i, [_vp, _vp, _vp, _vp, sz, _vp, _vp, P(sz)]),
         "fb200_interp_interpolate_vector_device": (i, [_vp, _vp, _vp, _vp, sz, _vp, _vp, P(sz), _vp]),
+        "fb200_interp_add_preprocess": (i, [_vp, C.c_char_p]),
+        "fb200_interp_add_postprocess": (i, [_vp, C.c_char_p]),
         "fb200_interp_get_data_slice": (i, [_vp, i, _vp, sz, C.c_double, i, _vp, P(sz)]),
         "fb200_interp_get_data_slice_device": (i, [_vp, i, _vp, sz, C.c_double, i, _vp, P(sz), _vp]),
         "fb200_interp_get_vector_slice": (i, [_vp, _vp, i, _vp, _vp, sz, C.c_double, C.c_double, i, _vp, _vp, P(sz)]),

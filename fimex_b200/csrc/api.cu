@@ -14,6 +14,7 @@
 #include <limits>
 #include <memory>
 #include <mutex>
+#include <sstream>
 #include <string>
 #include <vector>
 
@@ -218,6 +219,15 @@ struct fb200_interp {
     bool reduced = false;
     long long xMin = 0, yMin = 0;
     long long coordnn_ties = 0;
+    // 2-D pre/post-processes of getDataSlice (CDMInterpolator::addPreprocess / addPostprocess, src/CDMInterpolator.cc:289-297)
+    struct Process {
+        int kind = 0; // 0 fill2d, 1 creepfill2d, 2 creepfillval2d
+        float relaxCrit = 0.f, corrEff = 0.f, defVal = 0.f;
+        size_t maxLoop = 0;
+        unsigned short repeat = 0;
+        signed char weight = 0;
+    };
+    std::vector<Process> preprocesses, postprocesses;
 
     ~fb200_interp()
     {
@@ -427,6 +437,21 @@ int run_gather_vector(const fb200_interp* h, const fb200_vector* v, const float*
     }
 }
 
+// processArray_ (src/CDMInterpolator.cc:136-159): every process on every level of a float slab, in place
+int process_array(const std::vector<fb200_interp::Process>& procs, float* d_array, size_t nx, size_t ny, size_t nz, cudaStream_t st)
+{
+    for (const fb200_interp::Process& p : procs) {
+        int rc;
+        if (p.kind == 0)
+            rc = launch_fill2d(d_array, nx, ny, nz, p.relaxCrit, p.corrEff, p.maxLoop, nullptr, st);
+        else
+            rc = launch_creepfill2d(d_array, nx, ny, nz, p.kind == 1, p.defVal, p.repeat, p.weight, nullptr, st);
+        if (rc != FB_OK)
+            return rc;
+    }
+    return FB_OK;
+}
+
 // One slice on the device: nfields = 1 (scalar) or 2 (u/v with optional rotation).  With io.typed this is
 // data2InterpolationArray -> interpolateValues [-> reprojectValues] -> interpolationArray2Data; the staged gathers do the
 // first and last step inside the gather kernel, everything else goes through a float slab and a conversion pass.
@@ -439,6 +464,7 @@ int run_slice_device(const fb200_interp* h, const fb200_vector* v, int nfields, 
     const bool staged_scalar = nfields == 1 && !h->forward && (h->method == FB_BICUBIC ? h->bic_tiles.ready() : h->tiles.ready());
     const bool staged_vector = nfields == 2 && !h->forward && (h->method == FB_BICUBIC ? h->bic_tiles.ready() : h->tiles.ready());
     const bool kernel_fills = staged_scalar || staged_vector;
+    const bool pre = io.typed && !h->preprocesses.empty(), post = io.typed && !h->postprocesses.empty();
     Scratch tmp(st);
     SliceConv sc;
     const float* fin[2] = {nullptr, nullptr};
@@ -446,7 +472,13 @@ int run_slice_device(const fb200_interp* h, const fb200_vector* v, int nfields, 
         const float bad = (float)io.bad[f]; // mifi_bad2nanf takes a float (interpolation.c:1775)
         const bool has_bad = io.typed && !std::isnan(bad);
         sc.bad_in[f] = std::numeric_limits<float>::quiet_NaN();
-        if (!io.typed || (io.in_type == FB_T_FLOAT && (!has_bad || kernel_fills))) {
+        if (pre) { // the preprocesses work in place on the float + NaN array (:254-256): a private copy of the input
+            float* conv = nullptr;
+            if (tmp.get(&conv, in_n) != FB_OK || launch_as_float(io.in_type, d_in[f], (long long)in_n, has_bad, bad, conv, st) != FB_OK ||
+                process_array(h->preprocesses, conv, h->inX, h->inY, nz, st) != FB_OK)
+                return FB_ERROR;
+            fin[f] = conv;
+        } else if (!io.typed || (io.in_type == FB_T_FLOAT && (!has_bad || kernel_fills))) {
             fin[f] = static_cast<const float*>(d_in[f]);
             if (has_bad) {
                 sc.fill_in = true;
@@ -464,7 +496,7 @@ int run_slice_device(const fb200_interp* h, const fb200_vector* v, int nfields, 
             return run_gather(h, fin[0], nz, d_out[0], sc, st);
         return run_gather_vector(h, v, fin[0], fin[1], nz, static_cast<float*>(d_out[0]), static_cast<float*>(d_out[1]), sc, st);
     }
-    if (staged_scalar && staged_store_supports(io.out_type)) { // the fused form: one pass over the output
+    if (!post && staged_scalar && staged_store_supports(io.out_type)) { // the fused form: one pass over the output
         sc.convert_out = true;
         sc.out_type = io.out_type;
         sc.fill_out = io.bad[0];
@@ -480,9 +512,12 @@ int run_slice_device(const fb200_interp* h, const fb200_vector* v, int nfields, 
     const int rc = nfields == 1 ? run_gather(h, fin[0], nz, fout[0], sc, st) : run_gather_vector(h, v, fin[0], fin[1], nz, fout[0], fout[1], sc, st);
     if (rc != FB_OK)
         return rc;
-    for (int f = 0; f < nfields; ++f)
+    for (int f = 0; f < nfields; ++f) {
+        if (post && process_array(h->postprocesses, fout[f], h->outX, h->outY, nz, st) != FB_OK) // :284
+            return FB_ERROR;
         if (launch_from_float(fout[f], (long long)out_n, io.out_type, io.bad[f], d_out[f], st) != FB_OK)
             return FB_ERROR;
+    }
     return FB_OK;
 }
 
@@ -1386,6 +1421,102 @@ int fb200_interp_interpolate_vector(const fb200_interp* h, const fb200_vector* v
     const float* in[2] = {uIn, vIn};
     float* out[2] = {uOut, vOut};
     return run_host(h, (v && v->d_cs) ? v : nullptr, 2, in, out, nz);
+}
+
+// ---------------------------------------------------------------------------------------- interpolate.preprocess / postprocess
+} // extern "C"
+namespace {
+// string2type<T> of the reference (include/fimex/Utils.h:60-67): stream extraction; here a failed extraction is an error
+template <class T>
+bool parse_token(const std::string& s, T* out)
+{
+    std::istringstream in(s);
+    in >> *out;
+    return !in.fail();
+}
+
+// parseProcess, src/binSrc/fimex.cc:644-671
+int parse_process(const char* procString, fb200_interp::Process* p)
+{
+    FB_REQUIRE(procString != nullptr, "null process string");
+    std::string s(procString);
+    size_t b = s.find_first_not_of(" \t\n\r");
+    s = b == std::string::npos ? std::string() : s.substr(b);
+    auto args_of = [&](const char* name, std::string* args) {
+        const std::string head = std::string(name) + "(";
+        if (s.compare(0, head.size(), head) != 0)
+            return false;
+        const size_t close = s.rfind(')');
+        if (close == std::string::npos || close < head.size())
+            return false;
+        *args = s.substr(head.size(), close - head.size());
+        return true;
+    };
+    auto split = [](const std::string& a) {
+        std::vector<std::string> out;
+        size_t start = 0;
+        while (true) {
+            const size_t c = a.find(',', start);
+            out.push_back(a.substr(start, c == std::string::npos ? std::string::npos : c - start));
+            if (c == std::string::npos)
+                break;
+            start = c + 1;
+        }
+        return out;
+    };
+    std::string args;
+    if (args_of("fill2d", &args)) {
+        const std::vector<std::string> v = split(args);
+        double critx = 0, cor = 0;
+        size_t maxLoop = 0;
+        FB_REQUIRE(v.size() == 3 && parse_token(v[0], &critx) && parse_token(v[1], &cor) && parse_token(v[2], &maxLoop),
+                   "undefined interpolate process: " + s + " (fill2d(critx,cor,maxLoop))");
+        p->kind = 0;
+        p->relaxCrit = (float)critx;
+        p->corrEff = (float)cor;
+        p->maxLoop = maxLoop;
+        return FB_OK;
+    }
+    if (args_of("creepfill2d", &args)) {
+        const std::vector<std::string> v = split(args);
+        FB_REQUIRE(v.size() == 2 || v.size() == 3, "creepfill requires two or three arguments, got " + args);
+        unsigned short repeat = 0;
+        char weight = 0; // string2type<char> extracts ONE CHARACTER: "2" is the weight 50 ('2'), exactly as in the reference (:657)
+        FB_REQUIRE(parse_token(v[0], &repeat) && parse_token(v[1], &weight), "undefined interpolate process: " + s);
+        p->kind = 1;
+        p->repeat = repeat;
+        p->weight = (signed char)weight;
+        if (v.size() == 3) {
+            float defVal = 0.f;
+            FB_REQUIRE(parse_token(v[2], &defVal), "undefined interpolate process: " + s);
+            p->kind = 2;
+            p->defVal = defVal;
+        }
+        return FB_OK;
+    }
+    FB_REQUIRE(false, "undefined interpolate process: " + s);
+}
+} // namespace
+extern "C" {
+
+int fb200_interp_add_preprocess(fb200_interp* h, const char* procString)
+{
+    FB_REQUIRE(h != nullptr, "null interpolation handle");
+    fb200_interp::Process p;
+    if (parse_process(procString, &p) != FB_OK)
+        return MIFI_ERROR;
+    h->preprocesses.push_back(p);
+    return MIFI_OK;
+}
+
+int fb200_interp_add_postprocess(fb200_interp* h, const char* procString)
+{
+    FB_REQUIRE(h != nullptr, "null interpolation handle");
+    fb200_interp::Process p;
+    if (parse_process(procString, &p) != FB_OK)
+        return MIFI_ERROR;
+    h->postprocesses.push_back(p);
+    return MIFI_OK;
 }
 
 // ---------------------------------------------------------------------------------------- getDataSlice in one call

@@ -243,8 +243,17 @@ int fb200_interp_interpolate_vector_device(const fb200_interp* handle, const fb2
  * nearest neighbour / coord_nn, bicubic) both adapter passes run INSIDE the gather kernel: the fill -> NaN compare is
  * applied once per staged source value and the output is written once, in the variable's type (a `short` variable
  * halves the bytes stored).  Other methods / 64-bit integer outputs take a float slab and one conversion pass.
- * outData: outX*outY*inZ elements of outType.  The pre/post-processes (fill2d, creepfill2d) are not part of this call.
+ * outData: outX*outY*inZ elements of outType.  Pre/post-processes added with fb200_interp_add_pre/postprocess run inside the call.
  * ---------------------------------------------------------------------------------------------- */
+/* CDMInterpolator::addPreprocess / addPostprocess (src/CDMInterpolator.cc:289-297) with the option strings of
+ * --interpolate.preprocess / --interpolate.postprocess as parseProcess reads them (src/binSrc/fimex.cc:644-671):
+ * "fill2d(critx,cor,maxLoop)", "creepfill2d(repeat,weight)" or "creepfill2d(repeat,weight,defaultValue)" (weight is ONE
+ * CHARACTER and its code is the weight, as in the reference: "2" means 50).  They run on the device inside the slice calls
+ * below (before / after the gather, :256, :284) and switch the fused adapters to the three-pass form.  Part of construction:
+ * call before the handle is shared between threads. */
+int fb200_interp_add_preprocess(fb200_interp* handle, const char* procString);
+int fb200_interp_add_postprocess(fb200_interp* handle, const char* procString);
+
 int fb200_interp_get_data_slice(const fb200_interp* handle, int inType, const void* inData, size_t size, double badValue, int outType,
                                 void* outData, size_t* newSize);
 int fb200_interp_get_data_slice_device(const fb200_interp* handle, int inType, const void* d_inData, size_t size, double badValue,

@@ -893,3 +893,31 @@ def test_concurrent_calls_on_one_handle(oracle):
         assert not errors, errors
         for i in range(len(fields)):
             assert_bit_equal(got[i], want[i], f"thread {i}, method {method}")
+
+
+def test_get_data_slice_with_pre_and_postprocess(oracle):
+    """--interpolate.preprocess / postprocess inside the slice call (CDMInterpolator.cc:254-256, 284; parseProcess,
+    src/binSrc/fimex.cc:644-671 -- including its one-character weight: "2" is the weight 50)"""
+    inX, inY, inZ, outX, outY = 60, 50, 5, 120, 70
+    px, py = _smooth_positions(inX, inY, outX, outY, 17.0, 2.2, 3)  # zoom 2.2: part of the target hangs over the source grid
+    rng = np.random.default_rng(2)
+    fill = -32767.0
+    data = _typed_field(rng, (inZ, inY, inX), np.int16, fill)
+    data[:, 10:20, 15:30] = -32767
+    ci = fb.CachedInterpolation("x", "y", Method.BILINEAR, px, py, inX, inY, outX, outY)
+    ci.addPreprocess(" fill2d(0.01,1.6,100)")
+    ci.addPreprocess("creepfill2d(3,2)")
+    ci.addPostprocess("creepfill2d(2,1,-5.5)")
+    got = ci.getDataSlice(data, fill)
+    a = oracle.as_float(data, fill)
+    a, _ = oracle.fill2d(a, np.float32(0.01), np.float32(1.6), 100)
+    a, _ = oracle.creepfill2d(a, 3, ord("2"))
+    o = oracle.cached_interpolate(1, px, py, inX, inY, outX, outY, a)
+    assert np.isnan(o).any()  # outside the source grid: filled by the postprocess
+    o, _ = oracle.creepfill2d(o.reshape(inZ, outY, outX), 2, ord("1"), -5.5)
+    want = oracle.from_float(o, fill, np.int16).reshape(got.shape)
+    assert np.array_equal(got, want)
+    assert not (got == -32767).any()
+    for bad in ("fill2d(0.01,1.6)", "creepfill2d(1)", "smooth(3)", "fill2d(a,b,c)"):
+        with pytest.raises(fb.FimexB200Error):
+            ci.addPreprocess(bad)
