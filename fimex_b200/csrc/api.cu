@@ -219,7 +219,7 @@ struct fb200_interp {
     bool reduced = false;
     long long xMin = 0, yMin = 0;
     long long coordnn_ties = 0;
-    // 2-D pre/post-processes of getDataSlice (CDMInterpolator::addPreprocess / addPostprocess, src/CDMInterpolator.cc:289-297)
+    // 2-D pre/post-processes of getDataSlice (CDMInterpolator::addPreprocess / addPostprocess, src/CDMInterpolator.cc:1886-1896)
     struct Process {
         int kind = 0; // 0 fill2d, 1 creepfill2d, 2 creepfillval2d
         float relaxCrit = 0.f, corrEff = 0.f, defVal = 0.f;

@@ -245,7 +245,7 @@ int fb200_interp_interpolate_vector_device(const fb200_interp* handle, const fb2
  * halves the bytes stored).  Other methods / 64-bit integer outputs take a float slab and one conversion pass.
  * outData: outX*outY*inZ elements of outType.  Pre/post-processes added with fb200_interp_add_pre/postprocess run inside the call.
  * ---------------------------------------------------------------------------------------------- */
-/* CDMInterpolator::addPreprocess / addPostprocess (src/CDMInterpolator.cc:289-297) with the option strings of
+/* CDMInterpolator::addPreprocess / addPostprocess (src/CDMInterpolator.cc:1886-1896) with the option strings of
  * --interpolate.preprocess / --interpolate.postprocess as parseProcess reads them (src/binSrc/fimex.cc:644-671):
  * "fill2d(critx,cor,maxLoop)", "creepfill2d(repeat,weight)" or "creepfill2d(repeat,weight,defaultValue)" (weight is ONE
  * CHARACTER and its code is the weight, as in the reference: "2" means 50).  They run on the device inside the slice calls
