@@ -42,6 +42,10 @@ constexpr int kTilePts = 1024;
 // distinct taps, i.e. span fewer than ~30 source cells.
 //   bilinear: 64 x 16, lane = x, thread t owns (t & 63, (t >> 6) + 4k): a row is written by two neighbouring warps
 //   nearest neighbour: 128 x 8, thread t owns (4 (t & 31) + k, t >> 5): one 128-bit store per thread and level
+#ifndef FB_STAGE_BUFFERS
+#define FB_STAGE_BUFFERS 2 // staging buffers of the cp.async pipeline (experiments: -DFB_STAGE_BUFFERS=3)
+#endif
+constexpr int kBuffers = FB_STAGE_BUFFERS;
 #ifndef FB_NN_CTAS
 #define FB_NN_CTAS 3 // resident CTAs per SM the nearest-neighbour kernel is compiled for (experiments: -DFB_NN_CTAS=4)
 #endif
@@ -194,9 +198,10 @@ __device__ __forceinline__ void cp_async_commit()
 {
     asm volatile("cp.async.commit_group;\n" ::: "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all()
+template <int N>
+__device__ __forceinline__ void cp_async_wait_pending()
 {
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
 // Out: StorePlain (interpolateValues' own float output) or StoreAs<T> (interpolationArray2Data fused into the store:
@@ -211,7 +216,7 @@ __global__ void __launch_bounds__(kThreads, NF == 1 ? (NN ? FB_NN_CTAS : 3) : 2)
                              typename Out::type* __restrict__ out1, const double2* __restrict__ cs, Out conv, int fill_in, float bad0,
                              float bad1, int vec_ok)
 {
-    extern __shared__ __align__(16) float s_dyn[]; // [2 buffers][NF fields][kStageFloats]: batch b+1 lands while batch b is consumed
+    extern __shared__ __align__(16) float s_dyn[]; // [kBuffers][NF fields][kStageFloats]: later batches land while batch b is consumed
     auto stage = [&](int buf, int f) { return s_dyn + (buf * NF + f) * kStageFloats; };
     const int tile = blockIdx.x;
     const int t = threadIdx.x;
@@ -320,18 +325,25 @@ __global__ void __launch_bounds__(kThreads, NF == 1 ? (NN ? FB_NN_CTAS : 3) : 2)
         }
     };
 
-    if (z0 < z1)
-        issue(0, z0, (int)((z1 - z0) < zb ? (z1 - z0) : zb));
+    // kBuffers-deep pipeline: batches b+1 .. b+kBuffers-1 are in flight while batch b is consumed.  Every iteration commits
+    // exactly one cp.async group (possibly empty), so "all but the newest kBuffers-2 groups have landed" is the wait condition.
+    auto issue_or_skip = [&](int buf, long long z) {
+        if (z < z1)
+            issue(buf, z, (int)((z1 - z) < zb ? (z1 - z) : zb));
+        else
+            cp_async_commit();
+    };
+#pragma unroll
+    for (int b = 0; b < kBuffers - 1; ++b)
+        issue_or_skip(b, z0 + (long long)b * zb);
     int buf = 0;
-    for (long long z = z0; z < z1; z += zb, buf ^= 1) {
+    for (long long z = z0; z < z1; z += zb, buf = (buf + 1 == kBuffers ? 0 : buf + 1)) {
         const int nb = (int)((z1 - z) < zb ? (z1 - z) : zb);
-        cp_async_wait_all();
+        cp_async_wait_pending<kBuffers - 2>();
         if (fill_in)
             patch(buf, nb);
-        __syncthreads(); // batch z has landed for every thread, and every thread is done reading the other buffer
-        const long long zn = z + zb;
-        if (zn < z1)
-            issue(buf ^ 1, zn, (int)((z1 - zn) < zb ? (z1 - zn) : zb));
+        __syncthreads(); // batch z has landed for every thread, and every thread is done reading the buffer refilled next
+        issue_or_skip(buf == 0 ? kBuffers - 1 : buf - 1, z + (long long)(kBuffers - 1) * zb);
         if (nvalid == 0)
             continue;
         const float* lvl = stage(buf, 0);
@@ -492,7 +504,7 @@ void tile_table_free(TileTable* tt)
 }
 
 namespace {
-constexpr size_t kStageBytes = 2 * kStageFloats * sizeof(float); // per field: two buffers
+constexpr size_t kStageBytes = kBuffers * kStageFloats * sizeof(float); // per field
 
 template <bool NN, class Out>
 void launch_staged_as(dim3 grid, const GatherGeom& g, const TileTable& tt, const float* d_in, void* d_out, Out conv, const SliceConv& sc,
