@@ -521,6 +521,57 @@ int run_slice_device(const fb200_interp* h, const fb200_vector* v, int nfields, 
     return FB_OK;
 }
 
+// Per host thread and device: the three streams of the host-buffer pipeline and its events, created once.  A call owns them
+// for its duration (a thread runs one call at a time), so concurrent calls from several threads never share a stream.
+struct HostPipe {
+    int device = -1;
+    cudaStream_t up = nullptr, run = nullptr, down = nullptr;
+    cudaEvent_t ev[3][3] = {};
+    cudaEvent_t ready = nullptr;
+    void destroy()
+    {
+        if (device < 0)
+            return;
+        if (cudaSetDevice(device) == cudaSuccess) { // fails harmlessly when the runtime is already shutting down
+            for (auto& row : ev)
+                for (cudaEvent_t& e : row)
+                    if (e)
+                        cudaEventDestroy(e);
+            if (ready)
+                cudaEventDestroy(ready);
+            if (up)
+                cudaStreamDestroy(up);
+            if (run)
+                cudaStreamDestroy(run);
+            if (down)
+                cudaStreamDestroy(down);
+        }
+        *this = HostPipe();
+    }
+    ~HostPipe() { destroy(); }
+};
+
+HostPipe* host_pipe(int device)
+{
+    static thread_local HostPipe pipe;
+    if (pipe.device == device)
+        return &pipe;
+    pipe.destroy();
+    bool ok = cudaStreamCreateWithFlags(&pipe.up, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&pipe.run, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&pipe.down, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&pipe.ready, cudaEventDisableTiming) == cudaSuccess;
+    for (auto& row : pipe.ev)
+        for (cudaEvent_t& e : row)
+            ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+    pipe.device = device; // so that destroy() releases whatever was created
+    if (!ok) {
+        pipe.destroy();
+        return nullptr;
+    }
+    return &pipe;
+}
+
 // Host-buffer execution: levels are cut into chunks that rotate through three (stream, scratch) slots, so that
 // the H2D copy of chunk k+1, the kernel of chunk k and the D2H copy of chunk k-1 overlap.  `nfields` is 1
 // (scalar) or 2 (u/v).  Every call owns its streams and scratch => re-entrant on a shared handle.
@@ -553,26 +604,27 @@ int run_slice_host(const fb200_interp* h, const fb200_vector* v, int nfields, co
         void* d_out[2] = {nullptr, nullptr};
         cudaEvent_t uploaded = nullptr, computed = nullptr, downloaded = nullptr;
     } slots[3];
-    cudaStream_t s_up = nullptr, s_run = nullptr, s_down = nullptr;
+    HostPipe* pipe = host_pipe(h->device);
+    FB_REQUIRE(pipe != nullptr, std::string("cannot create the copy / compute streams: ") + cudaGetErrorString(cudaGetLastError()));
+    const cudaStream_t s_up = pipe->up, s_run = pipe->run, s_down = pipe->down;
+    for (int s = 0; s < nslots; ++s) {
+        slots[s].uploaded = pipe->ev[s][0];
+        slots[s].computed = pipe->ev[s][1];
+        slots[s].downloaded = pipe->ev[s][2];
+    }
     int rc = FB_OK;
     const bool trace = std::getenv("FIMEX_B200_TRACE") != nullptr;
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t0 = now(), t1 = 0, t2 = 0, t3 = 0;
     auto body = [&]() -> int {
-        FB_CUDA_CHECK(cudaStreamCreateWithFlags(&s_up, cudaStreamNonBlocking));
-        FB_CUDA_CHECK(cudaStreamCreateWithFlags(&s_run, cudaStreamNonBlocking));
-        FB_CUDA_CHECK(cudaStreamCreateWithFlags(&s_down, cudaStreamNonBlocking));
         for (int s = 0; s < nslots; ++s) {
             for (int f = 0; f < nfields; ++f) {
                 FB_CUDA_CHECK(cudaMallocAsync(&slots[s].d_in[f], in_elem * ((zc * in_level) > 0 ? zc * in_level : 1), s_run));
                 FB_CUDA_CHECK(cudaMallocAsync(&slots[s].d_out[f], out_elem * zc * out_level, s_run));
             }
-            FB_CUDA_CHECK(cudaEventCreateWithFlags(&slots[s].uploaded, cudaEventDisableTiming));
-            FB_CUDA_CHECK(cudaEventCreateWithFlags(&slots[s].computed, cudaEventDisableTiming));
-            FB_CUDA_CHECK(cudaEventCreateWithFlags(&slots[s].downloaded, cudaEventDisableTiming));
         }
         // the buffers were allocated in s_run's order: the copy streams must not touch them earlier
-        cudaEvent_t& ready = slots[0].computed;
+        cudaEvent_t ready = pipe->ready;
         FB_CUDA_CHECK(cudaEventRecord(ready, s_run));
         FB_CUDA_CHECK(cudaStreamWaitEvent(s_up, ready, 0));
         FB_CUDA_CHECK(cudaStreamWaitEvent(s_down, ready, 0));
@@ -602,41 +654,25 @@ int run_slice_host(const fb200_interp* h, const fb200_vector* v, int nfields, co
             FB_CUDA_CHECK(cudaEventRecord(sl.downloaded, s_down));
         }
         t2 = now();
-        FB_CUDA_CHECK(cudaStreamSynchronize(s_down));
-        FB_CUDA_CHECK(cudaStreamSynchronize(s_run));
-        FB_CUDA_CHECK(cudaStreamSynchronize(s_up));
+        FB_CUDA_CHECK(cudaStreamSynchronize(s_down)); // every download waited for its kernel, every kernel for its upload
         t3 = now();
         return FB_OK;
     };
     rc = body();
     if (rc != FB_OK) { // drain whatever was enqueued before the buffers go away
-        if (s_up)
-            cudaStreamSynchronize(s_up);
-        if (s_down)
-            cudaStreamSynchronize(s_down);
+        cudaStreamSynchronize(s_up);
+        cudaStreamSynchronize(s_run);
+        cudaStreamSynchronize(s_down);
     }
+    // all work that touches the buffers is complete: hand them back in s_run's order (no further synchronisation needed)
     for (int s = 0; s < nslots; ++s) {
         for (int f = 0; f < nfields; ++f) {
-            if (slots[s].d_in[f] && s_run)
+            if (slots[s].d_in[f])
                 cudaFreeAsync(slots[s].d_in[f], s_run);
-            if (slots[s].d_out[f] && s_run)
+            if (slots[s].d_out[f])
                 cudaFreeAsync(slots[s].d_out[f], s_run);
         }
-        if (slots[s].uploaded)
-            cudaEventDestroy(slots[s].uploaded);
-        if (slots[s].computed)
-            cudaEventDestroy(slots[s].computed);
-        if (slots[s].downloaded)
-            cudaEventDestroy(slots[s].downloaded);
     }
-    if (s_run) {
-        cudaStreamSynchronize(s_run);
-        cudaStreamDestroy(s_run);
-    }
-    if (s_up)
-        cudaStreamDestroy(s_up);
-    if (s_down)
-        cudaStreamDestroy(s_down);
     if (trace)
         fprintf(stderr, "[fb200 trace] host slice: setup %.3f ms, enqueue %.3f ms, wait %.3f ms, cleanup %.3f ms\n", t1 - t0, t2 - t1, t3 - t2,
                 now() - t3);
