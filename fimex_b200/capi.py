@@ -130,6 +130,7 @@ def _declare(lib):
         "fb200_kernel_launches": (C.c_ulonglong, []),
         "fb200_host_alloc": (_vp, [sz]),
         "fb200_host_free": (None, [_vp]),
+        "fb200_host_trim": (None, []),
         "fb200_cached_interpolation_create": (i, [i, _vp, _vp, sz, sz, sz, sz, P(_vp)]),
         "fb200_cached_interpolation_create_device": (i, [i, _vp, _vp, sz, sz, sz, sz, P(_vp)]),
         "fb200_cached_interpolation_create_from_projection": (i, [i, C.c_char_p, _vp, _vp, sz, sz, i, i, C.c_char_p, _vp, _vp, sz, sz, i,

@@ -12,6 +12,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <map>
+#include <unordered_map>
+#include <iterator>
 #include <memory>
 #include <mutex>
 #include <sstream>
@@ -908,21 +911,107 @@ unsigned long long fb200_kernel_launches(void)
 {
     return launches();
 }
+} // extern "C"
+namespace {
+// Page-locked host buffers with a size-keyed free list.  Page-locking costs about as much as copying the buffer, so the
+// buffers a host allocates per slice (interpolateValues returns a NEW array per call, src/CachedInterpolation.cc:123) are
+// recycled instead of being unpinned: up to FIMEX_B200_PINNED_CACHE_MB (default 8192) stay cached.
+struct PinnedCache {
+    std::mutex mu;
+    std::multimap<size_t, void*> free_blocks;      // capacity -> block
+    std::unordered_map<void*, size_t> capacity_of; // every live block, cached or handed out
+    size_t cached_bytes = 0;
+    size_t limit()
+    {
+        if (const char* env = std::getenv("FIMEX_B200_PINNED_CACHE_MB"))
+            return (size_t)std::atoll(env) << 20;
+        return (size_t)8192 << 20;
+    }
+    void* get(size_t bytes)
+    {
+        const size_t want = ((bytes ? bytes : 1) + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1); // 2 MB granules
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            auto it = free_blocks.lower_bound(want);
+            if (it != free_blocks.end() && it->first <= want + want / 4) { // do not burn a much larger block
+                void* p = it->second;
+                cached_bytes -= it->first;
+                free_blocks.erase(it);
+                return p;
+            }
+        }
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, want, cudaHostAllocPortable) != cudaSuccess) {
+            trim(0); // make room and retry once
+            if (cudaHostAlloc(&p, want, cudaHostAllocPortable) != cudaSuccess)
+                return nullptr;
+        }
+        std::lock_guard<std::mutex> lock(mu);
+        capacity_of[p] = want;
+        return p;
+    }
+    void put(void* p)
+    {
+        size_t cap = 0;
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            auto it = capacity_of.find(p);
+            if (it == capacity_of.end()) { // not ours (or already released): plain free
+                cudaFreeHost(p);
+                return;
+            }
+            cap = it->second;
+            if (cached_bytes + cap <= limit()) {
+                free_blocks.emplace(cap, p);
+                cached_bytes += cap;
+                return;
+            }
+            capacity_of.erase(it);
+        }
+        cudaFreeHost(p);
+    }
+    void trim(size_t keep_bytes)
+    {
+        std::vector<void*> victims;
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            while (cached_bytes > keep_bytes && !free_blocks.empty()) {
+                auto it = std::prev(free_blocks.end());
+                cached_bytes -= it->first;
+                capacity_of.erase(it->second);
+                victims.push_back(it->second);
+                free_blocks.erase(it);
+            }
+        }
+        for (void* p : victims)
+            cudaFreeHost(p);
+    }
+};
+PinnedCache& pinned_cache()
+{
+    static PinnedCache* c = new PinnedCache(); // leaked on purpose: no CUDA calls during static destruction
+    return *c;
+}
+} // namespace
+extern "C" {
+
 void* fb200_host_alloc(size_t bytes)
 {
-    void* p = nullptr;
     if (use_device(default_device()) != FB_OK)
         return nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+    void* p = pinned_cache().get(bytes);
+    if (!p)
         set_error("cudaHostAlloc failed");
-        return nullptr;
-    }
     return p;
 }
 void fb200_host_free(void* p)
 {
     if (p)
-        cudaFreeHost(p);
+        pinned_cache().put(p);
+}
+void fb200_host_trim(void)
+{
+    pinned_cache().trim(0);
 }
 
 // ---------------------------------------------------------------------------------------- CachedInterpolation

@@ -50,7 +50,11 @@ public:
     virtual shared_float_array interpolateValues(shared_float_array inData, size_t size, size_t& newSize) const
     {
         newSize = fb200_interp_new_size(handle_, size);
-        shared_float_array out(new float[newSize ? newSize : 1]);
+        // page-locked and recycled by the library (fb200_host_alloc): the download runs at the full PCIe rate
+        float* raw = static_cast<float*>(fb200_host_alloc(sizeof(float) * (newSize ? newSize : 1)));
+        if (!raw)
+            throw CDMException(std::string("error during interpolation: ") + fb200_last_error());
+        shared_float_array out(raw, fb200_host_free);
         size_t n = 0;
         if (fb200_interp_interpolate_values(handle_, inData.get(), size, out.get(), &n) != MIFI_OK)
             throw CDMException(std::string("error during interpolation: ") + fb200_last_error());

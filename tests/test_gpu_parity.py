@@ -921,3 +921,25 @@ def test_get_data_slice_with_pre_and_postprocess(oracle):
     for bad in ("fill2d(0.01,1.6)", "creepfill2d(1)", "smooth(3)", "fill2d(a,b,c)"):
         with pytest.raises(fb.FimexB200Error):
             ci.addPreprocess(bad)
+
+
+def test_pinned_host_buffers_are_recycled():
+    """fb200_host_alloc / fb200_host_free: freed page-locked buffers are handed out again (locking pages costs about as much
+    as copying them; the reference allocates a new output array per interpolateValues call)"""
+    import ctypes as C
+    lib = fb.load()
+    a = lib.fb200_host_alloc(50 << 20)
+    assert a
+    C.memset(a, 1, 50 << 20)
+    lib.fb200_host_free(a)
+    b = lib.fb200_host_alloc(49 << 20)  # same 2 MB size class or slightly smaller: the cached block comes back
+    assert b == a
+    c = lib.fb200_host_alloc(50 << 20)  # a second one while the first is in use: a different block
+    assert c and c != b
+    lib.fb200_host_free(b)
+    lib.fb200_host_free(c)
+    lib.fb200_host_trim()
+    d = lib.fb200_host_alloc(1)
+    assert d
+    lib.fb200_host_free(d)
+    lib.fb200_host_trim()
