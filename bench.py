@@ -193,6 +193,31 @@ def main_reference(args):
     return 0
 
 
+def bind_host_memory_to_gpu_node(local_rank):
+    """NUMA placement of this rank's page-locked host buffers: prefer the memory node the GPU hangs off, so that the 8 ranks of
+    a node do not push all their downloads through one socket's memory (and the inter-socket link).  Returns a description."""
+    try:
+        import ctypes
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
+        dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local_rank), "pci_device_id", 0)
+        if bus is None:
+            return "numa: pci bus id unavailable"
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        with open(path) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return "numa: node unknown"
+        libc = ctypes.CDLL(None, use_errno=True)
+        mask = ctypes.c_ulong(1 << node)
+        MPOL_PREFERRED, SYS_set_mempolicy = 1, 238  # x86-64
+        rc = libc.syscall(SYS_set_mempolicy, MPOL_PREFERRED, ctypes.byref(mask), ctypes.c_ulong(64))
+        return f"numa: host buffers prefer node {node}" if rc == 0 else f"numa: set_mempolicy failed (errno {ctypes.get_errno()})"
+    except Exception as e:  # placement is an optimisation, never a requirement
+        return f"numa: {type(e).__name__}: {e}"
+
+
 def workload_name(method):
     return f"ERA5-shape {NX}x{NY}x{NZ}x{NT} float32 -> {OUT_N}x{OUT_N} rotated-pole {OUT_STEP_DEG} deg (~2.5 km), {method}"
 
@@ -319,6 +344,7 @@ def main_b200(args):
     # ---- e2e: the same workload through the C ABI with HOST buffers (pinned); copies inside the timed region ----
     e2e = None
     if not args.no_e2e:
+        numa = bind_host_memory_to_gpu_node(local) if world > 1 else "numa: single rank, default placement"
         h_in = torch.empty((NZ, inY, inX), dtype=d_in.dtype, pin_memory=True)
         h_in.copy_(d_in[:NZ].cpu())
         h_out = torch.empty(NZ * OUT_N * OUT_N, dtype=d_in.dtype, pin_memory=True)
@@ -347,7 +373,7 @@ def main_b200(args):
                "d2h_bytes_per_step": int(out_elem * n_out * nlev), "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
                "how": ("fb200_interp_interpolate_values" if fill is None else "fb200_interp_get_data_slice") +
                       " (C ABI) on pinned host buffers, 24 calls of 137 levels per step, H2D + kernel + D2H pipelined in 3 streams "
-                      "inside the call",
+                      "inside the call; " + numa,
                "checksum": float(hout_np[::100003].astype(np.float64).sum())}
 
     # ---- CPU baseline (rank 0, N == 1 only): the reference's kernels on this box's host cores -----------------
