@@ -47,85 +47,142 @@ __global__ void k_forward_offsets(const unsigned* __restrict__ sorted_keys, long
 
 enum { AG_SUM = 0, AG_MEAN = 1, AG_MEDIAN = 2, AG_MAX = 3, AG_MIN = 4 };
 
+#ifndef FB_FWD_CELLS
+#define FB_FWD_CELLS 4
+#endif
+constexpr int kCells = FB_FWD_CELLS; // target cells per thread: their first gathers are issued together (the kernel is bound by the
+                          // dependent chain offsets -> permutation -> value, not by bandwidth)
+
+// one target cell: aggregate its CSR segment [beg, end) in ascending input order; v0 = value of the first entry (prefetched)
 template <int AGG, bool UNDEF>
-__global__ void __launch_bounds__(kThreads) k_forward(const int* __restrict__ perm, const int* __restrict__ offsets,
-                                                    const float* __restrict__ in, float* __restrict__ out, long long n_in,
-                                                    long long n_cells, long long nz)
+__device__ __forceinline__ float aggregate_cell(const float* __restrict__ lv, const int* __restrict__ perm, int beg, int end, float v0)
 {
-    const long long c = blockIdx.x * (long long)kThreads + threadIdx.x;
-    if (c >= n_cells)
-        return;
-    const int beg = __ldg(offsets + c), end = __ldg(offsets + c + 1);
-    for (long long z = blockIdx.y; z < nz; z += gridDim.y) {
-        const float* lv = in + z * n_in;
-        float res = undef_f();
-        if (AGG == AG_SUM || AGG == AG_MEAN) {
-            float s = 0.f; // std::accumulate(begin, end, 0.f): sequential, input order
-            long long cnt = 0;
-            for (int k = beg; k < end; ++k) {
-                const float v = __ldg(lv + __ldg(perm + k));
-                if (UNDEF || !isnan(v)) {
-                    s = __fadd_rn(s, v);
-                    ++cnt;
-                }
+    float res = undef_f();
+    if (beg >= end)
+        return res;
+    if (AGG == AG_SUM || AGG == AG_MEAN) {
+        float s = 0.f; // std::accumulate(begin, end, 0.f): sequential, input order
+        long long cnt = 0;
+        if (UNDEF || !isnan(v0)) {
+            s = __fadd_rn(s, v0);
+            ++cnt;
+        }
+        for (int k = beg + 1; k < end; ++k) {
+            const float v = __ldg(lv + __ldg(perm + k));
+            if (UNDEF || !isnan(v)) {
+                s = __fadd_rn(s, v);
+                ++cnt;
             }
-            if (cnt > 0)
-                res = (AGG == AG_MEAN) ? __fdiv_rn(s, __ll2float_rn(cnt)) : s;
-        } else if (AGG == AG_MAX || AGG == AG_MIN) {
-            bool have = false;
-            float best = 0.f;
-            for (int k = beg; k < end; ++k) {
-                const float v = __ldg(lv + __ldg(perm + k));
-                if (UNDEF || !isnan(v)) {
-                    if (!have) {
-                        best = v;
-                        have = true;
-                    } else if (AGG == AG_MAX ? (best < v) : (v < best)) { // std::max_element / min_element
-                        best = v;
-                    }
-                }
-            }
-            if (have)
-                res = best;
-        } else { // median = sorted[n/2] (nth_element, :49-53); rank selection, O(n^2) but segments are short
-            long long cnt = 0;
-            for (int k = beg; k < end; ++k) {
-                const float v = __ldg(lv + __ldg(perm + k));
-                if (UNDEF || !isnan(v))
-                    ++cnt;
-            }
-            if (cnt > 0) {
-                const long long want = cnt / 2;
-                for (int k = beg; k < end; ++k) {
-                    const float v = __ldg(lv + __ldg(perm + k));
-                    if (!(UNDEF || !isnan(v)))
-                        continue;
-                    long long less = 0, eq = 0;
-                    for (int j = beg; j < end; ++j) {
-                        const float w = __ldg(lv + __ldg(perm + j));
-                        if (!(UNDEF || !isnan(w)))
-                            continue;
-                        less += (w < v);
-                        eq += (w == v);
-                    }
-                    if (less <= want && want < less + eq) {
-                        res = v;
-                        break;
-                    }
+        }
+        if (cnt > 0)
+            res = (AGG == AG_MEAN) ? __fdiv_rn(s, __ll2float_rn(cnt)) : s;
+    } else if (AGG == AG_MAX || AGG == AG_MIN) {
+        bool have = false;
+        float best = 0.f;
+        if (UNDEF || !isnan(v0)) {
+            best = v0;
+            have = true;
+        }
+        for (int k = beg + 1; k < end; ++k) {
+            const float v = __ldg(lv + __ldg(perm + k));
+            if (UNDEF || !isnan(v)) {
+                if (!have) {
+                    best = v;
+                    have = true;
+                } else if (AGG == AG_MAX ? (best < v) : (v < best)) { // std::max_element / min_element
+                    best = v;
                 }
             }
         }
-        __stcs(out + z * n_cells + c, res);
+        if (have)
+            res = best;
+    } else { // median = sorted[n/2] (nth_element, :49-53); rank selection, O(n^2) but segments are short
+        long long cnt = 0;
+        for (int k = beg; k < end; ++k) {
+            const float v = __ldg(lv + __ldg(perm + k));
+            if (UNDEF || !isnan(v))
+                ++cnt;
+        }
+        if (cnt > 0) {
+            const long long want = cnt / 2;
+            for (int k = beg; k < end; ++k) {
+                const float v = __ldg(lv + __ldg(perm + k));
+                if (!(UNDEF || !isnan(v)))
+                    continue;
+                long long less = 0, eq = 0;
+                for (int j = beg; j < end; ++j) {
+                    const float w = __ldg(lv + __ldg(perm + j));
+                    if (!(UNDEF || !isnan(w)))
+                        continue;
+                    less += (w < v);
+                    eq += (w == v);
+                }
+                if (less <= want && want < less + eq) {
+                    res = v;
+                    break;
+                }
+            }
+        }
+    }
+    return res;
+}
+
+template <int AGG, bool UNDEF>
+__global__ void __launch_bounds__(kThreads) k_forward(const int* __restrict__ perm, const int* __restrict__ offsets,
+                                                    const float* __restrict__ in, float* __restrict__ out, long long n_in,
+                                                    long long n_cells, long long nz, int vec_ok)
+{
+    const long long c0 = (blockIdx.x * (long long)kThreads + threadIdx.x) * kCells;
+    if (c0 >= n_cells)
+        return;
+    int off[kCells + 1], first[kCells];
+    if (c0 + kCells <= n_cells) { // offsets[c0 .. c0+3] in one 128-bit load (c0 is a multiple of 4, cudaMalloc aligns the array)
+#pragma unroll
+        for (int q = 0; q < kCells / 4; ++q) {
+            const int4 o4 = __ldg(reinterpret_cast<const int4*>(offsets + c0) + q);
+            off[4 * q] = o4.x, off[4 * q + 1] = o4.y, off[4 * q + 2] = o4.z, off[4 * q + 3] = o4.w;
+        }
+        off[kCells] = __ldg(offsets + c0 + kCells);
+    } else {
+#pragma unroll
+        for (int j = 0; j <= kCells; ++j)
+            off[j] = __ldg(offsets + (c0 + j <= n_cells ? c0 + j : n_cells));
+    }
+#pragma unroll
+    for (int j = 0; j < kCells; ++j)
+        first[j] = off[j] < off[j + 1] ? __ldg(perm + off[j]) : -1; // the same for every level
+    const long long valid = n_cells - c0;
+    for (long long z = blockIdx.y; z < nz; z += gridDim.y) {
+        const float* lv = in + z * n_in;
+        float v0[kCells], res[kCells];
+#pragma unroll
+        for (int j = 0; j < kCells; ++j)
+            v0[j] = first[j] >= 0 ? __ldg(lv + first[j]) : 0.f; // kCells independent gathers in flight
+#pragma unroll
+        for (int j = 0; j < kCells; ++j)
+            res[j] = aggregate_cell<AGG, UNDEF>(lv, perm, off[j], off[j + 1], v0[j]);
+        float* o = out + z * n_cells + c0;
+        if (vec_ok && valid >= kCells) {
+#pragma unroll
+            for (int q = 0; q < kCells / 4; ++q)
+                __stcs(reinterpret_cast<float4*>(o) + q, make_float4(res[4 * q], res[4 * q + 1], res[4 * q + 2], res[4 * q + 3]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < kCells; ++j)
+                if (j < valid)
+                    __stcs(o + j, res[j]);
+        }
     }
 }
 
 template <int AGG>
 int launch_agg(bool undef, dim3 grid, cudaStream_t st, const ForwardPlan& p, const float* in, float* out, long long nz)
 {
+    const int vec_ok = ((p.n_cells % 4) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) ? 1 : 0;
     if (undef)
-        k_forward<AGG, true><<<grid, kThreads, 0, st>>>(p.d_perm, p.d_offsets, in, out, p.n_in, p.n_cells, nz);
+        k_forward<AGG, true><<<grid, kThreads, 0, st>>>(p.d_perm, p.d_offsets, in, out, p.n_in, p.n_cells, nz, vec_ok);
     else
-        k_forward<AGG, false><<<grid, kThreads, 0, st>>>(p.d_perm, p.d_offsets, in, out, p.n_in, p.n_cells, nz);
+        k_forward<AGG, false><<<grid, kThreads, 0, st>>>(p.d_perm, p.d_offsets, in, out, p.n_in, p.n_cells, nz, vec_ok);
     count_launch();
     FB_CUDA_CHECK(cudaGetLastError());
     return FB_OK;
@@ -192,7 +249,7 @@ int launch_forward(int method, const ForwardPlan& plan, const float* d_in, float
     if (plan.n_cells == 0 || nz == 0)
         return FB_OK;
     const bool undef = method >= FB_FWD_UNDEF_SUM;
-    const int gx = ceil_div(plan.n_cells, kThreads);
+    const int gx = ceil_div(ceil_div(plan.n_cells, kCells), kThreads);
     dim3 grid(gx, (unsigned)(nz < 64 ? nz : 64));
     switch (method) {
     case FB_FWD_SUM:
