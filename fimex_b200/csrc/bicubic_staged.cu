@@ -53,6 +53,10 @@ constexpr int kFastTaps = kT;                        // at most this many taps: 
 constexpr int kStageDoubles = 2 * kFastTaps * 5;     // per buffer: max(256*9, 2*256*5, 2048) = 2560 doubles
 constexpr int kMaxTapKeys = 16384;                   // 16 stencil taps for each of at most 896 distinct cells, padded to 2^k
 constexpr int kNoKey = 0x7fffffff;
+#ifndef FB_BIC_UNROLL
+#define FB_BIC_UNROLL 1 // unroll factor of the level loop of a full batch (experiments: -DFB_BIC_UNROLL=4 makes every shared address an immediate)
+#endif
+constexpr int kBicUnroll = FB_BIC_UNROLL;
 #ifndef FB_BIC_NL
 #define FB_BIC_NL 2 // levels per inner step of a full batch (independent accumulator chains: 4 points x NL levels)
 #endif
@@ -569,7 +573,7 @@ __device__ __forceinline__ void staged_tile(const GatherGeom& g, int tx, int ty,
                 if (rounds > 1)
                     load_group<S>(gr, gmeta, gfrac, (size_t)inf.z + gi);
                 if (L > 1 && nb == L) { // full batch: branch-free, two levels per step
-#pragma unroll 1
+#pragma unroll kBicUnroll
                     for (int zi = 0; zi < L; zi += kNL)
                         compute_levels<NF, ROT, S, (L > 1 ? kNL : 1)>(gr, st + zi, field_stride, tile + zi * kOutRow, L * kOutRow, s_cs);
                 } else {
