@@ -21,10 +21,10 @@ from .capi import (DataType, cdm_type, default_fill_value, LATITUDE, LONGITUDE, 
                    mifi_bad2nanf, mifi_nanf2bad, mifi_fill2d_f, mifi_creepfill2d_f, fill2d_device, creepfill2d_device, set_device,
                    version)
 from .cached import CachedForwardInterpolation, CachedInterpolation, CachedVectorReprojection
-from .interpolator import Interpolator
+from .interpolator import Interpolator, spatial_axis_spec, tokenize_dotted
 
 __all__ = [
-    "CachedInterpolation", "CachedForwardInterpolation", "CachedVectorReprojection", "Interpolator", "Method", "DataType", "cdm_type", "default_fill_value", "FimexB200Error",
+    "CachedInterpolation", "CachedForwardInterpolation", "CachedVectorReprojection", "Interpolator", "spatial_axis_spec", "tokenize_dotted", "Method", "DataType", "cdm_type", "default_fill_value", "FimexB200Error",
     "MIFI_OK", "MIFI_ERROR", "PROJ_AXIS", "LONGITUDE", "LATITUDE", "MIFI_VECTOR_KEEP_SIZE", "load", "lib_path", "version", "last_error",
     "set_device", "kernel_launches", "mifi_interpolate_f", "mifi_points2position", "mifi_project_axes", "mifi_project_values",
     "mifi_get_vector_reproject_matrix", "mifi_get_vector_reproject_matrix_field", "mifi_get_vector_reproject_matrix_points",

@@ -943,3 +943,57 @@ def test_pinned_host_buffers_are_recycled():
     assert d
     lib.fb200_host_free(d)
     lib.fb200_host_trim()
+
+
+# ---- test_interpolator_vector_backforth (test/testInterpolator.cc:398-472) ----------------------------------------
+# The reference's one quantitative end-to-end check of the vector path: a constant unit wind pointing north (or east) on
+# a global lat/lon grid is regridded (nearest neighbour, vectors rotated) to a projection and back to lat/lon; whatever
+# is not NaN must again be (0,1) / (1,0) within a per-projection delta.  test/data/north.nc / east.nc are NetCDF-4 files
+# this image cannot read; their content is the constant field synthesised here.  The utm row is outside the four
+# projections of the path and is left out; proj strings, axes and deltas are the reference's.
+_R = "6371000"
+_BACKFORTH = [
+    ("+proj=stere +lat_0=90 +lon_0=-32 +lat_ts=60 +ellps=sphere +R=" + _R, "-30000000,-29950000,...,30000000",
+     "-30000000,-29950000,...,30000000", "m", "-180,-179,...,179", "55,56,...,87", 8e-2),
+    ("+proj=stere +lat_0=90 +lon_0=0 +lat_ts=90 +ellps=sphere +R=" + _R, "-30000000,-29950000,...,30000000",
+     "-30000000,-29950000,...,30000000", "m", "-180,-179,...,179", "55,56,...,87", 8e-2),
+    ("+proj=stere +lat_0=-90 +lon_0=0 +lat_ts=-90 +ellps=sphere +R=" + _R, "-30000000,-29950000,...,30000000",
+     "-30000000,-29950000,...,30000000", "m", "0,1,359", "-55,-56,...,-87", 8e-2),
+    ("+proj=lcc +lat_0=63 +lon_0=15 +lat_1=63 +lat_2=63 +no_defs +R=6.371e+06", "-922000,-902000,...,922000",
+     "-1130000,-1110000,...,1230000", "m", "-30,-29,...,40", "50,51,...,85", 1e-2),
+    ("+proj=ob_tran +o_proj=longlat +lon_0=-40 +o_lat_p=22 +R=6.371e+06 +no_defs", "16.5,16.6,...,24.2", "-3.8,-3.7,...,14.9",
+     "degree", "-30,-29,...,40", "50,51,...,85", 5e-3),
+    ("+proj=ob_tran +o_proj=longlat +lon_0=0 +o_lat_p=25 +R=6.371e+06 +no_defs", "-46.4,-46.2,...,46.", "-36.4,-36.2,...,38.8",
+     "degree", "-90,-89,...,90", "40,51,...,85", 3e-2),
+    ("+proj=latlon +R=6.371e+06 +no_defs", "-179,-178,...,179", "-89.5,-89,...,89.5", "degree", "-180,-179,...,179",
+     "-90,-89,...,90", 1e-3),
+]
+
+
+@pytest.mark.parametrize("case", range(len(_BACKFORTH)))
+@pytest.mark.parametrize("wind", [(0.0, 1.0), (1.0, 0.0)], ids=["north", "east"])
+def test_interpolator_vector_backforth(case, wind):
+    proj, x_axis, y_axis, unit, lon_axis, lat_axis, delta = _BACKFORTH[case]
+    lon = np.arange(-180.0, 180.0, 1.0)
+    lat = np.arange(-90.0, 90.5, 1.0)
+    xw = np.full((lat.size, lon.size), wind[0], np.float32)
+    yw = np.full((lat.size, lon.size), wind[1], np.float32)
+
+    interp = fb.Interpolator("+proj=latlong +R=" + _R + " +no_defs", lon, lat, True, has_xy_vectors=True)
+    interp.changeProjection(fb.Method.NEAREST_NEIGHBOR, proj, x_axis, y_axis, unit, unit)
+    x1 = interp.getDataSlice(xw, counterpart=yw, direction="x")
+    y1 = interp.getDataSlice(yw, counterpart=xw, direction="y")
+    assert np.isfinite(x1).any()
+
+    is_degree = unit == "degree"
+    iback = fb.Interpolator(proj, fb.spatial_axis_spec(x_axis), fb.spatial_axis_spec(y_axis), is_degree, has_xy_vectors=True)
+    iback.changeProjection(fb.Method.NEAREST_NEIGHBOR, "+proj=latlon +R=" + _R, lon_axis, lat_axis, "degrees_east", "degrees_north")
+    x2 = iback.getDataSlice(x1, counterpart=y1, direction="x")
+    y2 = iback.getDataSlice(y1, counterpart=x1, direction="y")
+
+    # getScaledData (CDMReader.cc scaleDataOf) turns the variable's fill value back into NaN before the comparison
+    fill = fb.default_fill_value(np.float32)
+    ok = ~((x2 == np.float32(fill)) | (y2 == np.float32(fill)) | np.isnan(x2) | np.isnan(y2))
+    assert ok.sum() > 0.1 * ok.size, (int(ok.sum()), ok.size)  # hirlam8 covers only 338 of the 2556 lat/lon points
+    assert np.abs(x2[ok] - wind[0]).max() < delta, float(np.abs(x2[ok] - wind[0]).max())
+    assert np.abs(y2[ok] - wind[1]).max() < delta, float(np.abs(y2[ok] - wind[1]).max())
