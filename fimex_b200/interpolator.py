@@ -148,6 +148,43 @@ class Interpolator:
             self.cachedVectorReprojection = CachedVectorReprojection.fromProjection(capi.MIFI_VECTOR_KEEP_SIZE, self.source_proj4, proj_input,
                                                                                     out_x, out_y, xt, yt)
 
+    def changeProjectionToLonLatValues(self, method, lon_vals, lat_vals):
+        """CDMInterpolator::changeProjection(method, lonVals, latVals) (:460-510): a list of geographic points as the target
+        (outX = n, outY = 1).  The reference narrows the values to float before use (double_to_float_cast, :454-457)."""
+        lon_vals = np.asarray(lon_vals, dtype=np.float64).ravel()
+        lat_vals = np.asarray(lat_vals, dtype=np.float64).ravel()
+        if lon_vals.size != lat_vals.size:  # the reference logs an error and leaves the projection unchanged (:465-469)
+            raise FimexB200Error(f"changeProjection, number of longitude and latitude values differs: {lon_vals.size} != {lat_vals.size}")
+        lon32 = lon_vals.astype(np.float32).astype(np.float64)
+        lat32 = lat_vals.astype(np.float32).astype(np.float64)
+        return self.changeProjectionToTemplate(method, lon32, lat32, lon_vals.size, 1)
+
+    def changeProjectionToTemplate(self, method, tmpl_lon, tmpl_lat, out_x=None, out_y=None):
+        """CDMInterpolator::changeProjection(method, tmplReader, tmplRefVarName) (:651-720) after the template's 2-D
+        longitude/latitude (degrees, [y][x]) have been read by the host application ->
+        changeProjectionByProjectionParametersToLatLonTemplate (:1706-1823)."""
+        m = capi.mifi_string_to_interpolation_method(method) if isinstance(method, str) else int(method)
+        if m in (Method.COORD_NN, Method.COORD_NN_KD) or Method.FORWARD_SUM <= m <= Method.FORWARD_UNDEF_MIN:
+            raise FimexB200Error(f"projection method: {m}, not supported")  # :706-714
+        if m not in (Method.NEAREST_NEIGHBOR, Method.BILINEAR, Method.BICUBIC):
+            raise FimexB200Error(f"unknown projection method: {m}")
+        tmpl_lon = np.asarray(tmpl_lon, dtype=np.float64)
+        tmpl_lat = np.asarray(tmpl_lat, dtype=np.float64)
+        if out_x is None or out_y is None:
+            out_y, out_x = tmpl_lon.shape
+        self.cachedInterpolation = None
+        self.cachedVectorReprojection = None
+        ci = CachedInterpolation.fromTemplate(m, MIFI_WGS84_LATLON_PROJ4, tmpl_lon.ravel(), tmpl_lat.ravel(), out_x, out_y, self.source_proj4,
+                                              self.x_axis, self.y_axis, self.is_degree, self.x_dim, self.y_dim)
+        ci.createReducedDomain(self.x_dim, self.y_dim)  # :1797-1799
+        self.cachedInterpolation = ci
+        if self.has_xy_vectors:  # :1805-1820: matrix at the template points, source CRS -> geographic
+            self.cachedVectorReprojection = CachedVectorReprojection.fromPoints(capi.MIFI_VECTOR_KEEP_SIZE, self.source_proj4,
+                                                                                MIFI_WGS84_LATLON_PROJ4, 0 if self.is_degree else 1,
+                                                                                tmpl_lon.ravel(), tmpl_lat.ravel())
+        self.method = Method(m)
+        return self
+
     def _source_lonlat(self):
         if self.lon2d is not None and self.lat2d is not None:
             return self.lon2d, self.lat2d

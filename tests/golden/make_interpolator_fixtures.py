@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""Extract the inputs of the reference's CDMInterpolator tests (test/testInterpolator.cc) into one small fixture.
+
+The GPU box has no /root/reference and no NetCDF reader, so the arrays the reference's tests read from its own classic
+NetCDF-3 test files are stored in tests/golden/interpolator_fixtures.npz.  Only data is taken (coordinates, the fields the
+tests look at, the grid mapping's proj4 attribute); run here once:
+
+    python tests/golden/make_interpolator_fixtures.py [/root/reference]
+"""
+import os
+import sys
+
+import numpy as np
+from scipy.io import netcdf_file
+
+
+def native(a):
+    a = np.asarray(a)
+    return np.ascontiguousarray(a.astype(a.dtype.newbyteorder("=")))
+
+
+def main():
+    ref = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+    out = {}
+
+    # test_interpolator2coords (:129-180): temp2 lives on (y_c, x_c) with its own 2-D coordinates
+    nc = netcdf_file(os.path.join(ref, "test/twoCoordsTest.nc"), "r", mmap=False)
+    out["two_proj4"] = np.array(nc.variables["projection_1"].proj4.decode())
+    for name in ("x_c", "y_c", "longitude2", "latitude2", "temp2"):
+        out["two_" + name] = native(nc.variables[name].data)
+
+    # test_interpolatorSatellite (:105-126): swath with 2-D lat/lon (float, _FillValue -999), no projection
+    nc = netcdf_file(os.path.join(ref, "test/satellite_cma.nc"), "r", mmap=False)
+    for name in ("lat", "lon", "cma"):
+        out["sat_" + name] = native(nc.variables[name].data)
+
+    # test_interpolator_template (:220-239) and test_interpolator_latlon (:241-264)
+    nc = netcdf_file(os.path.join(ref, "test/erai.sfc.40N.0.75d.200301011200.nc"), "r", mmap=False)
+    out["erai_proj4"] = np.array(nc.variables["projection_regular_ll"].proj4.decode())
+    for name in ("longitude", "latitude", "ga_skt"):
+        out["erai_" + name] = native(nc.variables[name].data)
+    nc = netcdf_file(os.path.join(ref, "test/template_noaa17.nc"), "r", mmap=False)
+    for name in ("longitude", "latitude"):
+        out["tmpl_" + name] = native(nc.variables[name].data)
+
+    dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "interpolator_fixtures.npz")
+    np.savez_compressed(dst, **out)
+    for k, v in out.items():
+        print(k, v.dtype, v.shape)
+    print("wrote", dst, os.path.getsize(dst), "bytes")
+
+
+if __name__ == "__main__":
+    main()

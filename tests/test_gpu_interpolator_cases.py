@@ -1,0 +1,152 @@
+"""The reference's CDMInterpolator tests that run on its own NetCDF-3 test files (test/testInterpolator.cc), restated through
+the Interpolator mirror on the same data.  The arrays were extracted from the reference's files by
+tests/golden/make_interpolator_fixtures.py (the GPU box has neither /root/reference nor a NetCDF reader); every test keeps
+the reference's assertions and adds bit-parity with the oracle on the same inputs.
+
+Not restated: test_interpolator / test_interpolatorKDTree / test_interpolatorRelative / test_interpolator_vectorlatlon need
+the optional flth00.dat (hasTestExtra(), absent from the reference tree); test_interpolatorNcml and
+test_interpolator_wrongaxes_latlon test NcML metadata; test_interpolator_vcross is the cross-section processor.
+test_interpolator_vector_backforth is in test_gpu_parity.py.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import assert_bit_equal
+
+pytestmark = pytest.mark.gpu
+
+import fimex_b200 as fb  # noqa: E402
+from fimex_b200 import Method  # noqa: E402
+
+R = "6371000"
+WGS84 = "+proj=latlong +datum=WGS84 +towgs84=0,0,0 +no_defs"
+
+
+@pytest.fixture(scope="module")
+def fx():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "interpolator_fixtures.npz"))
+
+
+def test_interpolator2coords(fx, oracle):
+    # test/testInterpolator.cc:129-180: temp2(time, y_c, x_c) of twoCoordsTest.nc to a 12 x 12 polar-stereographic grid with
+    # coord_kdtree and with nearestneighbor; more than 100 of the 144 cells of the first time step are above 29000
+    proj = "+proj=stere +lat_0=90 +lon_0=0 +lat_ts=60 +ellps=sphere +a=" + R + " +e=0"
+    x_axis = -1705516 + 50000.0 * np.arange(12)
+    y_axis = -6872225 + 50000.0 * np.arange(12)
+    temp2 = fx["two_temp2"][0]  # getDataSlice(varName) == unLimDimPos 0
+    assert temp2.dtype == np.int16
+    xc, yc = fx["two_x_c"].astype(np.float64), fx["two_y_c"].astype(np.float64)
+    lon2, lat2 = fx["two_longitude2"].ravel(), fx["two_latitude2"].ravel()
+
+    interp = fb.Interpolator(str(fx["two_proj4"]), xc, yc, False, lon2d=lon2, lat2d=lat2)
+    interp.changeProjection(Method.COORD_NN_KD, proj, x_axis, y_axis, "m", "m")
+    got = interp.getDataSlice(temp2)
+    assert got.dtype == np.int16 and got.shape == (12, 12)
+    assert int((got.astype(np.float64) > 29000).sum()) > 100
+    # the same through the oracle: target lon/lat, kd search inside the distance of interest, gather, NaN -> fill, cast
+    rc, tx, ty = oracle.project_axes(proj, WGS84, x_axis, y_axis)
+    assert rc == 1
+    dist = oracle.max_distance_of_interest(x_axis, y_axis, True)
+    wx, wy, ties = oracle.coordkd(tx, ty, np.radians(lon2), np.radians(lat2), xc.size, yc.size, dist)
+    assert ties == 0
+    fill = fb.default_fill_value(np.int16)
+    want = oracle.from_float(oracle.cached_interpolate(4, wx, wy, xc.size, yc.size, 12, 12, oracle.as_float(temp2, fill)[None]), fill, np.int16)
+    assert np.array_equal(got, want.reshape(12, 12))
+
+    interp = fb.Interpolator(str(fx["two_proj4"]), xc, yc, False, lon2d=lon2, lat2d=lat2)
+    interp.changeProjection(Method.NEAREST_NEIGHBOR, proj, x_axis, y_axis, "m", "m")
+    got = interp.getDataSlice(temp2)
+    assert int((got.astype(np.float64) > 29000).sum()) > 100
+    rc, px, py = oracle.project_axes(proj, str(fx["two_proj4"]), x_axis, y_axis)
+    assert rc == 1
+    px = oracle.points2position(px, xc, 0)
+    py = oracle.points2position(py, yc, 0)
+    want = oracle.from_float(oracle.cached_interpolate(0, px, py, xc.size, yc.size, 12, 12, oracle.as_float(temp2, fill)[None]), fill, np.int16)
+    assert np.array_equal(got, want.reshape(12, 12))
+
+
+def test_interpolatorSatellite(fx):
+    # test/testInterpolator.cc:105-126: a swath with float 2-D lat/lon (fill -999 -> NaN by getScaledData) and no projection,
+    # coord_kdtree to a 10 x 10 lat/lon grid.  The reference only checks that both getDataSlice overloads return the same
+    # number of values (its axes put 55..55.9 on x and -106..-105.1 on y, i.e. swapped, so nothing is in range).
+    lat = fx["sat_lat"].astype(np.float64)
+    lon = fx["sat_lon"].astype(np.float64)
+    lat[lat == -999.0] = np.nan
+    lon[lon == -999.0] = np.nan
+    cma = fx["sat_cma"][0]
+    x_axis = 55 + 0.1 * np.arange(10)
+    y_axis = -106 + 0.1 * np.arange(10)
+    interp = fb.Interpolator("", np.arange(51.0), np.arange(51.0), False, lon2d=lon.ravel(), lat2d=lat.ravel())
+    interp.changeProjection(Method.COORD_NN_KD, "+proj=latlon +R=" + R + " +e=0", x_axis, y_axis, "degrees_east", "degrees_north")
+    got = interp.getDataSlice(cma)
+    assert got.shape == (10, 10) and got.dtype == np.int16
+    assert (got == fb.default_fill_value(np.int16)).all()
+    # with the axes the right way round the swath is found: lon on x, lat on y
+    interp.changeProjection(Method.COORD_NN_KD, "+proj=latlon +R=" + R + " +e=0", -106.5 + 0.1 * np.arange(10), 56.3 + 0.04 * np.arange(10),
+                            "degrees_east", "degrees_north")
+    got = interp.getDataSlice(cma)
+    assert np.isin(got, (0, 1, -32767)).all() and np.isin(got, (0, 1)).sum() > 50
+
+
+def _erai(fx):
+    return (str(fx["erai_proj4"]), fx["erai_longitude"].astype(np.float64), fx["erai_latitude"].astype(np.float64), fx["erai_ga_skt"])
+
+
+def _template_oracle(oracle, method, proj, lon, lat, tlon, tlat, ox, oy, field):
+    rc, x, y = oracle.project_values(WGS84, proj, np.radians(tlon), np.radians(tlat))
+    assert rc == 1
+    py = oracle.points2position(y, np.radians(lat), 2)
+    px = oracle.points2position(x, np.radians(lon), 1)
+    f32 = oracle.as_float(field, fb.default_fill_value(np.float64))
+    out = oracle.cached_interpolate(int(method), px, py, lon.size, lat.size, ox, oy, f32.reshape(-1, lat.size, lon.size))
+    return oracle.from_float(out, fb.default_fill_value(np.float64), np.float64)
+
+
+def test_interpolator_template(fx, oracle):
+    # test/testInterpolator.cc:220-239: ga_skt (double, 0.75-degree lat/long, latitude descending) bicubic to the 2-D
+    # longitude/latitude of template_noaa17.nc (29 x 31); only the first 7 data points are defined, between 270 and 280
+    proj, lon, lat, skt = _erai(fx)
+    tlon, tlat = fx["tmpl_longitude"].astype(np.float64), fx["tmpl_latitude"].astype(np.float64)
+    assert tlon.shape == (31, 29)
+    interp = fb.Interpolator(proj, lon, lat, True)
+    interp.changeProjectionToTemplate(Method.BICUBIC, tlon, tlat)
+    ci = interp.cachedInterpolation
+    assert ci.getOutX() == 29 and ci.getOutY() == 31
+    got = interp.getDataSlice(skt)  # getData("ga_skt"): all 8 times
+    assert got.dtype == np.float64 and got.shape == (8, 1, 31, 29)
+    fill = fb.default_fill_value(np.float64)
+    arr = np.where(got == fill, np.nan, got).ravel()  # asDouble() after getScaledData: fill -> NaN
+    assert (~np.isnan(arr[:7])).all() and (arr[:7] < 280).all() and (arr[:7] > 270).all()
+    assert np.isnan(arr[7])
+    want = _template_oracle(oracle, Method.BICUBIC, proj, lon, lat, tlon.ravel(), tlat.ravel(), 29, 31, skt)
+    assert_bit_equal(got.ravel(), want.ravel(), "template bicubic (double in, double out)")
+    with pytest.raises(fb.FimexB200Error):  # :706-714
+        interp.changeProjectionToTemplate(Method.COORD_NN, tlon, tlat)
+
+
+def test_interpolator_latlon(fx, oracle):
+    # test/testInterpolator.cc:241-264: bilinear to a list of 10 geographic points
+    lat_vals = [59.109, 59.052, 58.994, 58.934, 58.874, 58.812, 58.749, 58.685, 58.62, 64.0]
+    lon_vals = [4.965, 5.13, 5.296, 5.465, 5.637, 5.81, 5.986, 6.164001, 6.344, 3.0]
+    proj, lon, lat, skt = _erai(fx)
+    interp = fb.Interpolator(proj, lon, lat, True)
+    interp.changeProjectionToLonLatValues(Method.BILINEAR, lon_vals, lat_vals)
+    ci = interp.cachedInterpolation
+    assert ci.getOutX() == len(lon_vals) and ci.getOutY() == 1
+    got = interp.getDataSlice(skt)
+    assert got.shape == (8, 1, 1, 10)
+    fill = fb.default_fill_value(np.float64)
+    arr = np.where(got == fill, np.nan, got).ravel()
+    assert not np.isnan(arr[0]) and 270 < arr[0] < 280
+    assert (~np.isnan(arr)).all() and (arr < 281.1).all() and (arr > 266).all()
+    # the values are narrowed to float first (double_to_float_cast, CDMInterpolator.cc:454-457)
+    tlon = np.asarray(lon_vals, np.float32).astype(np.float64)
+    tlat = np.asarray(lat_vals, np.float32).astype(np.float64)
+    want = _template_oracle(oracle, Method.BILINEAR, proj, lon, lat, tlon, tlat, 10, 1, skt)
+    assert_bit_equal(got.ravel(), want.ravel(), "lon/lat values bilinear")
+    with pytest.raises(fb.FimexB200Error):
+        interp.changeProjectionToLonLatValues(Method.BILINEAR, lon_vals, lat_vals[:-1])
+    with pytest.raises(fb.FimexB200Error):
+        interp.changeProjectionToLonLatValues(Method.FORWARD_MEAN, lon_vals, lat_vals)
