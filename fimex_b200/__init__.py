@@ -10,6 +10,7 @@ The product is ``fimex_b200/lib/libfimex_b200.so`` (hand-written sm_100a CUDA be
   method names) working on numpy arrays (host path) or torch CUDA tensors (device-resident path);
 * :mod:`fimex_b200.interpolator` -- the table-producing part of ``CDMInterpolator::changeProjection*`` and the
   per-slice driver ``getDataSlice`` for in-memory slices;
+* :mod:`fimex_b200.processor` -- ``CDMProcessor::rotateVectorToLatLon`` / ``rotateDirectionToLatLon`` on the same rotation kernels;
 * :mod:`fimex_b200.slab`    -- one-process-per-GPU slab partition of the (time x level) stack with a single
   NCCL broadcast of the cached tables.
 """
@@ -22,9 +23,10 @@ from .capi import (DataType, cdm_type, default_fill_value, LATITUDE, LONGITUDE, 
                    version)
 from .cached import CachedForwardInterpolation, CachedInterpolation, CachedVectorReprojection
 from .interpolator import Interpolator, spatial_axis_spec, tokenize_dotted
+from .processor import Processor
 
 __all__ = [
-    "CachedInterpolation", "CachedForwardInterpolation", "CachedVectorReprojection", "Interpolator", "spatial_axis_spec", "tokenize_dotted", "Method", "DataType", "cdm_type", "default_fill_value", "FimexB200Error",
+    "CachedInterpolation", "CachedForwardInterpolation", "CachedVectorReprojection", "Interpolator", "Processor", "spatial_axis_spec", "tokenize_dotted", "Method", "DataType", "cdm_type", "default_fill_value", "FimexB200Error",
     "MIFI_OK", "MIFI_ERROR", "PROJ_AXIS", "LONGITUDE", "LATITUDE", "MIFI_VECTOR_KEEP_SIZE", "load", "lib_path", "version", "last_error",
     "set_device", "kernel_launches", "mifi_interpolate_f", "mifi_points2position", "mifi_project_axes", "mifi_project_values",
     "mifi_get_vector_reproject_matrix", "mifi_get_vector_reproject_matrix_field", "mifi_get_vector_reproject_matrix_points",

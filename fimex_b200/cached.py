@@ -382,6 +382,43 @@ class CachedVectorReprojection:
         self.ox, self.oy = lo.size, 1
         return self
 
+    @classmethod
+    def fromGrid(cls, method, proj, x_axis, y_axis, is_degree, toLatLon=True):
+        """makeCachedVectorReprojection(dataReader, cs, toLatLon) (src/CDMProcessor.cc:99-145): the rotation matrix of a grid's
+        own axes towards geographic directions (toLatLon) or from geographic to grid directions"""
+        xa, ya = f64(x_axis), f64(y_axis)
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        check(load().fb200_vector_create_from_grid(int(method), proj.encode(), ptr(xa), ptr(ya), xa.size, ya.size, int(bool(is_degree)),
+                                                   int(bool(toLatLon)), C.byref(self._h)), "makeCachedVectorReprojection")
+        self.ox, self.oy = xa.size, ya.size
+        return self
+
+    def getVectorSlice(self, uIn, vIn, badValueU, badValueV, outType=None, stream=None):
+        """The rotation branch of CDMProcessor::getDataSlice (src/CDMProcessor.cc:579-617) for both components at once:
+        fill -> NaN, reprojectValues, NaN -> fill + cast back to the variable's type"""
+        lib = load()
+        if _is_torch(uIn):
+            import torch
+            if uIn.dtype != vIn.dtype or uIn.numel() != vIn.numel():
+                raise FimexB200Error("xData != yData in vectorInterpolation")
+            out_dtype = outType if outType is not None else uIn.dtype
+            uo = torch.empty(uIn.shape, dtype=out_dtype, device=uIn.device)
+            vo = torch.empty(uIn.shape, dtype=out_dtype, device=uIn.device)
+            check(lib.fb200_vector_get_slice_device(self._h, int(capi.cdm_type(uIn.dtype)), ptr(uIn), ptr(vIn), uIn.numel(), float(badValueU),
+                                                    float(badValueV), int(capi.cdm_type(out_dtype)), ptr(uo), ptr(vo), _stream_ptr(stream)),
+                  "rotateVectorToLatLon")
+            return uo, vo
+        u, v = np.ascontiguousarray(uIn), np.ascontiguousarray(vIn)
+        if u.dtype != v.dtype or u.size != v.size:
+            raise FimexB200Error("xData != yData in vectorInterpolation")  # CDMProcessor.cc:608-610
+        out_dtype = np.dtype(outType) if outType is not None else u.dtype
+        uo = np.empty(u.shape, dtype=out_dtype)
+        vo = np.empty(u.shape, dtype=out_dtype)
+        check(lib.fb200_vector_get_slice(self._h, int(capi.cdm_type(u.dtype)), ptr(u), ptr(v), u.size, float(badValueU), float(badValueV),
+                                         int(capi.cdm_type(out_dtype)), ptr(uo), ptr(vo)), "rotateVectorToLatLon")
+        return uo, vo
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
             load().fb200_vector_destroy(self._h)

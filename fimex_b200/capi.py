@@ -160,6 +160,9 @@ def _declare(lib):
         "fb200_vector_reproject_values_device": (i, [_vp, _vp, _vp, sz, _vp]),
         "fb200_vector_reproject_direction_values": (i, [_vp, _vp, sz]),
         "fb200_vector_get_matrix": (i, [_vp, _vp]),
+        "fb200_vector_create_from_grid": (i, [i, C.c_char_p, _vp, _vp, i, i, i, i, P(_vp)]),
+        "fb200_vector_get_slice": (i, [_vp, i, _vp, _vp, sz, C.c_double, C.c_double, i, _vp, _vp]),
+        "fb200_vector_get_slice_device": (i, [_vp, i, _vp, _vp, sz, C.c_double, C.c_double, i, _vp, _vp, _vp]),
         "fb200_vector_destroy": (None, [_vp]),
         "fb200_interp_interpolate_vector": (i, [_vp, _vp, _vp, _vp, sz, _vp, _vp, P(sz)]),
         "fb200_interp_interpolate_vector_device": (i, [_vp, _vp, _vp, _vp, sz, _vp, _vp, P(sz), _vp]),

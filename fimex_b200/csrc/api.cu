@@ -1433,6 +1433,48 @@ int fb200_vector_create_from_points(int method, const char* proj_input, const ch
     return MIFI_OK;
 }
 
+int fb200_vector_create_from_grid(int method, const char* proj, const double* x_axis, const double* y_axis, int nx, int ny, int isDegree,
+                                  int toLatLon, fb200_vector** handle)
+{
+    // makeCachedVectorReprojection (src/CDMProcessor.cc:99-145): the matrix of a grid's own axes, towards geographic
+    // directions (toLatLon: matrix_field on the expanded mesh) or back (matrix from WGS84 lat/long to the grid's CRS, with
+    // MIFI_PROJ_AXIS "even for LAT/LON since axes already in radian")
+    FB_REQUIRE(handle != nullptr, "null handle pointer");
+    *handle = nullptr;
+    FB_REQUIRE(nx > 0 && ny > 0 && x_axis && y_axis && proj, "empty grid");
+    if (use_device(default_device()) != FB_OK)
+        return MIFI_ERROR;
+    std::unique_ptr<fb200_vector> v(new fb200_vector());
+    v->method = method;
+    v->ox = nx;
+    v->oy = ny;
+    v->device = default_device();
+    const size_t on = (size_t)nx * ny;
+    cudaStream_t st = cudaStreamPerThread;
+    if (dev_alloc(&v->d_matrix, 4 * on) != FB_OK || dev_alloc(&v->d_cs, on) != FB_OK)
+        return MIFI_ERROR;
+    const std::vector<double> xa = axis_in_radians(x_axis, (size_t)nx, isDegree != 0);
+    const std::vector<double> ya = axis_in_radians(y_axis, (size_t)ny, isDegree != 0);
+    if (toLatLon) {
+        std::vector<double> xf(on), yf(on);
+        for (int j = 0; j < ny; ++j)
+            for (int i = 0; i < nx; ++i) {
+                xf[(size_t)nx * j + i] = xa[i];
+                yf[(size_t)nx * j + i] = ya[j];
+            }
+        if (build_matrix_device(MI_FIELD, proj, kWgs84LatLon, xf.data(), yf.data(), 0, 0, nx, ny, 0, v->d_matrix, st) != FB_OK)
+            return MIFI_ERROR;
+    } else if (build_matrix_device(MI_AXES, kWgs84LatLon, proj, xa.data(), ya.data(), MIFI_PROJ_AXIS, MIFI_PROJ_AXIS, nx, ny, 0, v->d_matrix, st) !=
+               FB_OK) {
+        return MIFI_ERROR;
+    }
+    if (launch_matrix_to_cossin(v->d_matrix, (long long)on, v->d_cs, st) != FB_OK)
+        return MIFI_ERROR;
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    *handle = v.release();
+    return MIFI_OK;
+}
+
 int fb200_vector_reproject_values_device(const fb200_vector* v, float* d_u, float* d_v, size_t size, void* stream)
 {
     FB_REQUIRE(v != nullptr, "null vector handle");
@@ -1728,6 +1770,67 @@ int fb200_interp_get_vector_slice(const fb200_interp* h, const fb200_vector* v, 
     const void* in[2] = {uIn, vIn};
     void* out[2] = {uOut, vOut};
     return run_slice_host(h, (v && v->d_cs) ? v : nullptr, 2, in, out, nz, io);
+}
+
+int fb200_vector_get_slice_device(const fb200_vector* v, int inType, const void* d_u, const void* d_v, size_t size, double badU, double badV,
+                                  int outType, void* d_uo, void* d_vo, void* stream)
+{
+    // the rotation branch of CDMProcessor::getDataSlice (src/CDMProcessor.cc:579-617): both components fill -> NaN as float,
+    // reprojectValues, NaN -> fill + cast back -- no gather in between
+    FB_REQUIRE(v != nullptr, "null vector handle");
+    if (check_slice_types(inType, outType) != FB_OK)
+        return MIFI_ERROR;
+    if (size == 0)
+        return MIFI_OK;
+    FB_REQUIRE(d_u && d_v && d_uo && d_vo, "null data pointer");
+    if (use_device(v->device) != FB_OK)
+        return MIFI_ERROR;
+    cudaStream_t st = as_stream(stream);
+    Scratch tmp(st);
+    float *fu = nullptr, *fv = nullptr;
+    if (tmp.get(&fu, size) != FB_OK || tmp.get(&fv, size) != FB_OK)
+        return MIFI_ERROR;
+    const float bu = (float)badU, bv = (float)badV;
+    if (launch_as_float(inType, d_u, (long long)size, !std::isnan(bu), bu, fu, st) != FB_OK ||
+        launch_as_float(inType, d_v, (long long)size, !std::isnan(bv), bv, fv, st) != FB_OK)
+        return MIFI_ERROR;
+    if (v->ox == 0 || v->oy == 0 || v->d_cs == nullptr) {
+        fprintf(stderr, "fimex_b200: CachedVectorReprojection not initialized, using identity\n"); // CachedVectorReprojection.cc:37-40
+    } else {
+        const long long layer = (long long)v->ox * v->oy;
+        if (launch_rotate(v->d_cs, fu, fv, layer, (long long)(size / (size_t)layer), st) != FB_OK)
+            return MIFI_ERROR;
+    }
+    if (launch_from_float(fu, (long long)size, outType, badU, d_uo, st) != FB_OK ||
+        launch_from_float(fv, (long long)size, outType, badV, d_vo, st) != FB_OK)
+        return MIFI_ERROR;
+    return MIFI_OK;
+}
+
+int fb200_vector_get_slice(const fb200_vector* v, int inType, const void* uIn, const void* vIn, size_t size, double badU, double badV,
+                           int outType, void* uOut, void* vOut)
+{
+    FB_REQUIRE(v != nullptr, "null vector handle");
+    if (check_slice_types(inType, outType) != FB_OK)
+        return MIFI_ERROR;
+    if (size == 0)
+        return MIFI_OK;
+    FB_REQUIRE(uIn && vIn && uOut && vOut, "null data pointer");
+    if (use_device(v->device) != FB_OK)
+        return MIFI_ERROR;
+    cudaStream_t st = cudaStreamPerThread;
+    Scratch tmp(st);
+    const size_t ib = size * type_size(inType), ob = size * type_size(outType);
+    char *d_u = nullptr, *d_v = nullptr, *d_uo = nullptr, *d_vo = nullptr;
+    if (tmp.upload(&d_u, static_cast<const char*>(uIn), ib) != FB_OK || tmp.upload(&d_v, static_cast<const char*>(vIn), ib) != FB_OK ||
+        tmp.get(&d_uo, ob) != FB_OK || tmp.get(&d_vo, ob) != FB_OK)
+        return MIFI_ERROR;
+    if (fb200_vector_get_slice_device(v, inType, d_u, d_v, size, badU, badV, outType, d_uo, d_vo, st) != MIFI_OK)
+        return MIFI_ERROR;
+    FB_CUDA_CHECK(cudaMemcpyAsync(uOut, d_uo, ob, cudaMemcpyDeviceToHost, st));
+    FB_CUDA_CHECK(cudaMemcpyAsync(vOut, d_vo, ob, cudaMemcpyDeviceToHost, st));
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return MIFI_OK;
 }
 
 // ---------------------------------------------------------------------------------------- mifi_* drop-ins

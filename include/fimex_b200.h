@@ -219,12 +219,25 @@ int fb200_vector_create_from_projection(int method, const char* proj_input, cons
  * MIFI_WGS84_LATLON_PROJ4, inputIsMetric = !isDegree(source)); the handle has ox = on, oy = 1 */
 int fb200_vector_create_from_points(int method, const char* proj_input, const char* proj_output, int inputIsMetric, const double* lon,
                                     const double* lat, int on, fb200_vector** handle);
+/* makeCachedVectorReprojection(dataReader, cs, toLatLon) (src/CDMProcessor.cc:99-145), the matrix behind
+ * CDMProcessor::rotateVectorToLatLon / rotateDirectionToLatLon: the grid's OWN axes (degrees when isDegree, else metres).
+ * toLatLon != 0: grid directions -> geographic (mifi_get_vector_reproject_matrix_field on the expanded mesh, :124-135);
+ * toLatLon == 0: geographic -> grid directions (mifi_get_vector_reproject_matrix from MIFI_WGS84_LATLON_PROJ4, :137-140). */
+int fb200_vector_create_from_grid(int method, const char* proj, const double* x_axis, const double* y_axis, int nx, int ny, int isDegree,
+                                  int toLatLon, fb200_vector** handle);
 /* reprojectValues(uValues, vValues, size): rotate in place -- src/CachedVectorReprojection.cc:35-44 */
 int fb200_vector_reproject_values(const fb200_vector* handle, float* uValues, float* vValues, size_t size);
 int fb200_vector_reproject_values_device(const fb200_vector* handle, float* d_uValues, float* d_vValues, size_t size, void* cuda_stream);
 /* reprojectDirectionValues(angles, size) -- src/CachedVectorReprojection.cc:46-55 */
 int fb200_vector_reproject_direction_values(const fb200_vector* handle, float* angles, size_t size);
 int fb200_vector_get_matrix(const fb200_vector* handle, double* matrix);
+/* The rotation branch of CDMProcessor::getDataSlice (src/CDMProcessor.cc:579-617) for one x/y pair: both components
+ * fill -> NaN as float (data2InterpolationArray), reprojectValues, NaN -> fill and cast back (interpolationArray2Data).
+ * inType/outType: enum fb200_datatype; `size` values per component; the caller keeps the component it asked for. */
+int fb200_vector_get_slice(const fb200_vector* handle, int inType, const void* uIn, const void* vIn, size_t size, double badU, double badV,
+                           int outType, void* uOut, void* vOut);
+int fb200_vector_get_slice_device(const fb200_vector* handle, int inType, const void* d_uIn, const void* d_vIn, size_t size, double badU,
+                                  double badV, int outType, void* d_uOut, void* d_vOut, void* cuda_stream);
 void fb200_vector_destroy(fb200_vector* handle);
 
 /* Fused form of src/CDMInterpolator.cc:255-276: interpolate both components of an x/y vector with ONE table

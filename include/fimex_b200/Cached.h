@@ -148,6 +148,16 @@ public:
         if (fb200_vector_create(method, matrix.get(), ox, oy, &handle_) != MIFI_OK)
             throw CDMException(std::string("CachedVectorReprojection: ") + fb200_last_error());
     }
+    /** makeCachedVectorReprojection(dataReader, cs, toLatLon) (src/CDMProcessor.cc:99-145): the matrix is built and kept on the
+     *  device; axes in metres, or degrees when isDegree */
+    CachedVectorReprojection(int method, const std::string& proj4, const std::vector<double>& xAxis, const std::vector<double>& yAxis,
+                             bool isDegree, bool toLatLon)
+        : handle_(0), ox(static_cast<int>(xAxis.size())), oy(static_cast<int>(yAxis.size()))
+    {
+        if (fb200_vector_create_from_grid(method, proj4.c_str(), xAxis.data(), yAxis.data(), ox, oy, isDegree ? 1 : 0, toLatLon ? 1 : 0,
+                                          &handle_) != MIFI_OK)
+            throw CDMException(std::string("makeCachedVectorReprojection: ") + fb200_last_error());
+    }
     virtual ~CachedVectorReprojection() { fb200_vector_destroy(handle_); }
 
     void reprojectValues(shared_float_array& uValues, shared_float_array& vValues, size_t size) const
@@ -159,6 +169,13 @@ public:
     {
         if (fb200_vector_reproject_direction_values(handle_, angles.get(), size) != MIFI_OK)
             throw CDMException("Error during reprojection of vector-direction-values");
+    }
+    /** the rotation branch of CDMProcessor::getDataSlice (src/CDMProcessor.cc:579-617) on raw typed slices */
+    void getVectorSlice(fb200_datatype inType, const void* uIn, const void* vIn, size_t size, double badU, double badV, fb200_datatype outType,
+                        void* uOut, void* vOut) const
+    {
+        if (fb200_vector_get_slice(handle_, inType, uIn, vIn, size, badU, badV, outType, uOut, vOut) != MIFI_OK)
+            throw CDMException(std::string("Error during reprojection of vector-values: ") + fb200_last_error());
     }
     size_t getXSize() const { return static_cast<size_t>(ox); }
     size_t getYSize() const { return static_cast<size_t>(oy); }

@@ -267,6 +267,45 @@ static void test_get_data_slice()
     CHECK(bf[0] == 5.f && bf[1] == 2.5f);
 }
 
+// CDMProcessor::rotateVectorToLatLon on the mirror (makeCachedVectorReprojection, src/CDMProcessor.cc:99-145; test_rotate,
+// test/testProcessor.cc:71-93): on a polar-stereographic grid the components change, the speed does not, fill values survive
+static void test_rotate_vector_to_latlon()
+{
+    using namespace MetNoFimexB200;
+    const std::string proj = "+proj=stere +lat_0=90 +lon_0=0 +lat_ts=60 +units=m +a=6.371e+06 +e=0 +no_defs";
+    std::vector<double> x(11), y(11);
+    for (int i = 0; i < 11; ++i) {
+        x[i] = -1705516. + 50162. * i;
+        y[i] = -6872225. + 50162. * i;
+    }
+    CachedVectorReprojection cvr(MIFI_VECTOR_KEEP_SIZE, proj, x, y, false, true);
+    CHECK(cvr.getXSize() == 11 && cvr.getYSize() == 11);
+    std::vector<float> u(121), v(121), un(121), vn(121);
+    for (int i = 0; i < 121; ++i) {
+        u[i] = -3.f + 0.05f * i;
+        v[i] = -8.f - 0.02f * i;
+    }
+    u[7] = 9.96921e+36f;
+    cvr.getVectorSlice(FB200_FLOAT, u.data(), v.data(), 121, 9.9692099683868690e+36, 9.9692099683868690e+36, FB200_FLOAT, un.data(),
+                       vn.data());
+    CHECK(un[3] != u[3] && vn[3] != v[3]);
+    for (int i = 0; i < 121; ++i) {
+        if (i == 7)
+            continue;
+        const double a = (double)un[i] * un[i] + (double)vn[i] * vn[i], b = (double)u[i] * u[i] + (double)v[i] * v[i];
+        CHECK(std::fabs(a - b) < 1e-5 * b);
+    }
+    CHECK(un[7] == 9.96921e+36f && vn[7] == 9.96921e+36f);
+    // and back again
+    CachedVectorReprojection back(MIFI_VECTOR_KEEP_SIZE, proj, x, y, false, false);
+    std::vector<float> ub(121), vb(121);
+    back.getVectorSlice(FB200_FLOAT, un.data(), vn.data(), 121, 9.9692099683868690e+36, 9.9692099683868690e+36, FB200_FLOAT, ub.data(),
+                        vb.data());
+    for (int i = 0; i < 121; ++i)
+        if (i != 7)
+            CHECK(std::fabs(ub[i] - u[i]) < 2e-3 && std::fabs(vb[i] - v[i]) < 2e-3);
+}
+
 int main()
 {
     test_mifi_points2position();
@@ -279,6 +318,7 @@ int main()
     test_mifi_vector_reproject_values_rotate(180, 1e-5);
     test_cached_classes();
     test_get_data_slice();
+    test_rotate_vector_to_latlon();
     std::printf("%d checks, %d failures\n", checks, failures);
     return failures == 0 ? 0 : 1;
 }

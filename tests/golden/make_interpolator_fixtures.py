@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Extract the inputs of the reference's CDMInterpolator tests (test/testInterpolator.cc) into one small fixture.
+"""Extract the inputs of the reference's CDMInterpolator / CDMProcessor tests (test/testInterpolator.cc, test/testProcessor.cc)
+into one small fixture.
 
 The GPU box has no /root/reference and no NetCDF reader, so the arrays the reference's tests read from its own classic
 NetCDF-3 test files are stored in tests/golden/interpolator_fixtures.npz.  Only data is taken (coordinates, the fields the
@@ -42,6 +43,14 @@ def main():
     nc = netcdf_file(os.path.join(ref, "test/template_noaa17.nc"), "r", mmap=False)
     for name in ("longitude", "latitude"):
         out["tmpl_" + name] = native(nc.variables[name].data)
+
+    # test_rotate (test/testProcessor.cc:71-93): rotateAllVectorsToLatLon on the 10 m wind of coordTest.nc, first time step
+    nc = netcdf_file(os.path.join(ref, "test/coordTest.nc"), "r", mmap=False)
+    out["coord_proj4"] = np.array(nc.variables["projection_1"].proj4.decode())
+    for name in ("x", "y"):
+        out["coord_" + name] = native(nc.variables[name].data)
+    for name in ("x_wind_10m", "y_wind_10m"):
+        out["coord_" + name] = native(nc.variables[name].data[0])
 
     dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "interpolator_fixtures.npz")
     np.savez_compressed(dst, **out)

@@ -150,3 +150,68 @@ def test_interpolator_latlon(fx, oracle):
         interp.changeProjectionToLonLatValues(Method.BILINEAR, lon_vals, lat_vals[:-1])
     with pytest.raises(fb.FimexB200Error):
         interp.changeProjectionToLonLatValues(Method.FORWARD_MEAN, lon_vals, lat_vals)
+
+
+def test_processor_rotate(fx, oracle):
+    # test/testProcessor.cc:71-93: rotateAllVectorsToLatLon(true) on the 10 m wind of coordTest.nc; value 3 of each component
+    # changes, the speed does not (1e-4 percent)
+    proj = str(fx["coord_proj4"])
+    x, y = fx["coord_x"].astype(np.float64), fx["coord_y"].astype(np.float64)
+    xo, yo = fx["coord_x_wind_10m"], fx["coord_y_wind_10m"]
+    proc = fb.Processor(proj, x, y, False).rotateVectorToLatLon(True)
+    xn = proc.getDataSlice(xo, yo, "x")
+    yn = proc.getDataSlice(yo, xo, "y")
+    assert xn.dtype == np.float32 and xn.shape == xo.shape
+    assert xn.ravel()[3] != xo.ravel()[3] and yn.ravel()[3] != yo.ravel()[3]
+    a = float(xn.ravel()[3]) ** 2 + float(yn.ravel()[3]) ** 2
+    b = float(xo.ravel()[3]) ** 2 + float(yo.ravel()[3]) ** 2
+    assert abs(a - b) <= 1e-6 * max(a, b)
+    np.testing.assert_allclose(xn.astype(np.float64) ** 2 + yn.astype(np.float64) ** 2, xo.astype(np.float64) ** 2 + yo.astype(np.float64) ** 2,
+                               rtol=1e-5)
+    # against the oracle: matrix of the expanded mesh (makeCachedVectorReprojection, CDMProcessor.cc:124-135), then rotation
+    xf, yf = np.tile(x, y.size), np.repeat(y, x.size)
+    rc, m = oracle.vector_matrix_field(proj, WGS84, xf, yf, x.size, y.size)
+    assert rc == 1
+    got_m = proc.cachedVectorReprojection.getMatrix()
+    assert np.abs(got_m.reshape(-1, 4)[:, :3] - m.reshape(-1, 4)[:, :3]).max() < 1e-9
+    u, v = oracle.vector_reproject_by_matrix(got_m, xo.copy().ravel()[None], yo.copy().ravel()[None], x.size, y.size, 1)
+    assert_bit_equal(xn.ravel(), np.asarray(u).ravel(), "rotated x_wind_10m")
+    assert_bit_equal(yn.ravel(), np.asarray(v).ravel(), "rotated y_wind_10m")
+    # and back: geographic -> grid directions restores the wind
+    back = fb.Processor(proj, x, y, False).rotateVectorToLatLon(False)
+    xb, yb = back.getVectorSlices(xn, yn)
+    np.testing.assert_allclose(xb, xo, atol=2e-3)
+    np.testing.assert_allclose(yb, yo, atol=2e-3)
+    rc, m2 = oracle.vector_matrix(WGS84, proj, x, y, 0, 0)
+    assert rc == 1
+    assert np.abs(back.cachedVectorReprojection.getMatrix().reshape(-1, 4)[:, :3] - m2.reshape(-1, 4)[:, :3]).max() < 1e-9
+
+
+def test_processor_rotate_packed_short(oracle):
+    # the rotation branch on a packed variable: fill -> NaN, rotate the raw values, NaN -> fill, round to short
+    # (CDMProcessor.cc:604-616 with data2InterpolationArray / interpolationArray2Data)
+    rot = "+proj=ob_tran +o_proj=longlat +lon_0=-40 +o_lat_p=22 +R=6.371e+06 +no_defs"
+    x = -10 + 0.25 * np.arange(80)
+    y = -8 + 0.25 * np.arange(60)
+    rng = np.random.default_rng(5)
+    u = rng.integers(-3000, 3000, (3, y.size, x.size)).astype(np.int16)
+    v = rng.integers(-3000, 3000, (3, y.size, x.size)).astype(np.int16)
+    u[rng.random(u.shape) < 0.05] = -32767
+    v[rng.random(v.shape) < 0.05] = -32767
+    proc = fb.Processor(rot, x, y, True).rotateVectorToLatLon(True)
+    un, vn = proc.getVectorSlices(u, v)
+    assert un.dtype == np.int16 and un.shape == u.shape
+    m = proc.cachedVectorReprojection.getMatrix()
+    fu, fv = oracle.as_float(u, -32767), oracle.as_float(v, -32767)
+    ru, rv = oracle.vector_reproject_by_matrix(m, fu.reshape(3, -1), fv.reshape(3, -1), x.size, y.size, 3)
+    assert np.array_equal(un.ravel(), oracle.from_float(np.asarray(ru), -32767, np.int16).ravel())
+    assert np.array_equal(vn.ravel(), oracle.from_float(np.asarray(rv), -32767, np.int16).ravel())
+    mask = (u == -32767) | (v == -32767)
+    assert (un[mask] == -32767).all() and (vn[mask] == -32767).all()
+    # directions: same matrix through reprojectDirectionValues
+    ang = rng.uniform(0, 360, (2, y.size, x.size)).astype(np.float32)
+    got = proc.getDirectionSlice(ang)
+    want = oracle.vector_reproject_direction(m, ang.reshape(2, -1).copy(), x.size, y.size, 2)
+    assert_bit_equal(got.ravel(), np.asarray(want).ravel(), "rotated directions")
+    with pytest.raises(fb.FimexB200Error):
+        fb.Processor(rot, x, y, True).getVectorSlices(u, v)
