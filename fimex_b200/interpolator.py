@@ -110,6 +110,7 @@ class Interpolator:
         self.cachedVectorReprojection = None
         self.method = Method.UNKNOWN
         self.distanceOfInterest = 0.0  # CDMInterpolator::setDistanceOfInterest (metres; <= 0: derived from the output axes)
+        self._pair_cache = {}  # parked counterpart halves of x/y vector pairs, see getDataSlice(pair_key=...)
 
     # ---- setup --------------------------------------------------------------------------------
     def changeProjection(self, method, proj_input, out_x_axis, out_y_axis, out_x_axis_unit="m", out_y_axis_unit="m"):
@@ -121,6 +122,7 @@ class Interpolator:
             m = int(method)
         out_x = spatial_axis_spec(out_x_axis)
         out_y = spatial_axis_spec(out_y_axis)
+        self.clearPairCache()
         self.cachedInterpolation = None
         self.cachedVectorReprojection = None
         if m in (Method.NEAREST_NEIGHBOR, Method.BILINEAR, Method.BICUBIC):
@@ -172,6 +174,7 @@ class Interpolator:
         tmpl_lat = np.asarray(tmpl_lat, dtype=np.float64)
         if out_x is None or out_y is None:
             out_y, out_x = tmpl_lon.shape
+        self.clearPairCache()
         self.cachedInterpolation = None
         self.cachedVectorReprojection = None
         ci = CachedInterpolation.fromTemplate(m, MIFI_WGS84_LATLON_PROJ4, tmpl_lon.ravel(), tmpl_lat.ravel(), out_x, out_y, self.source_proj4,
@@ -209,11 +212,16 @@ class Interpolator:
                                                                               self.y_axis.size, self.x_dim, self.y_dim)
 
     # ---- per slice ------------------------------------------------------------------------------
-    def getDataSlice(self, data, bad_value=None, counterpart=None, direction="x", counterpart_bad_value=None):
+    def getDataSlice(self, data, bad_value=None, counterpart=None, direction="x", counterpart_bad_value=None, pair_key=None):
         """CDMInterpolator::getDataSlice for an in-memory slice [.., y, x] of the FULL source grid (:235-287):
         crop to the reduced domain, fill -> NaN, interpolate, [rotate with the counterpart component], NaN -> fill
         and cast back to the variable's type -- one C-ABI call, the adapters run inside the gather kernel.
-        `bad_value` = CDM::getFillValue(varName): the _FillValue attribute, else the type's default."""
+        `bad_value` = CDM::getFillValue(varName): the _FillValue attribute, else the type's default.
+
+        `pair_key` (any hashable naming the x/y pair and the slice, e.g. ("x_wind", "y_wind", unLimDimPos)): the reference
+        interpolates and rotates BOTH components on each component's call (:259-276) and throws one away; with a key the
+        other half is parked and handed out when the counterpart is asked for with the same key, so
+        the pair costs one pass instead of two.  A parked half is given out once; `clearPairCache()` drops what is left."""
         ci = self.cachedInterpolation
         if ci is None:
             raise FimexB200Error("no cached interpolation: call changeProjection first")
@@ -221,16 +229,34 @@ class Interpolator:
         if bad_value is None:
             bad_value = capi.default_fill_value(data.dtype)
         lead = data.shape[:-2]
-        arr = ci.getInputDataSlice(data)
         if counterpart is not None and self.cachedVectorReprojection is not None:
-            other = ci.getInputDataSlice(np.asarray(counterpart, dtype=data.dtype))
-            cbad = bad_value if counterpart_bad_value is None else counterpart_bad_value
             if "x" in direction:
-                out, _ = ci.getVectorSlice(arr, other, bad_value, cbad, self.cachedVectorReprojection)
+                want = 0
             elif "y" in direction:
-                _, out = ci.getVectorSlice(other, arr, cbad, bad_value, self.cachedVectorReprojection)
+                want = 1
             else:
                 raise FimexB200Error(f"could not find x,y direction for vector, direction: {direction}")
-        else:
-            out = ci.getDataSlice(arr, bad_value)
+            cache = self._pair_cache
+            if pair_key is not None and (pair_key, want) in cache:
+                return cache.pop((pair_key, want))
+            arr = ci.getInputDataSlice(data)
+            other = ci.getInputDataSlice(np.asarray(counterpart, dtype=data.dtype))
+            cbad = bad_value if counterpart_bad_value is None else counterpart_bad_value
+            if want == 0:
+                both = ci.getVectorSlice(arr, other, bad_value, cbad, self.cachedVectorReprojection)
+            else:
+                both = ci.getVectorSlice(other, arr, cbad, bad_value, self.cachedVectorReprojection)
+            shape = lead + (ci.getOutY(), ci.getOutX())
+            if pair_key is not None:
+                while len(cache) >= self.pairCacheSlots:  # bounded: oldest first
+                    cache.pop(next(iter(cache)))
+                cache[(pair_key, 1 - want)] = both[1 - want].reshape(shape)
+            return both[want].reshape(shape)
+        arr = ci.getInputDataSlice(data)
+        out = ci.getDataSlice(arr, bad_value)
         return out.reshape(lead + (ci.getOutY(), ci.getOutX()))
+
+    pairCacheSlots = 4  # parked counterpart slices kept at most (each is one output slice)
+
+    def clearPairCache(self):
+        self._pair_cache.clear()

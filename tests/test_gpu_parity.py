@@ -997,3 +997,38 @@ def test_interpolator_vector_backforth(case, wind):
     assert ok.sum() > 0.1 * ok.size, (int(ok.sum()), ok.size)  # hirlam8 covers only 338 of the 2556 lat/lon points
     assert np.abs(x2[ok] - wind[0]).max() < delta, float(np.abs(x2[ok] - wind[0]).max())
     assert np.abs(y2[ok] - wind[1]).max() < delta, float(np.abs(y2[ok] - wind[1]).max())
+
+
+def test_vector_pair_cache_serves_the_counterpart_without_a_second_pass():
+    # the reference interpolates and rotates both components on each component's call
+    # (CDMInterpolator.cc:259-276); with a pair key the second request is served from the parked half
+    lon, lat, _ = _config2_like(40)
+    rng = np.random.default_rng(21)
+    u = rng.normal(0, 10, (3, lat.size, lon.size)).astype(np.float32)
+    v = rng.normal(0, 10, (3, lat.size, lon.size)).astype(np.float32)
+    ax = (np.arange(50) - 24.5) * 0.5
+    interp = fb.Interpolator(SRC_LL, lon, lat, True, has_xy_vectors=True)
+    interp.changeProjection("bilinear", ROTPOLE, ax, ax, "degree", "degree")
+    plain_x = interp.getDataSlice(u, counterpart=v, direction="x")
+    plain_y = interp.getDataSlice(v, counterpart=u, direction="y")
+    n0 = fb.kernel_launches()
+    got_x = interp.getDataSlice(u, counterpart=v, direction="x", pair_key=("x_wind", "y_wind", 0))
+    n1 = fb.kernel_launches()
+    got_y = interp.getDataSlice(v, counterpart=u, direction="y", pair_key=("x_wind", "y_wind", 0))
+    n2 = fb.kernel_launches()
+    assert n1 > n0 and n2 == n1  # the second half launched nothing
+    assert_bit_equal(got_x, plain_x, "pair cache x")
+    assert_bit_equal(got_y, plain_y, "pair cache y")
+    # a parked half is handed out once; another slice (key) is computed afresh; y first works the same way
+    got_y2 = interp.getDataSlice(v, counterpart=u, direction="y", pair_key=("x_wind", "y_wind", 1))
+    assert fb.kernel_launches() > n2
+    n3 = fb.kernel_launches()
+    got_x2 = interp.getDataSlice(u, counterpart=v, direction="x", pair_key=("x_wind", "y_wind", 1))
+    assert fb.kernel_launches() == n3
+    assert_bit_equal(got_x2, plain_x, "pair cache x after y")
+    assert_bit_equal(got_y2, plain_y, "pair cache y first")
+    for k in range(10):  # bounded
+        interp.getDataSlice(u, counterpart=v, direction="x", pair_key=("x_wind", "y_wind", 100 + k))
+    assert len(interp._pair_cache) <= interp.pairCacheSlots
+    interp.changeProjection("bilinear", ROTPOLE, ax, ax, "degree", "degree")
+    assert not interp._pair_cache
