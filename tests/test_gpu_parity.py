@@ -1032,3 +1032,30 @@ def test_vector_pair_cache_serves_the_counterpart_without_a_second_pass():
     assert len(interp._pair_cache) <= interp.pairCacheSlots
     interp.changeProjection("bilinear", ROTPOLE, ax, ax, "degree", "degree")
     assert not interp._pair_cache
+
+
+@pytest.mark.parametrize("out_dtype", [np.int16, np.int32, np.uint8, np.uint16])
+def test_typed_store_rounding_is_exhaustive_per_exponent(oracle, out_dtype):
+    # interpolationArray2Data for integer targets is lround() narrowed to int (include/fimex/Utils.h:88-113, 444-464).  The
+    # staged store rounds values below 2^21 on the integer pipe and larger ones in fp64: every mantissa of a set of exponents
+    # either side of that switch, both signs, through the nearest-neighbour gather with an identity table
+    nx, ny = 4096, 2048  # 2^23 points per level: one exponent per level
+    px = np.tile(np.arange(nx, dtype=np.float64), ny)
+    py = np.repeat(np.arange(ny, dtype=np.float64), nx)
+    ci = fb.CachedInterpolation("x", "y", Method.NEAREST_NEIGHBOR, px, py, nx, ny, nx, ny)
+    mant = np.arange(1 << 23, dtype=np.uint32)
+    fill = fb.default_fill_value(out_dtype)
+    for exps in ((-3, -2, -1, 0), (1, 2, 7, 14), (15, 16, 19, 20), (21, 22, 23, 30)):
+        for sign in (0, 0x80000000):
+            bits = np.stack([((np.uint32(e + 127) << np.uint32(23)) | mant | np.uint32(sign)) for e in exps])
+            v = bits.view(np.float32).reshape(len(exps), ny, nx)
+            got = ci.getDataSlice(v, fill, outType=out_dtype)
+            want = oracle.from_float(v, fill, out_dtype)
+            assert np.array_equal(got.ravel(), want.ravel()), (exps, sign, out_dtype)
+    # NaN -> fill, zeros, ties and the float neighbours of the ties
+    ties = np.array([0.5, 1.5, 2.5, -0.5, -1.5, -2.5, 0.49999997, 0.50000006, -0.49999997, 1048575.5, 2097151.5, 2097152.0, 2097152.5, -2097151.5,
+                     4194303.5, 8388607.5, 0.0, -0.0, np.nan, 32767.5, -32768.5, 65535.5, 1e-45, -1e-45], np.float32)
+    v = np.zeros((1, ny, nx), np.float32)
+    v.ravel()[:ties.size] = ties
+    got = ci.getDataSlice(v, fill, outType=out_dtype)
+    assert np.array_equal(got.ravel(), oracle.from_float(v, fill, out_dtype).ravel())
