@@ -161,6 +161,80 @@ class Interpolator:
         lat32 = lat_vals.astype(np.float32).astype(np.float64)
         return self.changeProjectionToTemplate(method, lon32, lat32, lon_vals.size, 1)
 
+    # ---- Projection::convertFromLonLat / convertToLonLat (src/coordSys/Projection.cc:73-140) ------------------------------
+    def _latlong_of_source(self):
+        """"+proj=latlong " + getProj4EarthString() (ProjectionImpl.cc:139-159): a geographic CRS on the source's own earth
+        figure.  The reference assembles it from the CF grid-mapping attributes; here it is read back from the proj4 string."""
+        earth = [tok for tok in self.source_proj4.split()
+                 if tok.split("=")[0] in ("+a", "+b", "+rf", "+e", "+es", "+f", "+R", "+ellps", "+datum", "+towgs84")]
+        if not earth:
+            earth = [f"+a={MIFI_EARTH_RADIUS_M}", "+e=0"]  # default (:152)
+        return "+proj=latlong " + " ".join(earth)
+
+    def convertFromLonLat(self, lon, lat):
+        """degrees -> source projection coordinates (m, or degrees when the source isDegree)"""
+        x, y = np.radians(np.asarray(lon, dtype=np.float64)), np.radians(np.asarray(lat, dtype=np.float64))
+        ll = self._latlong_of_source()
+        if ll != self.source_proj4:
+            rc, x, y = capi.mifi_project_values(ll, self.source_proj4, x, y)
+            if rc != capi.MIFI_OK:
+                raise FimexB200Error(f"convertFromLonLat: unable to convert from '{ll}' to '{self.source_proj4}'")
+        return (np.degrees(x), np.degrees(y)) if self.is_degree else (x, y)
+
+    def convertToLonLat(self, x, y):
+        x, y = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
+        if self.is_degree:
+            x, y = np.radians(x), np.radians(y)
+        ll = self._latlong_of_source()
+        if ll != self.source_proj4:
+            rc, x, y = capi.mifi_project_values(self.source_proj4, ll, x, y)
+            if rc != capi.MIFI_OK:
+                raise FimexB200Error(f"convertToLonLat: unable to convert from '{self.source_proj4}' to '{ll}'")
+        return np.degrees(x), np.degrees(y)
+
+    def changeProjectionToCrossSections(self, method, cross_sections):
+        """CDMInterpolator::changeProjectionToCrossSections (:512-632).  `cross_sections`: [(name, [(lon, lat), ...]), ...] in
+        degrees.  Every leg is sampled in the SOURCE projection with about one point per grid cell (:564-582), the points go
+        back to lon/lat and become one point list (outY = 1).  Afterwards `vcross_names` and `vcross_bnds` (first and last
+        index, inclusive, per cross-section: the reference's vcross_bnds variable, :611-626) describe the list."""
+        if self.x_axis.size < 2 or self.y_axis.size < 2:
+            raise FimexB200Error("x- or y-axis sizes < 2 elements, not possible to interpolate")
+        dx = self.x_axis[1] - self.x_axis[0]
+        dy = self.y_axis[1] - self.y_axis[0]
+        if dx == 0 or dy == 0:
+            raise FimexB200Error("cross-section calculation: dx or dy derived from first two elements == 0")
+        lon_vals, lat_vals, starts, names = [], [], [], []
+        for name, lon_lat in cross_sections:
+            if len(lon_lat) == 0:
+                continue
+            names.append(name)
+            starts.append(len(lon_vals))
+            if len(lon_lat) == 1:
+                lon_vals.append(float(lon_lat[0][0]))
+                lat_vals.append(float(lon_lat[0][1]))
+                continue
+            for i in range(1, len(lon_lat)):
+                px, py = self.convertFromLonLat([lon_lat[i - 1][0], lon_lat[i][0]], [lon_lat[i - 1][1], lon_lat[i][1]])
+                xd, yd = px[1] - px[0], py[1] - py[0]
+                num = int(np.floor(max(abs(xd / dx), abs(yd / dy))))  # grid points between the two coordinates
+                xs, ys = [], []
+                if i == 1:  # the first point only once: it is the last point of the previous leg otherwise
+                    xs.append(px[0])
+                    ys.append(py[0])
+                for j in range(1, num):
+                    xs.append(px[0] + j * xd / num)
+                    ys.append(py[0] + j * yd / num)
+                xs.append(px[1])
+                ys.append(py[1])
+                lo, la = self.convertToLonLat(xs, ys)
+                lon_vals.extend(lo.tolist())
+                lat_vals.extend(la.tolist())
+        if not names:
+            raise FimexB200Error("no cross-section with coordinates")
+        self.vcross_names = names
+        self.vcross_bnds = [(starts[i], (starts[i + 1] if i + 1 < len(starts) else len(lon_vals)) - 1) for i in range(len(starts))]
+        return self.changeProjectionToLonLatValues(method, lon_vals, lat_vals)
+
     def changeProjectionToTemplate(self, method, tmpl_lon, tmpl_lat, out_x=None, out_y=None):
         """CDMInterpolator::changeProjection(method, tmplReader, tmplRefVarName) (:651-720) after the template's 2-D
         longitude/latitude (degrees, [y][x]) have been read by the host application ->

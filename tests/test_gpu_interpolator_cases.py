@@ -5,7 +5,7 @@ the reference's assertions and adds bit-parity with the oracle on the same input
 
 Not restated: test_interpolator / test_interpolatorKDTree / test_interpolatorRelative / test_interpolator_vectorlatlon need
 the optional flth00.dat (hasTestExtra(), absent from the reference tree); test_interpolatorNcml and
-test_interpolator_wrongaxes_latlon test NcML metadata; test_interpolator_vcross is the cross-section processor.
+test_interpolator_wrongaxes_latlon test NcML metadata.
 test_interpolator_vector_backforth is in test_gpu_parity.py.
 """
 import os
@@ -215,3 +215,51 @@ def test_processor_rotate_packed_short(oracle):
     assert_bit_equal(got.ravel(), np.asarray(want).ravel(), "rotated directions")
     with pytest.raises(fb.FimexB200Error):
         fb.Processor(rot, x, y, True).getVectorSlices(u, v)
+
+
+def test_interpolator_vcross(fx, oracle):
+    # test/testInterpolator.cc:474-497: two cross-sections over the 0.75-degree ERA-Interim field, bilinear
+    proj, lon, lat, skt = _erai(fx)
+    vc = [("OsloTrondheimTromso", [(10.74, 59.9), (10.3951, 63.4305), (18.9551, 69.6489)]),
+          ("BergenOslo", [(5.3290, 60.3983), (10.74, 59.9)])]
+    interp = fb.Interpolator(proj, lon, lat, True)
+    interp.changeProjectionToCrossSections(Method.BILINEAR, vc)
+    assert interp.vcross_names == ["OsloTrondheimTromso", "BergenOslo"] and len(interp.vcross_bnds) == 2  # nvcross == 2
+    ci = interp.cachedInterpolation
+    assert ci.getOutX() > 5 and ci.getOutY() == 1
+    # restated: legs sampled in the source CRS (degrees here: a lat/long grid), floor(max(|dx/0.75|, |dy/0.75|)) steps per leg
+    want_lon, want_lat, starts = [], [], []
+    for _, pts in vc:
+        starts.append(len(want_lon))
+        for i in range(1, len(pts)):
+            (x0, y0), (x1, y1) = pts[i - 1], pts[i]
+            num = int(np.floor(max(abs((x1 - x0) / (lon[1] - lon[0])), abs((y1 - y0) / (lat[1] - lat[0])))))
+            if i == 1:
+                want_lon.append(x0), want_lat.append(y0)
+            for j in range(1, num):
+                want_lon.append(x0 + j * (x1 - x0) / num), want_lat.append(y0 + j * (y1 - y0) / num)
+            want_lon.append(x1), want_lat.append(y1)
+    assert ci.getOutX() == len(want_lon)
+    assert interp.vcross_bnds == [(starts[0], starts[1] - 1), (starts[1], len(want_lon) - 1)]
+    # the source grid is itself lat/long on the same sphere, so the round trip through the projection is (nearly) the identity
+    tlon = np.asarray(want_lon, np.float32).astype(np.float64)
+    tlat = np.asarray(want_lat, np.float32).astype(np.float64)
+    got = interp.getDataSlice(skt)
+    assert got.shape == (8, 1, 1, len(want_lon))
+    want = _template_oracle(oracle, Method.BILINEAR, proj, lon, lat, tlon, tlat, len(want_lon), 1, skt)
+    fill = fb.default_fill_value(np.float64)
+    defined = want.ravel() != fill
+    assert defined.sum() >= 8 * 3  # only the Bergen end of the second section lies inside the 3..6.75 E x 57..64.5 N field
+    assert np.array_equal(got.ravel() != fill, defined)
+    np.testing.assert_allclose(got.ravel()[defined], want.ravel()[defined], rtol=1e-6)
+    # a projected source: the legs are straight in the projection plane, one point per 50 km cell
+    stere = "+proj=stere +lat_0=90 +lon_0=0 +lat_ts=60 +units=m +a=6.371e+06 +e=0 +no_defs"
+    x = -1705516 + 50162.0 * np.arange(40)
+    y = -6872225 + 50162.0 * np.arange(40)
+    ip = fb.Interpolator(stere, x, y, False)
+    ip.changeProjectionToCrossSections("bilinear", [("a", [(-13.0, 32.0), (-8.0, 44.0)]), ("p", [(-10.0, 40.0)])])
+    assert ip.vcross_bnds[1][0] == ip.vcross_bnds[1][1] == ip.cachedInterpolation.getOutX() - 1
+    gx, gy = ip.cachedInterpolation.points()
+    n = ip.vcross_bnds[0][1] + 1
+    assert n > 10 and np.abs(np.diff(gx[:n], 2)).max() < 1e-3 and np.abs(np.diff(gy[:n], 2)).max() < 1e-3  # equidistant in index space
+    assert np.hypot(np.diff(gx[:n]), np.diff(gy[:n])).max() <= 1.5
