@@ -27,9 +27,33 @@ __global__ void k_tiles(float* out, int ox, int oy, int nz, int chunk)
         for (int r = ly; r < TY; r += rows_per_pass) {
             if (VEC == 4)
                 __stcs(reinterpret_cast<float4*>(base + (size_t)r * ox), make_float4(1.f, 2.f, 3.f, (float)z));
+            else if (VEC == 2)
+                __stcs(reinterpret_cast<float2*>(base + (size_t)r * ox), make_float2(1.f, (float)z));
             else
                 __stcs(base + (size_t)r * ox, (float)z);
         }
+    }
+}
+
+
+// bilinear with an in-register 4x4 transpose: warp = 32 columns x 4 rows (rows 4 apart), lane L writes a float4 at columns
+// 4*(L>>2).., row (L&3): one STG.128 covers 4 rows x 128 B
+template <int TX, int TY>
+__global__ void k_tiles_tr(float* out, int ox, int oy, int nz, int chunk)
+{
+    const int tiles_x = ox / TX;
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    const int z0 = blockIdx.y * chunk, z1 = min(nz, z0 + chunk);
+    const int w = threadIdx.x >> 5, L = threadIdx.x & 31;
+    constexpr int segs = TX / 32;                 // warps side by side
+    const int lx = (w % segs) * 32 + 4 * (L >> 2);
+    const int ly = (w / segs) + (8 / segs) * (L & 3) ; // rows RowStep apart, RowStep = 8/segs
+    const size_t level = (size_t)ox * oy;
+    for (int z = z0; z < z1; ++z) {
+        float* base = out + z * level + (size_t)(ty * TY) * ox + tx * TX + lx;
+#pragma unroll
+        for (int r = ly; r < TY; r += 4 * (8 / segs))
+            __stcs(reinterpret_cast<float4*>(base + (size_t)r * ox), make_float4(1.f, 2.f, 3.f, (float)z));
     }
 }
 
@@ -76,6 +100,27 @@ int main()
         { dim3 g((ox / 32) * (oy / 32), (nz + chunk - 1) / chunk);
           ms = time_ms([&] { k_tiles<32, 32, 4><<<g, 256>>>(out, ox, oy, nz, chunk); });
           printf("tiles 32x32  float4 chunk %3d %8.3f ms %8.1f GB/s\n", chunk, ms, gb / ms * 1e3); }
+        { dim3 g((ox / 64) * (oy / 16), (nz + chunk - 1) / chunk);
+          ms = time_ms([&] { k_tiles<64, 16, 4><<<g, 256>>>(out, ox, oy, nz, chunk); });
+          printf("tiles 64x16  float4 chunk %3d %8.3f ms %8.1f GB/s\n", chunk, ms, gb / ms * 1e3); }
+        { dim3 g((ox / 64) * (oy / 16), (nz + chunk - 1) / chunk);
+          ms = time_ms([&] { k_tiles_tr<64, 16><<<g, 256>>>(out, ox, oy, nz, chunk); });
+          printf("tiles 64x16  transp chunk %3d %8.3f ms %8.1f GB/s\n", chunk, ms, gb / ms * 1e3); }
+        { dim3 g((ox / 128) * (oy / 8), (nz + chunk - 1) / chunk);
+          ms = time_ms([&] { k_tiles_tr<128, 8><<<g, 256>>>(out, ox, oy, nz, chunk); });
+          printf("tiles 128x8  transp chunk %3d %8.3f ms %8.1f GB/s\n", chunk, ms, gb / ms * 1e3); }
+        { dim3 g((ox / 256) * (oy / 4), (nz + chunk - 1) / chunk);
+          ms = time_ms([&] { k_tiles<256, 4, 1><<<g, 256>>>(out, ox, oy, nz, chunk); });
+          printf("tiles 256x4  scalar chunk %3d %8.3f ms %8.1f GB/s\n", chunk, ms, gb / ms * 1e3); }
+        { dim3 g((ox / 256) * (oy / 4), (nz + chunk - 1) / chunk);
+          ms = time_ms([&] { k_tiles<256, 4, 4><<<g, 256>>>(out, ox, oy, nz, chunk); });
+          printf("tiles 256x4  float4 chunk %3d %8.3f ms %8.1f GB/s\n", chunk, ms, gb / ms * 1e3); }
+        { dim3 g((ox / 64) * (oy / 16), (nz + chunk - 1) / chunk);
+          ms = time_ms([&] { k_tiles<64, 16, 2><<<g, 256>>>(out, ox, oy, nz, chunk); });
+          printf("tiles 64x16  float2 chunk %3d %8.3f ms %8.1f GB/s\n", chunk, ms, gb / ms * 1e3); }
+        { dim3 g((ox / 128) * (oy / 8), (nz + chunk - 1) / chunk);
+          ms = time_ms([&] { k_tiles<128, 8, 2><<<g, 256>>>(out, ox, oy, nz, chunk); });
+          printf("tiles 128x8  float2 chunk %3d %8.3f ms %8.1f GB/s\n", chunk, ms, gb / ms * 1e3); }
     }
     return 0;
 }
