@@ -33,14 +33,20 @@ namespace fb {
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kTilePts = 1024;
+#ifndef FB_CTA_THREADS
+#define FB_CTA_THREADS 256 // threads per CTA = quarter of the tile's points (experiments: -DFB_CTA_THREADS=128)
+#endif
+constexpr int kThreads = FB_CTA_THREADS;
+constexpr int kTilePts = 4 * kThreads;
 // Tile shapes (1024 target points, 4 per thread).  Measured on B200 (scratch/ubench/store_bw.cu, pure stores, 64-level
 // chunks): tiles whose rows are 128 B wide reach 5.66 TB/s, 256 B rows 6.35 TB/s, 512 B rows written with 128-bit stores
 // 7.1 TB/s -- the wider the contiguous run a CTA writes per row, the fewer DRAM pages are open at once.  The width a
 // bilinear warp can cover is limited by shared-memory banks instead: the 32 lanes of a load should see fewer than 32
 // distinct taps, i.e. span fewer than ~30 source cells.
-//   bilinear: 64 x 16, lane = x, thread t owns (t & 63, (t >> 6) + 4k): a row is written by two neighbouring warps
+//   bilinear: 64 x 16, lane = x, thread t owns (t & 63, (t >> 6) + 4k): a row is written by two neighbouring warps.  (Giving a
+//   thread two x-neighbours in each of two rows would let a warp write 256-byte row segments with 64-bit stores -- 7.1 TB/s in
+//   the store benchmark instead of 6.4 -- but its shared loads then see ~26 distinct taps per warp instead of ~13 and the
+//   kernel is 17 % slower: 13.1 ms against 11.2.)
 //   nearest neighbour: 128 x 8, thread t owns (4 (t & 31) + k, t >> 5): one 128-bit store per thread and level
 #ifndef FB_STAGE_BUFFERS
 #define FB_STAGE_BUFFERS 2 // staging buffers of the cp.async pipeline (experiments: -DFB_STAGE_BUFFERS=3)
@@ -61,11 +67,13 @@ struct Tile {
     static __device__ __forceinline__ int py(int t, int k) { return NN ? (t >> 5) : (t / X) + RowStep * k; }
 };
 constexpr int kMaxTaps = 4 * kTilePts;                              // worst case: every point has its own 4 taps
-constexpr int kStageFloats = 4096;                                  // one staging buffer (16 KB), two of them
+constexpr int kStageFloats = 16 * kThreads;                          // one staging buffer (16 KB), two of them
 constexpr int kMaxBatch = 8;                                        // levels staged per barrier
 constexpr int kNoTap = 0x7fffffff;
-constexpr int kLvlStride = kMaxBatch + 1;                            // tap-major staging: element (tap r, level zi) at r*9 + zi
-constexpr int kFastTaps = kStageFloats / kLvlStride;                // tiles with at most 455 taps use it (all but pole/seam tiles)
+// tap-major staging: element (tap r, level zi) at r*kLvlStride + zi.  12 words keep every tap 16-byte aligned, and the taps of
+// the 8 lanes of a quarter warp (consecutive r) start in banks 0, 12, 24, 4, 16, 28, 8, 20: four banks each, no conflict.
+constexpr int kLvlStride = 12;
+constexpr int kFastTaps = kStageFloats / kLvlStride;                // tiles with at most 341 taps use it (all but pole/seam tiles)
 
 // ------------------------------------------------------------------------------------------------ table compiler
 template <bool NN>
@@ -209,7 +217,7 @@ __device__ __forceinline__ void cp_async_wait_pending()
 // bad0 / bad1 become NaN before any point reads them).  NF = 2: both components of a vector through one table pass
 // (CDMInterpolator.cc:255-276), ROT: rotated in the epilogue (mifi_vector_reproject_values_by_matrix_f, interpolation.c:790-812).
 template <bool NN, int NF, bool ROT, class Out>
-__global__ void __launch_bounds__(kThreads, NF == 1 ? (NN ? FB_NN_CTAS : 3) : 2)
+__global__ void __launch_bounds__(kThreads, (NF == 1 ? (NN ? FB_NN_CTAS : 3) : 2) * (256 / kThreads))
     k_gather_bilinear_staged(GatherGeom g, int tiles_x, const int* __restrict__ taps, const int* __restrict__ ntaps_tab,
                              const uint4* __restrict__ meta, const float4* __restrict__ xf4, const float4* __restrict__ yf4,
                              const float* __restrict__ in0, const float* __restrict__ in1, typename Out::type* __restrict__ out0,
@@ -241,28 +249,29 @@ __global__ void __launch_bounds__(kThreads, NF == 1 ? (NN ? FB_NN_CTAS : 3) : 2)
         all_full = all_full && (mode[k] == (NN ? FB_BL_NEAR : FB_BL_FULL));
     }
     const int tx = tile % tiles_x, ty = tile / tiles_x;
-    // points k < nvalid of this thread exist (k runs along x for nearest neighbour, down the rows for bilinear)
+    // which of the thread's 4 points exist (the grid need not be a multiple of the tile), and their element offsets in a level
     const int x0 = tx * Tile<NN>::X + Tile<NN>::px(t, 0), y0 = ty * Tile<NN>::Y + Tile<NN>::py(t, 0);
+    const unsigned rstep = (unsigned)Tile<NN>::RowStep * (unsigned)g.ox; // bilinear: from point k to point k+1 of a thread
+    auto poff = [&](int k) -> unsigned { return NN ? (unsigned)k : (unsigned)k * rstep; };
+    // points k < nvalid exist (k runs along x for nearest neighbour, down the rows for bilinear)
     int nvalid = 0;
     if (y0 < g.oy && x0 < g.ox)
         nvalid = NN ? g.ox - x0 : (g.oy - y0 + Tile<NN>::RowStep - 1) / (NN ? 1 : Tile<NN>::RowStep);
-    nvalid = nvalid > 4 ? 4 : nvalid;
+    const unsigned vmask = nvalid >= 4 ? 0xfu : (1u << nvalid) - 1u;
     const long long per = (g.nz + gridDim.y - 1) / gridDim.y;
     const long long z0 = (long long)blockIdx.y * per;
     const long long z1 = z0 + per < g.nz ? z0 + per : g.nz;
-    // element offset of point 0 inside a level, and from point k to point k+1
-    const unsigned off0 = (unsigned)y0 * (unsigned)g.ox + (unsigned)x0;
-    const unsigned kstep = NN ? 1u : (unsigned)Tile<NN>::RowStep * (unsigned)g.ox;
+    const unsigned off0 = (unsigned)y0 * (unsigned)g.ox + (unsigned)x0; // point 0
     double2 rot[4];
     if (ROT) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            rot[k] = k < nvalid ? __ldg(cs + off0 + (unsigned)k * kstep) : make_double2(1., 0.);
+            rot[k] = ((vmask >> k) & 1u) ? __ldg(cs + off0 + poff(k)) : make_double2(1., 0.);
     }
-    // Two staging layouts.  fast: tap-major, element (tap r, level zi) at r*9 + zi -- a thread's eight row pointers are then
+    // Two staging layouts.  fast: tap-major, element (tap r, level zi) at r*12 + zi -- a thread's eight row pointers are then
     // constant for a whole batch and the level is an immediate offset of the shared load (no address arithmetic in the
-    // inner loop; 9 is odd, so any 32 taps with distinct r mod 32 still hit distinct banks).  Tiles with more than 455 taps
-    // (over the pole, across the seam) keep the level-major layout with as many levels per batch as fit.
+    // inner loop).  Tiles with more than 341 taps (over the pole, across the seam) keep the level-major layout with as many
+    // levels per batch as fit.
     const bool fast = ntaps <= kFastTaps;
     const int zb = fast ? kMaxBatch : (kStageFloats / ntaps);
     // the first staging element of this thread is the same for every level; larger tiles loop over the rest
@@ -344,12 +353,12 @@ __global__ void __launch_bounds__(kThreads, NF == 1 ? (NN ? FB_NN_CTAS : 3) : 2)
             patch(buf, nb);
         __syncthreads(); // batch z has landed for every thread, and every thread is done reading the buffer refilled next
         issue_or_skip(buf == 0 ? kBuffers - 1 : buf - 1, z + (long long)(kBuffers - 1) * zb);
-        if (nvalid == 0)
+        if (vmask == 0)
             continue;
         const float* lvl = stage(buf, 0);
         typename Out::type* base0 = out0 + z * g.out_level; // uniform across the CTA
         typename Out::type* base1 = NF == 2 ? out1 + z * g.out_level : nullptr;
-        if (fast && all_full && nvalid == 4) {
+        if (fast && all_full && vmask == 0xfu) {
             const float* pa[4];
             const float* pb[4];
 #pragma unroll
@@ -357,54 +366,67 @@ __global__ void __launch_bounds__(kThreads, NF == 1 ? (NN ? FB_NN_CTAS : 3) : 2)
                 pa[k] = lvl + ia[k] * kLvlStride;
                 pb[k] = lvl + ib[k] * kLvlStride;
             }
-            auto one_level = [&](int zi) {
-                float r[NF][4];
+            // Four levels at a time: the staged levels of a tap are contiguous, so one LDS.128 brings four of them -- a quarter
+            // of the load instructions (9 % fewer instructions overall).  The L1TEX cycles stay what they were: 4.45 shared-load
+            // wavefronts per 32 outputs and level either way (ncu), i.e. the merging of equal addresses that a 128-bit load
+            // shows in scratch/ubench/lds_width.cu does not happen for the irregular runs of equal taps a rotated grid produces.
+            auto quad = [&](int q, int nlev) {
+                float r[NF][4][4]; // [field][point][level]
 #pragma unroll
                 for (int f = 0; f < NF; ++f) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const float* qa = pa[k] + f * kStageFloats;
-                        const float* qb = pb[k] + f * kStageFloats;
+                        const float* qa = pa[k] + f * kStageFloats + 4 * q;
+                        const float* qb = pb[k] + f * kStageFloats + 4 * q;
                         if (NN) { // copied value, bit for bit (interpolation.c:869-871)
-                            r[f][k] = qa[zi];
+                            const float4 v = *reinterpret_cast<const float4*>(qa);
+                            r[f][k][0] = v.x, r[f][k][1] = v.y, r[f][k][2] = v.z, r[f][k][3] = v.w;
                         } else {
-                            const float s00 = qa[zi], s01 = qa[kLvlStride + zi], s10 = qb[zi], s11 = qb[kLvlStride + zi];
-                            const float top = __fadd_rn(__fmul_rn(wx0[k], s00), __fmul_rn(xf[k], s01));
-                            const float bot = __fadd_rn(__fmul_rn(wx0[k], s10), __fmul_rn(xf[k], s11));
-                            r[f][k] = __fadd_rn(__fmul_rn(wy0[k], top), __fmul_rn(yf[k], bot));
+                            const float4 a0 = *reinterpret_cast<const float4*>(qa), a1 = *reinterpret_cast<const float4*>(qa + kLvlStride);
+                            const float4 b0 = *reinterpret_cast<const float4*>(qb), b1 = *reinterpret_cast<const float4*>(qb + kLvlStride);
+                            r[f][k][0] = bilinear_full(wx0[k], xf[k], wy0[k], yf[k], a0.x, a1.x, b0.x, b1.x);
+                            r[f][k][1] = bilinear_full(wx0[k], xf[k], wy0[k], yf[k], a0.y, a1.y, b0.y, b1.y);
+                            r[f][k][2] = bilinear_full(wx0[k], xf[k], wy0[k], yf[k], a0.z, a1.z, b0.z, b1.z);
+                            r[f][k][3] = bilinear_full(wx0[k], xf[k], wy0[k], yf[k], a0.w, a1.w, b0.w, b1.w);
                         }
                     }
                 }
                 if (ROT) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        rotate_uv(r[0][k], r[NF - 1][k], rot[k].x, rot[k].y);
+#pragma unroll
+                        for (int l = 0; l < 4; ++l)
+                            rotate_uv(r[0][k][l], r[NF - 1][k][l], rot[k].x, rot[k].y);
                 }
 #pragma unroll
-                for (int f = 0; f < NF; ++f) {
-                    typename Out::type* dst = (f == 0 ? base0 : base1) + off0;
-                    if (NN && vec_ok) {
-                        store_vec4<typename Out::type>(dst, conv(r[f][0]), conv(r[f][1]), conv(r[f][2]), conv(r[f][3]));
-                    } else {
-                        __stcs(dst, conv(r[f][0]));
-                        __stcs(dst + kstep, conv(r[f][1]));
-                        __stcs(dst + 2 * kstep, conv(r[f][2]));
-                        __stcs(dst + 3 * kstep, conv(r[f][3]));
+                for (int l = 0; l < 4; ++l) {
+                    if (l < nlev) {
+#pragma unroll
+                        for (int f = 0; f < NF; ++f) {
+                            typename Out::type* dst = (f == 0 ? base0 : base1) + off0;
+                            if (NN && vec_ok) {
+                                store_vec4<typename Out::type>(dst, conv(r[f][0][l]), conv(r[f][1][l]), conv(r[f][2][l]), conv(r[f][3][l]));
+                            } else {
+                                __stcs(dst, conv(r[f][0][l]));
+                                __stcs(dst + poff(1), conv(r[f][1][l]));
+                                __stcs(dst + poff(2), conv(r[f][2][l]));
+                                __stcs(dst + poff(3), conv(r[f][3][l]));
+                            }
+                        }
+                        base0 += g.out_level;
+                        if (NF == 2)
+                            base1 += g.out_level;
                     }
                 }
-                base0 += g.out_level;
-                if (NF == 2)
-                    base1 += g.out_level;
             };
+            static_assert(kMaxBatch == 8, "two quads per batch");
             if (nb == kMaxBatch) { // full batch: no per-level test
-#pragma unroll
-                for (int zi = 0; zi < kMaxBatch; ++zi)
-                    one_level(zi);
-            } else {
-#pragma unroll
-                for (int zi = 0; zi < kMaxBatch; ++zi)
-                    if (zi < nb)
-                        one_level(zi);
+                quad(0, 4);
+                quad(1, 4);
+            } else { // levels past nb hold stale values of an earlier batch: computed, never stored
+                quad(0, nb < 4 ? nb : 4);
+                if (nb > 4)
+                    quad(1, nb - 4);
             }
         } else { // grid edge, partial tile or a tile with many taps: per-point mode (interpolation.c:904-953)
             const int sr = fast ? kLvlStride : 1;      // stride between neighbouring taps
@@ -440,10 +462,10 @@ __global__ void __launch_bounds__(kThreads, NF == 1 ? (NN ? FB_NN_CTAS : 3) : 2)
                     }
                     if (ROT)
                         rotate_uv(v[0], v[NF - 1], rot[k].x, rot[k].y);
-                    if (k < nvalid) {
-                        __stcs(base0 + off0 + (unsigned)k * kstep, conv(v[0]));
+                    if ((vmask >> k) & 1u) {
+                        __stcs(base0 + off0 + poff(k), conv(v[0]));
                         if (NF == 2)
-                            __stcs(base1 + off0 + (unsigned)k * kstep, conv(v[NF - 1]));
+                            __stcs(base1 + off0 + poff(k), conv(v[NF - 1]));
                     }
                 }
                 base0 += g.out_level;
