@@ -366,28 +366,38 @@ __global__ void __launch_bounds__(kThreads, (NF == 1 ? (NN ? FB_NN_CTAS : 3) : 2
                 pa[k] = lvl + ia[k] * kLvlStride;
                 pb[k] = lvl + ib[k] * kLvlStride;
             }
-            // Four levels at a time: the staged levels of a tap are contiguous, so one LDS.128 brings four of them -- a quarter
+            // Several levels at a time: the staged levels of a tap are contiguous, so one LDS.128 brings four of them -- a quarter
             // of the load instructions (9 % fewer instructions overall).  The L1TEX cycles stay what they were: 4.45 shared-load
             // wavefronts per 32 outputs and level either way (ncu), i.e. the merging of equal addresses that a 128-bit load
             // shows in scratch/ubench/lds_width.cu does not happen for the irregular runs of equal taps a rotated grid produces.
-            auto quad = [&](int q, int nlev) {
-                float r[NF][4][4]; // [field][point][level]
+            // LV levels per step: 4 for a scalar field; 2 for a vector pair, whose 2 x 4 x LV results (and the fp64 rotation)
+            // have to fit the 128 registers of 2 CTAs per SM
+            constexpr int LV = NF == 1 ? 4 : 2;
+            auto ldv = [](const float* p, float (&v)[LV]) {
+                if constexpr (LV == 4) {
+                    const float4 t4 = *reinterpret_cast<const float4*>(p);
+                    v[0] = t4.x, v[1] = t4.y, v[2] = t4.z, v[3] = t4.w;
+                } else {
+                    const float2 t2 = *reinterpret_cast<const float2*>(p);
+                    v[0] = t2.x, v[1] = t2.y;
+                }
+            };
+            auto step = [&](int q, int nlev) { // levels LV*q .. LV*q + LV-1 of the batch, the first nlev of them are stored
+                float r[NF][4][LV]; // [field][point][level]
 #pragma unroll
                 for (int f = 0; f < NF; ++f) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const float* qa = pa[k] + f * kStageFloats + 4 * q;
-                        const float* qb = pb[k] + f * kStageFloats + 4 * q;
+                        const float* qa = pa[k] + f * kStageFloats + LV * q;
+                        const float* qb = pb[k] + f * kStageFloats + LV * q;
                         if (NN) { // copied value, bit for bit (interpolation.c:869-871)
-                            const float4 v = *reinterpret_cast<const float4*>(qa);
-                            r[f][k][0] = v.x, r[f][k][1] = v.y, r[f][k][2] = v.z, r[f][k][3] = v.w;
+                            ldv(qa, r[f][k]);
                         } else {
-                            const float4 a0 = *reinterpret_cast<const float4*>(qa), a1 = *reinterpret_cast<const float4*>(qa + kLvlStride);
-                            const float4 b0 = *reinterpret_cast<const float4*>(qb), b1 = *reinterpret_cast<const float4*>(qb + kLvlStride);
-                            r[f][k][0] = bilinear_full(wx0[k], xf[k], wy0[k], yf[k], a0.x, a1.x, b0.x, b1.x);
-                            r[f][k][1] = bilinear_full(wx0[k], xf[k], wy0[k], yf[k], a0.y, a1.y, b0.y, b1.y);
-                            r[f][k][2] = bilinear_full(wx0[k], xf[k], wy0[k], yf[k], a0.z, a1.z, b0.z, b1.z);
-                            r[f][k][3] = bilinear_full(wx0[k], xf[k], wy0[k], yf[k], a0.w, a1.w, b0.w, b1.w);
+                            float a0[LV], a1[LV], b0[LV], b1[LV];
+                            ldv(qa, a0), ldv(qa + kLvlStride, a1), ldv(qb, b0), ldv(qb + kLvlStride, b1);
+#pragma unroll
+                            for (int l = 0; l < LV; ++l)
+                                r[f][k][l] = bilinear_full(wx0[k], xf[k], wy0[k], yf[k], a0[l], a1[l], b0[l], b1[l]);
                         }
                     }
                 }
@@ -395,11 +405,11 @@ __global__ void __launch_bounds__(kThreads, (NF == 1 ? (NN ? FB_NN_CTAS : 3) : 2
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
 #pragma unroll
-                        for (int l = 0; l < 4; ++l)
+                        for (int l = 0; l < LV; ++l)
                             rotate_uv(r[0][k][l], r[NF - 1][k][l], rot[k].x, rot[k].y);
                 }
 #pragma unroll
-                for (int l = 0; l < 4; ++l) {
+                for (int l = 0; l < LV; ++l) {
                     if (l < nlev) {
 #pragma unroll
                         for (int f = 0; f < NF; ++f) {
@@ -419,14 +429,17 @@ __global__ void __launch_bounds__(kThreads, (NF == 1 ? (NN ? FB_NN_CTAS : 3) : 2
                     }
                 }
             };
-            static_assert(kMaxBatch == 8, "two quads per batch");
+            static_assert(kMaxBatch % LV == 0, "whole steps per batch");
+            // (vector pairs: a real loop -- unrolled, the scheduler hoists the loads of later steps and spills)
             if (nb == kMaxBatch) { // full batch: no per-level test
-                quad(0, 4);
-                quad(1, 4);
+#pragma unroll(NF == 1 ? kMaxBatch / LV : 1)
+                for (int q = 0; q < kMaxBatch / LV; ++q)
+                    step(q, LV);
             } else { // levels past nb hold stale values of an earlier batch: computed, never stored
-                quad(0, nb < 4 ? nb : 4);
-                if (nb > 4)
-                    quad(1, nb - 4);
+#pragma unroll(NF == 1 ? kMaxBatch / LV : 1)
+                for (int q = 0; q < kMaxBatch / LV; ++q)
+                    if (LV * q < nb)
+                        step(q, nb - LV * q);
             }
         } else { // grid edge, partial tile or a tile with many taps: per-point mode (interpolation.c:904-953)
             const int sr = fast ? kLvlStride : 1;      // stride between neighbouring taps
