@@ -370,9 +370,9 @@ __global__ void __launch_bounds__(kThreads, (NF == 1 ? (NN ? FB_NN_CTAS : 3) : 2
             // of the load instructions (9 % fewer instructions overall).  The L1TEX cycles stay what they were: 4.45 shared-load
             // wavefronts per 32 outputs and level either way (ncu), i.e. the merging of equal addresses that a 128-bit load
             // shows in scratch/ubench/lds_width.cu does not happen for the irregular runs of equal taps a rotated grid produces.
-            // LV levels per step: 4 for a scalar field; 2 for a vector pair, whose 2 x 4 x LV results (and the fp64 rotation)
+            // LV levels per step: 4; 2 for a rotated vector pair, whose 2 x 4 x LV results and the fp64 rotation
             // have to fit the 128 registers of 2 CTAs per SM
-            constexpr int LV = NF == 1 ? 4 : 2;
+            constexpr int LV = (NF == 2 && ROT) ? 2 : 4;
             auto ldv = [](const float* p, float (&v)[LV]) {
                 if constexpr (LV == 4) {
                     const float4 t4 = *reinterpret_cast<const float4*>(p);
@@ -430,13 +430,13 @@ __global__ void __launch_bounds__(kThreads, (NF == 1 ? (NN ? FB_NN_CTAS : 3) : 2
                 }
             };
             static_assert(kMaxBatch % LV == 0, "whole steps per batch");
-            // (vector pairs: a real loop -- unrolled, the scheduler hoists the loads of later steps and spills)
+            // (rotated vector pairs: a real loop -- unrolled, the scheduler hoists the loads of later steps and spills)
             if (nb == kMaxBatch) { // full batch: no per-level test
-#pragma unroll(NF == 1 ? kMaxBatch / LV : 1)
+#pragma unroll((NF == 2 && ROT) ? 1 : kMaxBatch / LV)
                 for (int q = 0; q < kMaxBatch / LV; ++q)
                     step(q, LV);
             } else { // levels past nb hold stale values of an earlier batch: computed, never stored
-#pragma unroll(NF == 1 ? kMaxBatch / LV : 1)
+#pragma unroll((NF == 2 && ROT) ? 1 : kMaxBatch / LV)
                 for (int q = 0; q < kMaxBatch / LV; ++q)
                     if (LV * q < nb)
                         step(q, nb - LV * q);
