@@ -57,6 +57,34 @@ __global__ void k_tiles_tr(float* out, int ox, int oy, int nz, int chunk)
     }
 }
 
+
+// like k_tiles<TX, TY, VEC>, but every row of the tile is shifted left so that the warp stores start on 128-byte boundaries
+template <int TX, int TY, int VEC>
+__global__ void k_tiles_al(float* out, int ox, int oy, int nz, int chunk)
+{
+    const int tiles_x = (ox + 31 + TX - 1) / TX;
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    const int z0 = blockIdx.y * chunk, z1 = min(nz, z0 + chunk);
+    constexpr int per_row = TX / VEC;
+    constexpr int rows_per_pass = 256 / per_row;
+    const int lx = (threadIdx.x % per_row) * VEC, ly = threadIdx.x / per_row;
+    const size_t level = (size_t)ox * oy;
+    for (int z = z0; z < z1; ++z) {
+#pragma unroll
+        for (int r = ly; r < TY; r += rows_per_pass) {
+            const int y = ty * TY + r;
+            const int x = tx * TX + lx - (int)(((size_t)y * ox) & 31);
+            if (x >= 0 && x + VEC <= ox && y < oy) {
+                float* p = out + z * level + (size_t)y * ox + x;
+                if (VEC == 4)
+                    __stcs(reinterpret_cast<float4*>(p), make_float4(1.f, 2.f, 3.f, (float)z));
+                else
+                    __stcs(p, (float)z);
+            }
+        }
+    }
+}
+
 template <class F>
 float time_ms(F f, int reps = 5)
 {
@@ -71,9 +99,10 @@ float time_ms(F f, int reps = 5)
     return ms / reps;
 }
 
-int main()
+int main(int argc, char** argv)
 {
-    const int ox = 2000 / 128 * 128 + 128 == 2048 ? 2048 : 2048, oy = 2016, nz = 1644; // 2048 x 2016 x 1644 floats = 27 GB
+    const int ox = argc > 1 ? atoi(argv[1]) : 2048, oy = 2016, nz = 1644; // row pitch 4*ox bytes: 2000 -> rows start on 64-byte, not 128-byte, boundaries
+    printf("ox = %d (row pitch %d B)\n", ox, 4 * ox); // 2048 x 2016 x 1644 floats = 27 GB
     const size_t n = (size_t)ox * oy * nz;
     float* out; CK(cudaMalloc(&out, n * 4));
     float* in; CK(cudaMalloc(&in, n * 4));
@@ -121,6 +150,12 @@ int main()
         { dim3 g((ox / 128) * (oy / 8), (nz + chunk - 1) / chunk);
           ms = time_ms([&] { k_tiles<128, 8, 2><<<g, 256>>>(out, ox, oy, nz, chunk); });
           printf("tiles 128x8  float2 chunk %3d %8.3f ms %8.1f GB/s\n", chunk, ms, gb / ms * 1e3); }
+        { dim3 g(((ox + 31 + 63) / 64) * (oy / 16), (nz + chunk - 1) / chunk);
+          ms = time_ms([&] { k_tiles_al<64, 16, 1><<<g, 256>>>(out, ox, oy, nz, chunk); });
+          printf("tiles 64x16  scalar ALIGNED %3d %8.3f ms %8.1f GB/s\n", chunk, ms, gb / ms * 1e3); }
+        { dim3 g(((ox + 31 + 127) / 128) * (oy / 8), (nz + chunk - 1) / chunk);
+          ms = time_ms([&] { k_tiles_al<128, 8, 4><<<g, 256>>>(out, ox, oy, nz, chunk); });
+          printf("tiles 128x8  float4 ALIGNED %3d %8.3f ms %8.1f GB/s\n", chunk, ms, gb / ms * 1e3); }
     }
     return 0;
 }
