@@ -326,28 +326,61 @@ __device__ __forceinline__ void load_group(Group& gr, const uint4* __restrict__ 
     }
 }
 
-// NL levels of one group: 4 points x NF fields x NL levels = 4*NF*NL independent accumulator chains for the scheduler
-template <int NF, bool ROT, int S, int NL>
+// NL levels of one group: 4 points x NF fields x NL levels = 4*NF*NL independent accumulator chains for the scheduler.
+// EXACT: the reference's operation order, every multiply and add rounded separately and the accumulator re-rounded to fp32
+// after each stencil row (35 fp64 instructions + 7 conversions per output).  !EXACT (opt-in, FIMEX_B200_BICUBIC_CONTRACT=1):
+// the same sums as fp64 FMA chains with ONE final rounding to fp32 (20 fp64 instructions + 1 conversion) -- not bit-identical,
+// within 1e-5 of the field's magnitude (the tolerance the north star states for interpolated floats), since every
+// intermediate is at least as accurate as the reference's.
+template <int NF, bool ROT, int S, int NL, bool EXACT>
 __device__ __forceinline__ void compute_levels(const Group& gr, const double* __restrict__ st, int field_stride, float* __restrict__ s_out,
                                                int out_field_stride, const double2* __restrict__ s_cs)
 {
     float a[NL][NF][4];
+    if (EXACT) {
 #pragma unroll
-    for (int f = 0; f < NF; ++f) {
-        const double* sf = st + f * field_stride;
+        for (int f = 0; f < NF; ++f) {
+            const double* sf = st + f * field_stride;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const double* rp = sf + gr.row[r];
+            for (int r = 0; r < 4; ++r) {
+                const double* rp = sf + gr.row[r];
 #pragma unroll
-            for (int l = 0; l < NL; ++l) {
-                const double v0 = rp[l], v1 = rp[S + l], v2 = rp[2 * S + l], v3 = rp[3 * S + l];
+                for (int l = 0; l < NL; ++l) {
+                    const double v0 = rp[l], v1 = rp[S + l], v2 = rp[2 * S + l], v3 = rp[3 * S + l];
 #pragma unroll
-                for (int p = 0; p < 4; ++p) {
-                    const double row = bicubic_row(gr.wx[p], v0, v1, v2, v3);
-                    a[l][f][p] = (r == 0) ? bicubic_acc<true>(0.f, row, gr.wy[p][0]) : bicubic_acc<false>(a[l][f][p], row, gr.wy[p][r]);
+                    for (int p = 0; p < 4; ++p) {
+                        const double row = bicubic_row(gr.wx[p], v0, v1, v2, v3);
+                        a[l][f][p] = (r == 0) ? bicubic_acc<true>(0.f, row, gr.wy[p][0]) : bicubic_acc<false>(a[l][f][p], row, gr.wy[p][r]);
+                    }
                 }
             }
         }
+    } else {
+        double d[NL][NF][4];
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            const double* sf = st + f * field_stride;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const double* rp = sf + gr.row[r];
+#pragma unroll
+                for (int l = 0; l < NL; ++l) {
+                    const double v0 = rp[l], v1 = rp[S + l], v2 = rp[2 * S + l], v3 = rp[3 * S + l];
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        const double row = fma(gr.wx[p][3], v3, fma(gr.wx[p][2], v2, fma(gr.wx[p][1], v1, gr.wx[p][0] * v0)));
+                        d[l][f][p] = (r == 0) ? row * gr.wy[p][0] : fma(row, gr.wy[p][r], d[l][f][p]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int l = 0; l < NL; ++l)
+#pragma unroll
+            for (int f = 0; f < NF; ++f)
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+                    a[l][f][p] = (float)d[l][f][p];
     }
     if (ROT) {
 #pragma unroll
@@ -445,7 +478,7 @@ __device__ void direct_tile(const GatherGeom& g, int tx, int ty, long long z0, l
 // FAST: at most 256 taps; 8/NF levels per batch; warp w stages (field, level) row w of the batch and later stores
 //       (field, level) row w of the output tile.
 // else: up to 2048/NF taps, one level per batch, every thread stages 8/NF taps per field.
-template <int NF, bool ROT, bool FAST, class Out>
+template <int NF, bool ROT, bool FAST, class Out, bool EXACT>
 __device__ __forceinline__ void staged_tile(const GatherGeom& g, int tx, int ty, long long z0, long long z1, int4 inf,
                                             const int* __restrict__ taps, const uint4* __restrict__ gmeta, const double2* __restrict__ gfrac,
                                             const double2* __restrict__ cs, const float* __restrict__ in0, const float* __restrict__ in1,
@@ -575,11 +608,11 @@ __device__ __forceinline__ void staged_tile(const GatherGeom& g, int tx, int ty,
                 if (L > 1 && nb == L) { // full batch: branch-free, two levels per step
 #pragma unroll kBicUnroll
                     for (int zi = 0; zi < L; zi += kNL)
-                        compute_levels<NF, ROT, S, (L > 1 ? kNL : 1)>(gr, st + zi, field_stride, tile + zi * kOutRow, L * kOutRow, s_cs);
+                        compute_levels<NF, ROT, S, (L > 1 ? kNL : 1), EXACT>(gr, st + zi, field_stride, tile + zi * kOutRow, L * kOutRow, s_cs);
                 } else {
 #pragma unroll 1
                     for (int zi = 0; zi < nb; ++zi)
-                        compute_levels<NF, ROT, S, 1>(gr, st + zi, field_stride, tile + zi * kOutRow, L * kOutRow, s_cs);
+                        compute_levels<NF, ROT, S, 1, EXACT>(gr, st + zi, field_stride, tile + zi * kOutRow, L * kOutRow, s_cs);
                 }
             }
         }
@@ -594,7 +627,7 @@ __device__ __forceinline__ void staged_tile(const GatherGeom& g, int tx, int ty,
     }
 }
 
-template <int NF, bool ROT, class Out>
+template <int NF, bool ROT, class Out, bool EXACT>
 __global__ void __launch_bounds__(kT, 2) k_gather_bicubic_staged(GatherGeom g, int tiles_x, const int4* __restrict__ info,
                                                                  const int* __restrict__ taps, const uint4* __restrict__ gmeta,
                                                                  const double2* __restrict__ gfrac, const int* __restrict__ off_tab,
@@ -617,10 +650,10 @@ __global__ void __launch_bounds__(kT, 2) k_gather_bicubic_staged(GatherGeom g, i
     if (inf.y < 0 || NF * inf.y > kStageElems)
         direct_tile<NF, ROT, Out>(g, tx, ty, z0, z1, off_tab, frac_tab, cs, in0, in1, out0, out1, conv, fill_in != 0, bad0, bad1);
     else if (inf.y <= kFastTaps)
-        staged_tile<NF, ROT, true, Out>(g, tx, ty, z0, z1, inf, taps, gmeta, gfrac, cs, in0, in1, out0, out1, vec_ok != 0, s_stage, s_out, s_cs,
+        staged_tile<NF, ROT, true, Out, EXACT>(g, tx, ty, z0, z1, inf, taps, gmeta, gfrac, cs, in0, in1, out0, out1, vec_ok != 0, s_stage, s_out, s_cs,
                                         conv, fill_in != 0, bad0, bad1);
     else
-        staged_tile<NF, ROT, false, Out>(g, tx, ty, z0, z1, inf, taps, gmeta, gfrac, cs, in0, in1, out0, out1, vec_ok != 0, s_stage, s_out,
+        staged_tile<NF, ROT, false, Out, EXACT>(g, tx, ty, z0, z1, inf, taps, gmeta, gfrac, cs, in0, in1, out0, out1, vec_ok != 0, s_stage, s_out,
                                          s_cs, conv, fill_in != 0, bad0, bad1);
 }
 
@@ -704,17 +737,25 @@ int bicubic_tiles_build(const int* d_off, const double2* d_frac, int ix, int iy,
 }
 
 namespace {
-template <int NF, bool ROT, class Out>
+template <int NF, bool ROT, class Out, bool EXACT = true>
 int launch_bic(dim3 grid, size_t smem, const GatherGeom& g, const BicubicTiles& bt, const int* d_off, const double2* d_frac, const double2* d_cs,
                const float* d_in0, const float* d_in1, void* d_out0, void* d_out1, int vec_ok, long long per, Out conv, const SliceConv& sc,
                cudaStream_t st)
 {
     typedef typename Out::type T;
-    FB_CUDA_CHECK(cudaFuncSetAttribute(k_gather_bicubic_staged<NF, ROT, Out>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_gather_bicubic_staged<NF, ROT, Out><<<grid, kT, smem, st>>>(g, bt.tiles_x, bt.d_info, bt.d_taps, bt.d_gmeta, bt.d_gfrac, d_off, d_frac, d_cs,
-                                                                  d_in0, d_in1, static_cast<T*>(d_out0), static_cast<T*>(d_out1), vec_ok, per,
-                                                                  conv, sc.fill_in ? 1 : 0, sc.bad_in[0], sc.bad_in[1]);
+    FB_CUDA_CHECK(cudaFuncSetAttribute(k_gather_bicubic_staged<NF, ROT, Out, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_gather_bicubic_staged<NF, ROT, Out, EXACT><<<grid, kT, smem, st>>>(g, bt.tiles_x, bt.d_info, bt.d_taps, bt.d_gmeta, bt.d_gfrac, d_off, d_frac,
+                                                                         d_cs, d_in0, d_in1, static_cast<T*>(d_out0), static_cast<T*>(d_out1),
+                                                                         vec_ok, per, conv, sc.fill_in ? 1 : 0, sc.bad_in[0], sc.bad_in[1]);
     return FB_OK;
+}
+
+// FIMEX_B200_BICUBIC_CONTRACT=1: fp64 FMA chains with one final rounding instead of the reference's operation order (plain float
+// output only; see compute_levels).  Read at every launch, default off: the shipped behaviour is bit-identical to the reference.
+bool bicubic_contract()
+{
+    const char* env = std::getenv("FIMEX_B200_BICUBIC_CONTRACT");
+    return env && env[0] == '1';
 }
 } // namespace
 
@@ -747,12 +788,22 @@ int launch_gather_bicubic_staged(const GatherGeom& g, const BicubicTiles& bt, co
     const uintptr_t align = reinterpret_cast<uintptr_t>(d_out0) | (two ? reinterpret_cast<uintptr_t>(d_out1) : 0);
     const int vec_ok = ((g.ox % 4) == 0 && (align & (4 * elem - 1)) == 0) ? 1 : 0;
     int rc = FB_ERROR;
+    const bool contract = bicubic_contract();
     if (two) {
         FB_REQUIRE(!sc.convert_out, "bicubic vector gather writes plain floats");
-        if (d_cs)
+        if (d_cs && contract)
+            rc = launch_bic<2, true, StorePlain, false>(grid, kGatherSmemRot, g, bt, d_off, d_frac, d_cs, d_in0, d_in1, d_out0, d_out1, vec_ok, per,
+                                                        StorePlain(), sc, st);
+        else if (d_cs)
             rc = launch_bic<2, true>(grid, kGatherSmemRot, g, bt, d_off, d_frac, d_cs, d_in0, d_in1, d_out0, d_out1, vec_ok, per, StorePlain(), sc, st);
+        else if (contract)
+            rc = launch_bic<2, false, StorePlain, false>(grid, kGatherSmem, g, bt, d_off, d_frac, d_cs, d_in0, d_in1, d_out0, d_out1, vec_ok, per,
+                                                         StorePlain(), sc, st);
         else
             rc = launch_bic<2, false>(grid, kGatherSmem, g, bt, d_off, d_frac, d_cs, d_in0, d_in1, d_out0, d_out1, vec_ok, per, StorePlain(), sc, st);
+    } else if (!sc.convert_out && contract) {
+        rc = launch_bic<1, false, StorePlain, false>(grid, kGatherSmem, g, bt, d_off, d_frac, d_cs, d_in0, d_in1, d_out0, d_out1, vec_ok, per,
+                                                     StorePlain(), sc, st);
     } else if (!sc.convert_out) {
         rc = launch_bic<1, false>(grid, kGatherSmem, g, bt, d_off, d_frac, d_cs, d_in0, d_in1, d_out0, d_out1, vec_ok, per, StorePlain(), sc, st);
     } else {

@@ -1059,3 +1059,34 @@ def test_typed_store_rounding_is_exhaustive_per_exponent(oracle, out_dtype):
     v.ravel()[:ties.size] = ties
     got = ci.getDataSlice(v, fill, outType=out_dtype)
     assert np.array_equal(got.ravel(), oracle.from_float(v, fill, out_dtype).ravel())
+
+
+def test_bicubic_contracted_mode_is_opt_in_and_within_tolerance(oracle, monkeypatch):
+    # FIMEX_B200_BICUBIC_CONTRACT=1 evaluates the bicubic sums as fp64 FMA chains with one final rounding to float (20 fp64
+    # instructions per value instead of 35): not bit-identical, but inside the 1e-5 relative bar the north star states for
+    # interpolated floats.  Default (unset) stays bit-identical to the reference.
+    lon, lat, ax = _config2_like(300)
+    rng = np.random.default_rng(8)
+    field = rng.normal(250, 30, (9, lat.size, lon.size)).astype(np.float32)
+    u = rng.normal(0, 12, (3, lat.size, lon.size)).astype(np.float32)
+    v = rng.normal(0, 12, (3, lat.size, lon.size)).astype(np.float32)
+    ci = fb.CachedInterpolation.fromProjection(Method.BICUBIC, ROTPOLE, ax, ax, True, True, SRC_LL, lon, lat, True)
+    cvr = fb.CachedVectorReprojection.fromProjection(fb.MIFI_VECTOR_KEEP_SIZE, SRC_LL, ROTPOLE, ax, ax, fb.LONGITUDE, fb.LATITUDE)
+    monkeypatch.delenv("FIMEX_B200_BICUBIC_CONTRACT", raising=False)
+    exact = ci.interpolateValues(field)
+    eu, ev = ci.interpolateVector(u, v, cvr)
+    gx, gy = ci.points()
+    assert_bit_equal(exact, oracle.cached_interpolate(2, gx, gy, lon.size, lat.size, ax.size, ax.size, field), "bicubic exact (default)")
+    monkeypatch.setenv("FIMEX_B200_BICUBIC_CONTRACT", "1")
+    fast = ci.interpolateValues(field)
+    fu, fv = ci.interpolateVector(u, v, cvr)
+    monkeypatch.delenv("FIMEX_B200_BICUBIC_CONTRACT")
+    assert np.array_equal(np.isnan(fast), np.isnan(exact))
+    ok = ~np.isnan(exact)
+    assert ok.sum() > 0.5 * ok.size
+    assert np.abs(fast[ok] - exact[ok]).max() <= 1e-5 * np.abs(field).max()
+    assert (fast[ok] != exact[ok]).any()  # the mode was really taken
+    for f, e in ((fu, eu), (fv, ev)):
+        m = ~np.isnan(e)
+        assert np.array_equal(np.isnan(f), ~m) and np.abs(f[m] - e[m]).max() <= 1e-5 * 60.0
+    assert_bit_equal(ci.interpolateValues(field), exact, "bicubic exact again")
