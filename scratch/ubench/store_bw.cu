@@ -85,6 +85,24 @@ __global__ void k_tiles_al(float* out, int ox, int oy, int nz, int chunk)
     }
 }
 
+
+// k_tiles<TX, TY, 1> launched as thread-block clusters of CL x-adjacent tiles (co-scheduled: their row segments are written together)
+template <int TX, int TY, int CL>
+__global__ void __cluster_dims__(CL, 1, 1) k_tiles_cl(float* out, int ox, int oy, int nz, int chunk, int tiles_x)
+{
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    const int z0 = blockIdx.y * chunk, z1 = min(nz, z0 + chunk);
+    constexpr int rows_per_pass = 256 / TX;
+    const int lx = threadIdx.x % TX, ly = threadIdx.x / TX;
+    const size_t level = (size_t)ox * oy;
+    for (int z = z0; z < z1; ++z) {
+        float* base = out + z * level + (size_t)(ty * TY) * ox + tx * TX + lx;
+#pragma unroll
+        for (int r = ly; r < TY; r += rows_per_pass)
+            __stcs(base + (size_t)r * ox, (float)z);
+    }
+}
+
 template <class F>
 float time_ms(F f, int reps = 5)
 {
@@ -156,6 +174,15 @@ int main(int argc, char** argv)
         { dim3 g(((ox + 31 + 127) / 128) * (oy / 8), (nz + chunk - 1) / chunk);
           ms = time_ms([&] { k_tiles_al<128, 8, 4><<<g, 256>>>(out, ox, oy, nz, chunk); });
           printf("tiles 128x8  float4 ALIGNED %3d %8.3f ms %8.1f GB/s\n", chunk, ms, gb / ms * 1e3); }
+        { const int tcx = (ox / 64) / 4 * 4; dim3 g(tcx * (oy / 16), (nz + chunk - 1) / chunk);
+          ms = time_ms([&] { k_tiles_cl<64, 16, 1><<<g, 256>>>(out, ox, oy, nz, chunk, tcx); });
+          printf("tiles 64x16  scalar CLUSTER1 %3d %8.3f ms %8.1f GB/s (of %d columns)\n", chunk, ms, 4e-9 * tcx * 64 * (double)oy * nz / ms * 1e3, tcx * 64); }
+        { const int tcx = (ox / 64) / 4 * 4; dim3 g(tcx * (oy / 16), (nz + chunk - 1) / chunk);
+          ms = time_ms([&] { k_tiles_cl<64, 16, 4><<<g, 256>>>(out, ox, oy, nz, chunk, tcx); });
+          printf("tiles 64x16  scalar CLUSTER4 %3d %8.3f ms %8.1f GB/s (of %d columns)\n", chunk, ms, 4e-9 * tcx * 64 * (double)oy * nz / ms * 1e3, tcx * 64); }
+        { const int tcx = (ox / 64) / 2 * 2; dim3 g(tcx * (oy / 16), (nz + chunk - 1) / chunk);
+          ms = time_ms([&] { k_tiles_cl<64, 16, 2><<<g, 256>>>(out, ox, oy, nz, chunk, tcx); });
+          printf("tiles 64x16  scalar CLUSTER2 %3d %8.3f ms %8.1f GB/s (of %d columns)\n", chunk, ms, 4e-9 * tcx * 64 * (double)oy * nz / ms * 1e3, tcx * 64); }
     }
     return 0;
 }
