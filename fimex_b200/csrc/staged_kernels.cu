@@ -5,14 +5,17 @@
 // Why: the direct gather (gather_kernels.cu) issues four 4-byte global loads per output value and is bound by
 // L1/LSU request rate and load latency (ncu, profiles/): ~33 % of the HBM roofline.  The target grid is
 // normally finer than the source, so the 1024 target points of a tile touch only a few dozen distinct source
-// values.  Here a CTA owns a tile of 128 x 8 target points and, per batch of up to 8 levels,
+// values.  Here a CTA owns a tile of 1024 target points (64 x 16 for bilinear, 128 x 8 for nearest neighbour) and, per batch of
+// up to 8 levels,
 //   1. copies the tile's DISTINCT source values ("taps", a sorted list of offsets inside a level) into shared
 //      memory with cp.async (LDGSTS), double buffered: batch b+1 is in flight while batch b is consumed, so
-//      each source value is requested from L2/HBM once per tile and level, not once per target point;
-//   2. every thread then reads its four taps from shared memory (two row indices per point; the right-hand
-//      neighbour is the next list entry), evaluates the reference's formula (no FMA contraction: bit-identical
-//      to the CPU) and streams its 4 consecutive outputs with one 128-bit st.global.cs, a warp writing 512
-//      contiguous bytes of a row.
+//      each source value is requested from L2/HBM once per tile and level, not once per target point.  The staging
+//      buffer is tap-major (tap r, level zi at r*12 + zi), so the levels of a tap are contiguous;
+//   2. every thread then reads four levels of each of its taps with one 128-bit shared load (two row indices per
+//      point; the right-hand neighbour is the next list entry), evaluates the reference's formula (no FMA
+//      contraction: bit-identical to the CPU) and streams its outputs with st.global.cs: bilinear lane = x, a warp
+//      writing 128 contiguous bytes of a row; nearest neighbour 4 consecutive points per thread with one 128-bit store,
+//      a warp writing 512 contiguous bytes.
 // The tap list is per tile, not a bounding box, so tiles over the pole or across the 0/360 longitude seam
 // (where the footprint of a tile is scattered) cost no more than their number of distinct taps.
 //
