@@ -125,3 +125,27 @@ def test_header_is_plain_c():
     r = subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, "-x", "c", "-"], input=src, text=True,
                        capture_output=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_interpolator_host_logic_without_gpu():
+    # argument checks and string handling of the CDMInterpolator mirror that run before any device call
+    from fimex_b200 import FimexB200Error, Interpolator, Method
+
+    ip = Interpolator("+proj=stere +lat_0=90 +lon_0=0 +lat_ts=60 +units=m +a=6.371e+06 +e=0 +no_defs", [0.0, 1000.0], [0.0, 1000.0], False)
+    assert ip._latlong_of_source() == "+proj=latlong +a=6.371e+06 +e=0"  # "+proj=latlong " + getProj4EarthString()
+    assert Interpolator("+proj=ob_tran +o_proj=longlat +lon_0=-40 +o_lat_p=22 +R=6.371e+06 +no_defs", [0.0, 1.0], [0.0, 1.0],
+                        True)._latlong_of_source() == "+proj=latlong +R=6.371e+06"
+    assert Interpolator("+proj=lcc +lat_1=63 +lat_0=63 +lon_0=15", [0.0, 1.0], [0.0, 1.0], False)._latlong_of_source() == \
+        "+proj=latlong +a=6371000 +e=0"  # default earth (ProjectionImpl.cc:152)
+    with pytest.raises(FimexB200Error):  # CDMInterpolator.cc:465-469
+        ip.changeProjectionToLonLatValues(Method.BILINEAR, [1.0, 2.0], [1.0])
+    with pytest.raises(FimexB200Error):  # :706-714: coordinate and forward methods cannot take a template
+        ip.changeProjectionToTemplate(Method.COORD_NN_KD, np.zeros((2, 2)), np.zeros((2, 2)))
+    with pytest.raises(FimexB200Error):
+        ip.changeProjectionToTemplate("forward_mean", np.zeros((2, 2)), np.zeros((2, 2)))
+    with pytest.raises(FimexB200Error):  # :533-535
+        Interpolator("+proj=latlong +R=6371000", [0.0], [0.0, 1.0], True).changeProjectionToCrossSections(Method.BILINEAR, [("a", [(0, 0)])])
+    with pytest.raises(FimexB200Error):  # :541-543
+        Interpolator("+proj=latlong +R=6371000", [1.0, 1.0], [0.0, 1.0], True).changeProjectionToCrossSections(Method.BILINEAR, [("a", [(0, 0)])])
+    with pytest.raises(FimexB200Error):
+        ip.getDataSlice(np.zeros((2, 2), np.float32))  # no changeProjection yet
