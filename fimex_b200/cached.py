@@ -97,12 +97,14 @@ class CachedInterpolationInterface:
     def _npoints(self):
         raise NotImplementedError
 
-    def getInputDataSlice(self, array: np.ndarray) -> np.ndarray:
+    def getInputDataSlice(self, array):
         """The array-level part of getInputDataSlice (CachedInterpolation.cc:44-90): crop [.., y, x] to the
-        reduced domain if there is one."""
+        reduced domain if there is one (numpy array, or a CUDA tensor cropped on the device)."""
         if self._reduced is None:
             return array
         _, _, x0, y0, _, _ = self._reduced
+        if _is_torch(array):
+            return array[..., y0:y0 + self.getInY(), x0:x0 + self.getInX()].contiguous()
         return np.ascontiguousarray(array[..., y0:y0 + self.getInY(), x0:x0 + self.getInX()])
 
     # -- the hot path -----------------------------------------------------------------------------

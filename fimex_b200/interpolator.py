@@ -299,10 +299,12 @@ class Interpolator:
         ci = self.cachedInterpolation
         if ci is None:
             raise FimexB200Error("no cached interpolation: call changeProjection first")
-        data = np.asarray(data)
+        on_device = type(data).__module__.startswith("torch")  # a CUDA tensor: the slab stays on the GPU, result is a CUDA tensor
+        if not on_device:
+            data = np.asarray(data)
         if bad_value is None:
             bad_value = capi.default_fill_value(data.dtype)
-        lead = data.shape[:-2]
+        lead = tuple(data.shape[:-2])
         if counterpart is not None and self.cachedVectorReprojection is not None:
             if "x" in direction:
                 want = 0
@@ -314,7 +316,7 @@ class Interpolator:
             if pair_key is not None and (pair_key, want) in cache:
                 return cache.pop((pair_key, want))
             arr = ci.getInputDataSlice(data)
-            other = ci.getInputDataSlice(np.asarray(counterpart, dtype=data.dtype))
+            other = ci.getInputDataSlice(counterpart if on_device else np.asarray(counterpart, dtype=data.dtype))
             cbad = bad_value if counterpart_bad_value is None else counterpart_bad_value
             if want == 0:
                 both = ci.getVectorSlice(arr, other, bad_value, cbad, self.cachedVectorReprojection)

@@ -1090,3 +1090,29 @@ def test_bicubic_contracted_mode_is_opt_in_and_within_tolerance(oracle, monkeypa
         m = ~np.isnan(e)
         assert np.array_equal(np.isnan(f), ~m) and np.abs(f[m] - e[m]).max() <= 1e-5 * 60.0
     assert_bit_equal(ci.interpolateValues(field), exact, "bicubic exact again")
+
+
+def test_interpolator_device_resident_slices():
+    # the same getDataSlice with CUDA tensors: crop, adapters, gather and rotation on the device, CUDA tensors back
+    import torch
+    lon, lat, _ = _config2_like(40)
+    rng = np.random.default_rng(31)
+    t = rng.integers(-3000, 3000, (4, lat.size, lon.size)).astype(np.int16)
+    t[rng.random(t.shape) < 0.03] = -32767
+    u = rng.normal(0, 10, (2, lat.size, lon.size)).astype(np.float32)
+    v = rng.normal(0, 10, (2, lat.size, lon.size)).astype(np.float32)
+    ax = (np.arange(64) - 31.5) * 0.4
+    interp = fb.Interpolator(SRC_LL, lon, lat, True, has_xy_vectors=True)
+    interp.changeProjection("bilinear", ROTPOLE, ax, ax, "degree", "degree")
+    want_t = interp.getDataSlice(t)
+    want_u = interp.getDataSlice(u, counterpart=v, direction="x")
+    want_v = interp.getDataSlice(v, counterpart=u, direction="y")
+    dt, du, dv = (torch.from_numpy(a).cuda() for a in (t, u, v))
+    got_t = interp.getDataSlice(dt)
+    assert got_t.is_cuda and got_t.dtype == torch.int16 and tuple(got_t.shape) == want_t.shape
+    assert np.array_equal(got_t.cpu().numpy(), want_t)
+    got_u = interp.getDataSlice(du, counterpart=dv, direction="x", pair_key=("u", "v", 0))
+    got_v = interp.getDataSlice(dv, counterpart=du, direction="y", pair_key=("u", "v", 0))
+    assert got_u.is_cuda and got_v.is_cuda
+    assert_bit_equal(got_u.cpu().numpy(), want_u, "device-resident x component")
+    assert_bit_equal(got_v.cpu().numpy(), want_v, "device-resident y component")
