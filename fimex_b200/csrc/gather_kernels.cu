@@ -322,10 +322,11 @@ bool aligned16(const void* p)
 // entry of a point is read once per chunk.  Measured on B200 (profiles/): chunks of 32..96 levels run at the same
 // speed, longer ones are slower (CTAs drift apart in z and the set of DRAM pages being written at any moment
 // grows: 658-level chunks cost 40 % more time per level than 64-level chunks), shorter ones re-read the tables too
-// often.  So: ~64 levels per chunk, and at least ~4 CTAs per SM in flight for small slices.
-int z_chunks(long long ctas_x, long long nz)
+// often.  So: ~64 levels per chunk (`levels`; the staged bilinear gather is 1.5 % faster with 128), and at least ~4 CTAs per
+// SM in flight for small slices.
+int z_chunks(long long ctas_x, long long nz, int levels)
 {
-    long long gy = (nz + 63) / 64;
+    long long gy = (nz + levels - 1) / levels;
     const long long min_ctas = (long long)sm_count() * 4;
     if (ctas_x * gy < min_ctas) {
         const long long more = (min_ctas + ctas_x - 1) / ctas_x;

@@ -56,7 +56,7 @@ struct GatherGeom {
     long long out_level; // ox*oy
     long long nz;
 };
-int z_chunks(long long ctas_x, long long nz); // gridDim.y policy shared by the gather kernels
+int z_chunks(long long ctas_x, long long nz, int levels = 64); // gridDim.y policy shared by the gather kernels
 int launch_gather_nn(const GatherGeom& g, const int* d_off, const float* d_in, float* d_out, cudaStream_t st);
 int launch_gather_bilinear(const GatherGeom& g, const int4* d_tab, const float* d_in, float* d_out, cudaStream_t st);
 int launch_gather_bicubic(const GatherGeom& g, const int* d_off, const double2* d_frac, const float* d_in, float* d_out, cudaStream_t st);
