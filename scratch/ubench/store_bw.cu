@@ -103,6 +103,30 @@ __global__ void __cluster_dims__(CL, 1, 1) k_tiles_cl(float* out, int ox, int oy
     }
 }
 
+
+// k_tiles<TX, TY, 1> with other cache operators on the store: 0 = default (write-back, evict-normal), 1 = .cg, 2 = .wt, 3 = .cs
+template <int TX, int TY, int OP>
+__global__ void k_tiles_op(float* out, int ox, int oy, int nz, int chunk)
+{
+    const int tiles_x = ox / TX;
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    const int z0 = blockIdx.y * chunk, z1 = min(nz, z0 + chunk);
+    constexpr int rows_per_pass = 256 / TX;
+    const int lx = threadIdx.x % TX, ly = threadIdx.x / TX;
+    const size_t level = (size_t)ox * oy;
+    for (int z = z0; z < z1; ++z) {
+        float* base = out + z * level + (size_t)(ty * TY) * ox + tx * TX + lx;
+#pragma unroll
+        for (int r = ly; r < TY; r += rows_per_pass) {
+            float* p = base + (size_t)r * ox;
+            if (OP == 0) *p = (float)z;
+            else if (OP == 1) __stcg(p, (float)z);
+            else if (OP == 2) __stwt(p, (float)z);
+            else __stcs(p, (float)z);
+        }
+    }
+}
+
 template <class F>
 float time_ms(F f, int reps = 5)
 {
@@ -183,6 +207,15 @@ int main(int argc, char** argv)
         { const int tcx = (ox / 64) / 2 * 2; dim3 g(tcx * (oy / 16), (nz + chunk - 1) / chunk);
           ms = time_ms([&] { k_tiles_cl<64, 16, 2><<<g, 256>>>(out, ox, oy, nz, chunk, tcx); });
           printf("tiles 64x16  scalar CLUSTER2 %3d %8.3f ms %8.1f GB/s (of %d columns)\n", chunk, ms, 4e-9 * tcx * 64 * (double)oy * nz / ms * 1e3, tcx * 64); }
+        { dim3 g((ox / 64) * (oy / 16), (nz + chunk - 1) / chunk);
+          ms = time_ms([&] { k_tiles_op<64, 16, 0><<<g, 256>>>(out, ox, oy, nz, chunk); });
+          printf("tiles 64x16  scalar st.wb     %3d %8.3f ms %8.1f GB/s\n", chunk, ms, 4e-9 * (ox / 64 * 64) * (double)oy * nz / ms * 1e3);
+          ms = time_ms([&] { k_tiles_op<64, 16, 1><<<g, 256>>>(out, ox, oy, nz, chunk); });
+          printf("tiles 64x16  scalar st.cg     %3d %8.3f ms %8.1f GB/s\n", chunk, ms, 4e-9 * (ox / 64 * 64) * (double)oy * nz / ms * 1e3);
+          ms = time_ms([&] { k_tiles_op<64, 16, 2><<<g, 256>>>(out, ox, oy, nz, chunk); });
+          printf("tiles 64x16  scalar st.wt     %3d %8.3f ms %8.1f GB/s\n", chunk, ms, 4e-9 * (ox / 64 * 64) * (double)oy * nz / ms * 1e3);
+          ms = time_ms([&] { k_tiles_op<64, 16, 3><<<g, 256>>>(out, ox, oy, nz, chunk); });
+          printf("tiles 64x16  scalar st.cs     %3d %8.3f ms %8.1f GB/s\n", chunk, ms, 4e-9 * (ox / 64 * 64) * (double)oy * nz / ms * 1e3); }
     }
     return 0;
 }
