@@ -22,11 +22,11 @@ from .capi import (DataType, cdm_type, default_fill_value, LATITUDE, LONGITUDE, 
                    mifi_bad2nanf, mifi_nanf2bad, mifi_fill2d_f, mifi_creepfill2d_f, fill2d_device, creepfill2d_device, set_device,
                    version)
 from .cached import CachedForwardInterpolation, CachedInterpolation, CachedVectorReprojection
-from .interpolator import Interpolator, spatial_axis_spec, tokenize_dotted
+from .interpolator import Interpolator, axis_spec_requires_start_end, spatial_axis_spec, tokenize_dotted
 from .processor import Processor
 
 __all__ = [
-    "CachedInterpolation", "CachedForwardInterpolation", "CachedVectorReprojection", "Interpolator", "Processor", "spatial_axis_spec", "tokenize_dotted", "Method", "DataType", "cdm_type", "default_fill_value", "FimexB200Error",
+    "CachedInterpolation", "CachedForwardInterpolation", "CachedVectorReprojection", "Interpolator", "Processor", "spatial_axis_spec", "axis_spec_requires_start_end", "tokenize_dotted", "Method", "DataType", "cdm_type", "default_fill_value", "FimexB200Error",
     "MIFI_OK", "MIFI_ERROR", "PROJ_AXIS", "LONGITUDE", "LATITUDE", "MIFI_VECTOR_KEEP_SIZE", "load", "lib_path", "version", "last_error",
     "set_device", "kernel_launches", "mifi_interpolate_f", "mifi_points2position", "mifi_project_axes", "mifi_project_values",
     "mifi_get_vector_reproject_matrix", "mifi_get_vector_reproject_matrix_field", "mifi_get_vector_reproject_matrix_points",

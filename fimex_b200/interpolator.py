@@ -56,25 +56,61 @@ def tokenize_dotted(spec: str, delimiter: str = ",") -> list:
     return vals
 
 
-def spatial_axis_spec(spec) -> np.ndarray:
-    """SpatialAxisSpec for absolute axis strings (src/SpatialAxisSpec.cc:84-150); relativeStart needs the source
-    bounding box and is left to the caller."""
+_RELATIVE_FINAL = re.compile(r"x\s*([+-])?\s*(\d\.?\d*)?\s*")  # TranslateRelativePlace, src/SpatialAxisSpec.cc:58
+
+
+def axis_spec_requires_start_end(spec) -> bool:
+    """SpatialAxisSpec::requireStartEnd (src/SpatialAxisSpec.cc:153-158) before setStartEnd"""
+    return isinstance(spec, str) and "relativeStart" in spec
+
+
+def spatial_axis_spec(spec, start=None, end=None) -> np.ndarray:
+    """SpatialAxisSpec (src/SpatialAxisSpec.cc:84-150): absolute axis strings ("0,0.5,...,3"), or strings relative to the
+    bounding box [start, end] of the data in the target projection ("0,50000,...,x,x+50000;relativeStart=0": 0 is the
+    first multiple of the step inside the box, x the last one; test/testSpatialAxisSpec.cc)."""
     if not isinstance(spec, str):
         return np.asarray(spec, dtype=np.float64)
     steps = None
+    relative = ""
     for part in spec.split(";"):
         kv = part.split("=")
         if len(kv) == 1:
             if steps is not None:
-                raise FimexB200Error("axis-steps redefined")
+                raise FimexB200Error(f"axis-steps redefined from {steps} to {kv[0]}")
             steps = kv[0]
-        elif kv[0] == "relativeStart":
-            raise FimexB200Error("relativeStart axis specs need the source bounding box; pass explicit values")
-        elif kv[0] == "unit":
+        elif len(kv) == 2 and kv[0] == "relativeStart":
+            relative = kv[1]
+        elif len(kv) == 2 and kv[0] == "unit":
             raise FimexB200Error("unit not supported yet in SpatialAxisSpec, please enter values in m or degree")
-        else:
+        elif len(kv) == 2:
             raise FimexB200Error(f"unknown axisSpec parameter: '{kv[0]}'")
-    return np.asarray(tokenize_dotted(steps or ""), dtype=np.float64)
+        else:
+            raise FimexB200Error(f"unknown axisSpec section: '{part}'")
+    if relative == "":
+        return np.asarray(tokenize_dotted(steps or ""), dtype=np.float64)
+    if start is None or end is None:
+        raise FimexB200Error("require start and end for axisSpec: " + spec)
+    places = [p for p in (steps or "").split(",")]
+    if len(places) < 2:
+        raise FimexB200Error("SpatialAxisSpec requires at least 2 values with relative start definition, got: " + (steps or ""))
+    delta = float(places[1]) - float(places[0])
+    start_offset = int(start / delta) * delta  # static_cast<int>: towards zero
+    if start < start_offset:
+        start_offset += delta
+    final = int(end / delta) * delta
+    absolute = []
+    for value in places:
+        if value.strip() == "...":
+            absolute.append("...")
+            continue
+        m = _RELATIVE_FINAL.search(value)
+        if m:
+            amount = float(m.group(2)) if m.group(2) else 0.0
+            v = final + amount if m.group(1) == "+" else final - amount if m.group(1) == "-" else final
+        else:
+            v = start_offset + float(value)
+        absolute.append(repr(float(v)))
+    return np.asarray(tokenize_dotted(",".join(absolute)), dtype=np.float64)
 
 
 def lon_lat_vals_to_matrix(lon_vals, lat_vals):
@@ -120,8 +156,13 @@ class Interpolator:
             m = capi.mifi_string_to_interpolation_method(method)
         else:
             m = int(method)
-        out_x = spatial_axis_spec(out_x_axis)
-        out_y = spatial_axis_spec(out_y_axis)
+        if axis_spec_requires_start_end(out_x_axis) or axis_spec_requires_start_end(out_y_axis):
+            (x_min, x_max), (y_min, y_max) = self._bounding_box_in(proj_input)
+            out_x = spatial_axis_spec(out_x_axis, x_min, x_max)
+            out_y = spatial_axis_spec(out_y_axis, y_min, y_max)
+        else:
+            out_x = spatial_axis_spec(out_x_axis)
+            out_y = spatial_axis_spec(out_y_axis)
         self.clearPairCache()
         self.cachedInterpolation = None
         self.cachedVectorReprojection = None
@@ -135,6 +176,28 @@ class Interpolator:
             raise FimexB200Error(f"unknown projection method: {m}")
         self.method = Method(m)
         return self
+
+    def _bounding_box_in(self, proj_input):
+        """the bounding box of the data in the target projection for relative axis specs (CDMInterpolator.cc:349-401): all
+        longitude/latitude values of the source grid projected to `proj_input`, min / max per axis"""
+        m = re.search(r"\+proj=(\S+)", proj_input)
+        name = m.group(1) if m else ""
+        if name == "latlong":
+            raise FimexB200Error("changeProjection with autotuning axes only implemented for projections in m, not degree yet")
+        if self.lon2d is not None and self.lat2d is not None:
+            lon, lat = self.lon2d, self.lat2d
+        elif self.is_degree and "ob_tran" not in self.source_proj4:
+            lon, lat = lon_lat_vals_to_matrix(self.x_axis, self.y_axis)  # 1-D axes made 2-D (:365-379)
+        else:  # the reference reads the CDM's longitude/latitude variables; here they follow from the source grid itself
+            lon, lat = self.convertToLonLat(np.tile(self.x_axis, self.y_axis.size), np.repeat(self.y_axis, self.x_axis.size))
+        rc, x, y = capi.mifi_project_values(MIFI_WGS84_LATLON_PROJ4, proj_input, np.radians(lon), np.radians(lat))
+        if rc != capi.MIFI_OK:
+            raise FimexB200Error(f"unable to project axes from {MIFI_WGS84_LATLON_PROJ4} to {proj_input}")
+        ok = np.isfinite(x) & np.isfinite(y)
+        box = [(float(x[ok].min()), float(x[ok].max())), (float(y[ok].min()), float(y[ok].max()))]
+        if name == "ob_tran":
+            box = [(np.degrees(a), np.degrees(b)) for a, b in box]
+        return box
 
     def _by_projection_parameters(self, method, proj_input, out_x, out_y, xunit, yunit):
         # :1440-1503

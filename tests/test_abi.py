@@ -149,3 +149,20 @@ def test_interpolator_host_logic_without_gpu():
         Interpolator("+proj=latlong +R=6371000", [1.0, 1.0], [0.0, 1.0], True).changeProjectionToCrossSections(Method.BILINEAR, [("a", [(0, 0)])])
     with pytest.raises(FimexB200Error):
         ip.getDataSlice(np.zeros((2, 2), np.float32))  # no changeProjection yet
+
+
+def test_spatial_axis_spec_relative():
+    # test/testSpatialAxisSpec.cc:36-66
+    vals = spatial_axis_spec("-450000,-400000,...,50000", 30000, 230000)
+    assert vals.size == 11 and vals[0] == -450000 and vals[10] == 50000
+    rel = spatial_axis_spec("0,50000,...,x,x+50000;relativeStart=0", 30000, 230000)
+    assert rel.size == 6 and rel[0] == 0 and rel[5] == 250000
+    # a negative start moves on to the next multiple of the step (src/SpatialAxisSpec.cc:128-133)
+    rel = spatial_axis_spec("0,1000,...,x;relativeStart=0", -2500.0, 3999.0)
+    assert rel[0] == -1000 and rel[-1] == 3000 and np.all(np.diff(rel) == 1000)
+    with pytest.raises(fimex_b200.FimexB200Error):
+        spatial_axis_spec("0,50000,...,x;relativeStart=0")  # "require start and end for axisSpec"
+    with pytest.raises(fimex_b200.FimexB200Error):
+        spatial_axis_spec("0;relativeStart=0", 0.0, 1.0)
+    with pytest.raises(fimex_b200.FimexB200Error):
+        spatial_axis_spec("0,1,...,5;unit=km")

@@ -263,3 +263,32 @@ def test_interpolator_vcross(fx, oracle):
     n = ip.vcross_bnds[0][1] + 1
     assert n > 10 and np.abs(np.diff(gx[:n], 2)).max() < 1e-3 and np.abs(np.diff(gy[:n], 2)).max() < 1e-3  # equidistant in index space
     assert np.hypot(np.diff(gx[:n]), np.diff(gy[:n])).max() <= 1.5
+
+
+def test_interpolator_relative_axes(oracle):
+    # test_interpolatorRelative (test/testInterpolator.cc:182-196, needs the optional flth00.dat there): axes given relative to
+    # the bounding box of the data in the target projection, "0,50000,...,x;relativeStart=0" (CDMInterpolator.cc:345-412)
+    lon = np.arange(-10.0, 30.25, 0.5)
+    lat = np.arange(50.0, 72.25, 0.5)
+    proj = "+proj=stere +lat_0=90 +lon_0=-32 +lat_ts=60 +ellps=sphere +a=6371000 +e=0"
+    interp = fb.Interpolator("+proj=latlong +a=6371000 +e=0 +no_defs", lon, lat, True)
+    interp.changeProjection("bilinear", proj, "0,50000,...,x;relativeStart=0", "0,50000,...,x;relativeStart=0", "m", "m")
+    ci = interp.cachedInterpolation
+    lon2d, lat2d = np.tile(lon, lat.size), np.repeat(lat, lon.size)
+    rc, x, y = oracle.project_values(WGS84, proj, np.radians(lon2d), np.radians(lat2d))
+    assert rc == 1
+    want_x = fb.spatial_axis_spec("0,50000,...,x;relativeStart=0", x.min(), x.max())
+    want_y = fb.spatial_axis_spec("0,50000,...,x;relativeStart=0", y.min(), y.max())
+    assert ci.getOutX() == want_x.size and ci.getOutY() == want_y.size
+    assert want_x[0] >= x.min() - 50000 and want_x[-1] <= x.max() and np.all(np.diff(want_x) == 50000)
+    field = np.random.default_rng(3).normal(280, 5, (2, lat.size, lon.size)).astype(np.float32)
+    got = interp.getDataSlice(field)
+    assert got.shape == (2, want_y.size, want_x.size)
+    inside = np.isfinite(got) & (got != np.float32(fb.default_fill_value(np.float32)))
+    assert inside.mean() > 0.5  # the box of a lat/lon rectangle in a polar projection has empty corners
+    # same table as with the explicit axes
+    ref = fb.Interpolator("+proj=latlong +a=6371000 +e=0 +no_defs", lon, lat, True)
+    ref.changeProjection("bilinear", proj, want_x, want_y, "m", "m")
+    assert_bit_equal(got, ref.getDataSlice(field), "relative axes")
+    with pytest.raises(fb.FimexB200Error):  # "only implemented for projections in m, not degree yet"
+        interp.changeProjection("bilinear", "+proj=latlong +R=6371000", "0,1,...,x;relativeStart=0", "0,1,...,x;relativeStart=0", "degree", "degree")
