@@ -19,6 +19,7 @@
 #include <mutex>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 // ======================================================================================================
@@ -575,6 +576,58 @@ HostPipe* host_pipe(int device)
     return &pipe;
 }
 
+// ---- pageable host buffers ------------------------------------------------------------------------------------------------
+// The reference hands `new float[]` arrays in and expects one back (boost::shared_array).  cudaMemcpyAsync to or from such
+// pageable memory goes through the driver's own staging at ~15 GB/s (measured: a 137-level call takes 146 ms instead of
+// 43 ms), slower than the reference's CPU loop; staged here with 16 host threads it takes 79 ms.  run_slice_host therefore detects pageable buffers and stages them itself:
+// page-locked bounce buffers from the pinned cache, filled / drained by a few host threads while the next chunks are in flight.
+bool host_pageable(const void* p)
+{
+    if (!p)
+        return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError(); // older drivers report plain malloc memory as an error
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+int copy_threads()
+{
+    static const int n = []() {
+        int want = 16; // measured (one 2.19 GB pageable output, 16-core host): 1 / 4 / 8 / 16 threads -> 167 / 105 / 93 / 79 ms
+        if (const char* env = std::getenv("FIMEX_B200_COPY_THREADS"))
+            want = std::atoi(env);
+        const int hw = (int)std::thread::hardware_concurrency();
+        if (hw > 0 && want > hw)
+            want = hw;
+        return want < 1 ? 1 : want;
+    }();
+    return n;
+}
+
+void parallel_memcpy(void* dst, const void* src, size_t bytes)
+{
+    const int nt = copy_threads();
+    if (nt <= 1 || bytes < (size_t)(8u << 20)) {
+        std::memcpy(dst, src, bytes);
+        return;
+    }
+    const size_t per = ((bytes + nt - 1) / nt + 4095) & ~(size_t)4095;
+    std::vector<std::thread> workers;
+    for (int t = 1; t < nt; ++t) {
+        const size_t off = per * (size_t)t;
+        if (off >= bytes)
+            break;
+        const size_t len = bytes - off < per ? bytes - off : per;
+        workers.emplace_back([=]() { std::memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, len); });
+    }
+    std::memcpy(dst, src, per < bytes ? per : bytes);
+    for (auto& w : workers)
+        w.join();
+}
+
 // Host-buffer execution: levels are cut into chunks that rotate through three (stream, scratch) slots, so that
 // the H2D copy of chunk k+1, the kernel of chunk k and the D2H copy of chunk k-1 overlap.  `nfields` is 1
 // (scalar) or 2 (u/v).  Every call owns its streams and scratch => re-entrant on a shared handle.
@@ -601,10 +654,24 @@ int run_slice_host(const fb200_interp* h, const fb200_vector* v, int nfields, co
     // chunk and guard the reuse of a slot's buffers.  Measured on B200 (PCIe Gen5 x16): a 137-level call (0.16 GB up, 2.19 GB
     // down) takes 41.7 ms = 52 GB/s; one monolithic 2.19 GB download takes 38.3-40.3 ms, the same bytes as 13 back-to-back
     // copies 42.5 ms, so the call runs at the rate chunked copies allow and the kernels are invisible.
+    bool bounce_in = false, bounce_out = false; // pageable host arrays: staged through page-locked bounce buffers, see above
+    if (copy_threads() >= 4) { // with fewer host threads the driver's own staging (one thread, ~15 GB/s) is as fast
+        for (int f = 0; f < nfields; ++f) {
+            bounce_in = bounce_in || (in_level && host_pageable(in[f]));
+            bounce_out = bounce_out || host_pageable(out[f]);
+        }
+    }
+    if ((bounce_in || bounce_out) && zc * bytes_per_level > (64ull << 20)) { // smaller chunks: the host copy of chunk k runs while k+1, k+2 are in flight
+        zc = (64ull << 20) / bytes_per_level;
+        if (zc < 1)
+            zc = 1;
+    }
     const int nslots = (nz > zc) ? 3 : 1;
     struct Slot {
         void* d_in[2] = {nullptr, nullptr};
         void* d_out[2] = {nullptr, nullptr};
+        void* h_in[2] = {nullptr, nullptr};  // bounce buffers (page-locked, from the pinned cache)
+        void* h_out[2] = {nullptr, nullptr};
         cudaEvent_t uploaded = nullptr, computed = nullptr, downloaded = nullptr;
     } slots[3];
     HostPipe* pipe = host_pipe(h->device);
@@ -631,18 +698,39 @@ int run_slice_host(const fb200_interp* h, const fb200_vector* v, int nfields, co
         FB_CUDA_CHECK(cudaEventRecord(ready, s_run));
         FB_CUDA_CHECK(cudaStreamWaitEvent(s_up, ready, 0));
         FB_CUDA_CHECK(cudaStreamWaitEvent(s_down, ready, 0));
+        if (bounce_in || bounce_out) {
+            for (int s = 0; s < nslots; ++s) {
+                for (int f = 0; f < nfields; ++f) {
+                    if (bounce_in) {
+                        slots[s].h_in[f] = fb200_host_alloc(in_elem * zc * in_level);
+                        FB_REQUIRE(slots[s].h_in[f] != nullptr, "cannot allocate a page-locked staging buffer");
+                    }
+                    if (bounce_out) {
+                        slots[s].h_out[f] = fb200_host_alloc(out_elem * zc * out_level);
+                        FB_REQUIRE(slots[s].h_out[f] != nullptr, "cannot allocate a page-locked staging buffer");
+                    }
+                }
+            }
+        }
         t1 = now();
-        size_t chunk = 0;
-        for (size_t z0 = 0; z0 < nz; z0 += zc, ++chunk) {
+        const size_t nchunks = (nz + zc - 1) / zc;
+        auto enqueue = [&](size_t chunk) -> int {
             Slot& sl = slots[chunk % nslots];
             const bool reused = chunk >= (size_t)nslots;
+            const size_t z0 = chunk * zc;
             const size_t zn = (z0 + zc <= nz) ? zc : nz - z0;
             if (reused) // the kernel that read this slot's input three chunks ago is done
                 FB_CUDA_CHECK(cudaStreamWaitEvent(s_up, sl.computed, 0));
-            for (int f = 0; f < nfields; ++f)
-                if (in_level)
-                    FB_CUDA_CHECK(cudaMemcpyAsync(sl.d_in[f], static_cast<const char*>(in[f]) + z0 * in_level * in_elem, in_elem * zn * in_level,
-                                                  cudaMemcpyHostToDevice, s_up));
+            for (int f = 0; f < nfields; ++f) {
+                if (!in_level)
+                    continue;
+                const char* src = static_cast<const char*>(in[f]) + z0 * in_level * in_elem;
+                if (bounce_in) { // the upload that last read this bounce buffer finished before its chunk's download was waited for
+                    parallel_memcpy(sl.h_in[f], src, in_elem * zn * in_level);
+                    src = static_cast<const char*>(sl.h_in[f]);
+                }
+                FB_CUDA_CHECK(cudaMemcpyAsync(sl.d_in[f], src, in_elem * zn * in_level, cudaMemcpyHostToDevice, s_up));
+            }
             FB_CUDA_CHECK(cudaEventRecord(sl.uploaded, s_up));
             FB_CUDA_CHECK(cudaStreamWaitEvent(s_run, sl.uploaded, 0));
             if (reused) // ... and the download of its previous output
@@ -651,13 +739,39 @@ int run_slice_host(const fb200_interp* h, const fb200_vector* v, int nfields, co
                 return FB_ERROR;
             FB_CUDA_CHECK(cudaEventRecord(sl.computed, s_run));
             FB_CUDA_CHECK(cudaStreamWaitEvent(s_down, sl.computed, 0));
-            for (int f = 0; f < nfields; ++f)
-                FB_CUDA_CHECK(cudaMemcpyAsync(static_cast<char*>(out[f]) + z0 * out_level * out_elem, sl.d_out[f], out_elem * zn * out_level,
-                                              cudaMemcpyDeviceToHost, s_down));
+            for (int f = 0; f < nfields; ++f) {
+                char* dst = bounce_out ? static_cast<char*>(sl.h_out[f]) : static_cast<char*>(out[f]) + z0 * out_level * out_elem;
+                FB_CUDA_CHECK(cudaMemcpyAsync(dst, sl.d_out[f], out_elem * zn * out_level, cudaMemcpyDeviceToHost, s_down));
+            }
             FB_CUDA_CHECK(cudaEventRecord(sl.downloaded, s_down));
+            return FB_OK;
+        };
+        if (!bounce_in && !bounce_out) { // page-locked host arrays: everything is enqueued at once
+            for (size_t chunk = 0; chunk < nchunks; ++chunk)
+                if (enqueue(chunk) != FB_OK)
+                    return FB_ERROR;
+            t2 = now();
+            FB_CUDA_CHECK(cudaStreamSynchronize(s_down)); // every download waited for its kernel, every kernel for its upload
+            t3 = now();
+            return FB_OK;
+        }
+        // pageable host arrays: nslots chunks in flight; the host drains chunk k (and fills chunk k + nslots) meanwhile
+        for (size_t chunk = 0; chunk < nchunks && chunk < (size_t)nslots; ++chunk)
+            if (enqueue(chunk) != FB_OK)
+                return FB_ERROR;
+        for (size_t chunk = 0; chunk < nchunks; ++chunk) {
+            Slot& sl = slots[chunk % nslots];
+            const size_t z0 = chunk * zc;
+            const size_t zn = (z0 + zc <= nz) ? zc : nz - z0;
+            FB_CUDA_CHECK(cudaEventSynchronize(sl.downloaded));
+            if (bounce_out)
+                for (int f = 0; f < nfields; ++f)
+                    parallel_memcpy(static_cast<char*>(out[f]) + z0 * out_level * out_elem, sl.h_out[f], out_elem * zn * out_level);
+            if (chunk + nslots < nchunks && enqueue(chunk + nslots) != FB_OK)
+                return FB_ERROR;
         }
         t2 = now();
-        FB_CUDA_CHECK(cudaStreamSynchronize(s_down)); // every download waited for its kernel, every kernel for its upload
+        FB_CUDA_CHECK(cudaStreamSynchronize(s_down));
         t3 = now();
         return FB_OK;
     };
@@ -674,6 +788,10 @@ int run_slice_host(const fb200_interp* h, const fb200_vector* v, int nfields, co
                 cudaFreeAsync(slots[s].d_in[f], s_run);
             if (slots[s].d_out[f])
                 cudaFreeAsync(slots[s].d_out[f], s_run);
+            if (slots[s].h_in[f])
+                fb200_host_free(slots[s].h_in[f]);
+            if (slots[s].h_out[f])
+                fb200_host_free(slots[s].h_out[f]);
         }
     }
     if (trace)
