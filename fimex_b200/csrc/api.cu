@@ -655,7 +655,8 @@ int run_slice_host(const fb200_interp* h, const fb200_vector* v, int nfields, co
     // down) takes 41.7 ms = 52 GB/s; one monolithic 2.19 GB download takes 38.3-40.3 ms, the same bytes as 13 back-to-back
     // copies 42.5 ms, so the call runs at the rate chunked copies allow and the kernels are invisible.
     bool bounce_in = false, bounce_out = false; // pageable host arrays: staged through page-locked bounce buffers, see above
-    if (copy_threads() >= 4) { // with fewer host threads the driver's own staging (one thread, ~15 GB/s) is as fast
+    // (with fewer than 4 host threads the driver's own staging, one thread at ~15 GB/s, is as fast; small calls are latency-bound)
+    if (copy_threads() >= 4 && nz * bytes_per_level >= (size_t)(8u << 20)) {
         for (int f = 0; f < nfields; ++f) {
             bounce_in = bounce_in || (in_level && host_pageable(in[f]));
             bounce_out = bounce_out || host_pageable(out[f]);
