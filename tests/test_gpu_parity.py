@@ -1116,3 +1116,36 @@ def test_interpolator_device_resident_slices():
     assert got_u.is_cuda and got_v.is_cuda
     assert_bit_equal(got_u.cpu().numpy(), want_u, "device-resident x component")
     assert_bit_equal(got_v.cpu().numpy(), want_v, "device-resident y component")
+
+
+def test_concurrent_large_pageable_slices(oracle):
+    """Calls big enough to be cut into chunks and staged through page-locked bounce buffers (pageable numpy arrays in and out,
+    > 64 MB per call), from four host threads on one handle: the chunk pipeline, the pinned cache and the copy threads are
+    all per call or locked."""
+    import threading
+    lon, lat, ax = _config2_like(700)
+    ci = fb.CachedInterpolation.fromProjection(Method.BILINEAR, ROTPOLE, ax, ax, True, True, SRC_LL, lon, lat, True)
+    ci.createReducedDomain()
+    rng = np.random.default_rng(5)
+    nz = 60  # 60 x 700 x 700 x 4 B = 118 MB out per call
+    fields = [rng.normal(250, 30, (nz, ci.getInY(), ci.getInX())).astype(np.float32) for _ in range(4)]
+    gx, gy = ci.points()
+    want = [oracle.cached_interpolate(1, gx, gy, ci.getInX(), ci.getInY(), ax.size, ax.size, f) for f in fields]
+    got = [None] * 4
+    errors = []
+
+    def work(i):
+        try:
+            for _ in range(2):
+                got[i] = ci.interpolateValues(fields[i])
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for i in range(4):
+        assert_bit_equal(got[i], want[i], f"thread {i}")
