@@ -616,14 +616,20 @@ void parallel_memcpy(void* dst, const void* src, size_t bytes)
     }
     const size_t per = ((bytes + nt - 1) / nt + 4095) & ~(size_t)4095;
     std::vector<std::thread> workers;
-    for (int t = 1; t < nt; ++t) {
+    size_t done_by_workers_from = bytes; // everything below this offset that no worker took is copied here
+    for (int t = nt - 1; t >= 1; --t) {
         const size_t off = per * (size_t)t;
         if (off >= bytes)
+            continue;
+        const size_t len = done_by_workers_from - off;
+        try {
+            workers.emplace_back([=]() { std::memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, len); });
+        } catch (...) { // no more threads to be had: the calling thread copies the rest
             break;
-        const size_t len = bytes - off < per ? bytes - off : per;
-        workers.emplace_back([=]() { std::memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, len); });
+        }
+        done_by_workers_from = off;
     }
-    std::memcpy(dst, src, per < bytes ? per : bytes);
+    std::memcpy(dst, src, done_by_workers_from);
     for (auto& w : workers)
         w.join();
 }
