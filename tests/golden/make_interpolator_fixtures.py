@@ -52,6 +52,35 @@ def main():
     for name in ("x_wind_10m", "y_wind_10m"):
         out["coord_" + name] = native(nc.variables[name].data[0])
 
+    # BASELINE config 1: the fimex CLI's bilinear regrid of test/hirlam12.nc to a 0.5-degree lat/long grid.  The file's own
+    # data (axes in degrees, no grid_mapping => latitude_longitude on the default sphere, CF1_xCoordSysBuilder.cc:398-410),
+    # plus golden outputs from the COMPILED reference (oracle/_ref = src/interpolation.c unmodified): its one-shot
+    # mifi_interpolate_f and mifi_vector_reproject_values_f on the file's fields with fill values turned into NaN
+    # (data2InterpolationArray, CDMInterpolator.cc:115-119) for the CLI's target axes 5,5.5,6,6.5 / 61.5,62,62.5
+    nc = netcdf_file(os.path.join(ref, "test/hirlam12.nc"), "r", mmap=False)
+    for name in ("Xc", "Yc", "geopotential_height", "air_potential_temperature", "x_wind", "y_wind"):
+        out["hirlam_" + name] = native(nc.variables[name].data)
+    out["hirlam_fill"] = np.float32(nc.variables["x_wind"]._FillValue)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
+    from oracle import oracle as orc
+    if orc.Reference.available():
+        refc = orc.Reference()
+        sphere = "+proj=latlong +a=6371000 +e=0 +no_defs"
+        tx, ty = np.array([5, 5.5, 6, 6.5]), np.array([61.5, 62, 62.5])
+        out["hirlam_target_x"], out["hirlam_target_y"] = tx, ty
+        fields = {}
+        for name in ("geopotential_height", "air_potential_temperature", "x_wind", "y_wind"):
+            f = out["hirlam_" + name].astype(np.float32).reshape(4, 12, 17).copy()
+            f[f == out["hirlam_fill"]] = np.nan
+            rc, o = refc.interpolate_f(orc.BILINEAR, sphere, f, out["hirlam_Xc"], out["hirlam_Yc"], orc.LONGITUDE, orc.LATITUDE, 4, sphere,
+                                       tx, ty, orc.LONGITUDE, orc.LATITUDE)
+            assert rc == 1
+            fields[name] = o
+            out["hirlam_golden_" + name] = o
+        rc, u, v = refc.vector_reproject_values(sphere, sphere, fields["x_wind"], fields["y_wind"], tx, ty, orc.LONGITUDE, orc.LATITUDE, 4)
+        assert rc == 1
+        out["hirlam_golden_x_wind_rotated"], out["hirlam_golden_y_wind_rotated"] = u.reshape(4, 3, 4), v.reshape(4, 3, 4)
+
     dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "interpolator_fixtures.npz")
     np.savez_compressed(dst, **out)
     for k, v in out.items():

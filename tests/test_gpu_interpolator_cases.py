@@ -292,3 +292,46 @@ def test_interpolator_relative_axes(oracle):
     assert_bit_equal(got, ref.getDataSlice(field), "relative axes")
     with pytest.raises(fb.FimexB200Error):  # "only implemented for projections in m, not degree yet"
         interp.changeProjection("bilinear", "+proj=latlong +R=6371000", "0,1,...,x;relativeStart=0", "0,1,...,x;relativeStart=0", "degree", "degree")
+
+
+def test_config1_hirlam12_real_file(fx, oracle):
+    """BASELINE config 1 on the reference's OWN file: test/hirlam12.nc (time=2, pressure=2, Yc=12, Xc=17, float32 with
+    _FillValue 9.96921e+36, axes in degrees) through the CLI's option strings --interpolate.method=bilinear
+    --interpolate.projString="+proj=latlong ..." --interpolate.xAxisValues=5,5.5,6,6.5 --interpolate.yAxisValues=61.5,62,62.5
+    --interpolate.{x,y}AxisUnit=degree (src/binSrc/fimex.cc:1008-1034).  Golden = the COMPILED reference's mifi_interpolate_f /
+    mifi_vector_reproject_values_f on the same fields (tests/golden/make_interpolator_fixtures.py); bit for bit, fill values
+    where the reference has NaN (interpolationArray2Data, CDMInterpolator.cc:121-124)."""
+    sphere = "+proj=latlong +a=6371000 +e=0 +no_defs"
+    fill = np.float32(fx["hirlam_fill"])
+    assert fill == np.float32(9.96921e+36)
+    ip = fb.Interpolator(sphere, fx["hirlam_Xc"], fx["hirlam_Yc"], True, has_xy_vectors=True)
+    ip.changeProjection("bilinear", sphere, "5,5.5,6,6.5", "61.5,62,62.5", "degree", "degree")
+    for name in ("geopotential_height", "air_potential_temperature"):
+        data = fx["hirlam_" + name]
+        assert data.shape == (2, 2, 12, 17) and (data == fill).sum() > 0  # the file has undefined rows
+        golden = fx["hirlam_golden_" + name]
+        for t in range(2):  # one getDataSlice per unlimited-dimension position, as the writer calls it
+            got = ip.getDataSlice(data[t], bad_value=float(fill))
+            want = golden[2 * t:2 * t + 2]
+            assert got.dtype == np.float32 and got.shape == (2, 3, 4)
+            assert np.array_equal(got == fill, np.isnan(want)), name
+            assert_bit_equal(np.where(got == fill, np.float32(np.nan), got), want, f"hirlam12 {name} t={t}")
+        assert np.isnan(golden).sum() > 0 and (~np.isnan(golden)).sum() > 0
+    # x_wind / y_wind: spatial vectors, rotated with the lat/long-target bearing branch (interpolation.c:366,408); each
+    # component's call interpolates both and rotates (CDMInterpolator.cc:260-283)
+    xw, yw = fx["hirlam_x_wind"], fx["hirlam_y_wind"]
+    for t in range(2):
+        gu = ip.getDataSlice(xw[t], counterpart=yw[t], direction="x", bad_value=float(fill))
+        gv = ip.getDataSlice(yw[t], counterpart=xw[t], direction="y", bad_value=float(fill))
+        for got, key in ((gu, "x_wind_rotated"), (gv, "y_wind_rotated")):
+            want = fx["hirlam_golden_" + key][2 * t:2 * t + 2]
+            assert np.array_equal(got == fill, np.isnan(want)), key
+            ok = ~np.isnan(want)
+            assert np.abs(got[ok] - want[ok]).max() <= 1e-5 * np.abs(want[ok]).max(), key  # north_star: <= 1e-5 relative for vector output
+    # and the same numbers through the library's own one-shot C symbol (the reference's prototype)
+    f = fx["hirlam_air_potential_temperature"].reshape(4, 12, 17).copy()
+    f[f == fill] = np.nan
+    rc, out = fb.mifi_interpolate_f(Method.BILINEAR, sphere, f, fx["hirlam_Xc"], fx["hirlam_Yc"], fb.LONGITUDE, fb.LATITUDE, 4, sphere,
+                                    fx["hirlam_target_x"], fx["hirlam_target_y"], fb.LONGITUDE, fb.LATITUDE)
+    assert rc == fb.MIFI_OK
+    assert_bit_equal(out.reshape(4, 3, 4), fx["hirlam_golden_air_potential_temperature"], "hirlam12 mifi_interpolate_f")
