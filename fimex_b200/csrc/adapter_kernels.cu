@@ -35,9 +35,10 @@ __global__ void k_as_float(const T* __restrict__ in, long long n, int has_bad, f
         out[i] = load_as_float<T>(in[i], has_bad != 0, bad);
 }
 
-// interpolationArray2Data for a whole slab (used where the gather kernel does not convert while storing)
+// interpolationArray2Data for a whole slab (used where the gather kernel does not convert while storing).  No __restrict__:
+// for float output the pass runs IN PLACE (in == out, run_slice_device); every thread reads element i before it writes it.
 template <class Out>
-__global__ void k_from_float(const float* __restrict__ in, long long n, Out conv, typename Out::type* __restrict__ out)
+__global__ void k_from_float(const float* in, long long n, Out conv, typename Out::type* out)
 {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         out[i] = conv(in[i]);

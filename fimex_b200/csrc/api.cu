@@ -22,6 +22,8 @@
 #include <thread>
 #include <vector>
 
+#include <unistd.h>
+
 // ======================================================================================================
 // library state
 // ======================================================================================================
@@ -106,6 +108,26 @@ int default_device()
     }
     return t_device;
 }
+
+// Switch the calling thread's current device for a scope and put it back: destructors and helpers must not leak a
+// cudaSetDevice into the caller (a thread may alternate between handles that live on different GPUs).
+struct DeviceGuard {
+    int saved = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&saved) != cudaSuccess)
+            saved = -1;
+        if (dev >= 0 && dev != saved)
+            switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    bool ok(int dev) const { return switched || saved == dev; }
+    ~DeviceGuard()
+    {
+        if (switched && saved >= 0)
+            cudaSetDevice(saved);
+    }
+};
 
 cudaStream_t as_stream(void* s)
 {
@@ -221,6 +243,7 @@ struct fb200_interp {
     TileTable tiles;       // staged fast path of the bilinear / nearest-neighbour gather
     BicubicTiles bic_tiles; // staged fast path of the bicubic gather
     bool reduced = false;
+    bool invalid = false; // a table rebuild failed half-way (createReducedDomain out of memory): every later call is refused
     long long xMin = 0, yMin = 0;
     long long coordnn_ties = 0;
     // 2-D pre/post-processes of getDataSlice (CDMInterpolator::addPreprocess / addPostprocess, src/CDMInterpolator.cc:1886-1896)
@@ -235,7 +258,7 @@ struct fb200_interp {
 
     ~fb200_interp()
     {
-        cudaSetDevice(device);
+        fb::DeviceGuard on(device); // restored on return: destroying a handle does not change the caller's current device
         free_tables();
         if (d_px)
             cudaFree(d_px);
@@ -270,7 +293,7 @@ struct fb200_vector {
     double2* d_cs = nullptr;    // compact (cos, sin)
     ~fb200_vector()
     {
-        cudaSetDevice(device);
+        fb::DeviceGuard on(device);
         if (d_matrix)
             cudaFree(d_matrix);
         if (d_cs)
@@ -536,7 +559,8 @@ struct HostPipe {
     {
         if (device < 0)
             return;
-        if (cudaSetDevice(device) == cudaSuccess) { // fails harmlessly when the runtime is already shutting down
+        DeviceGuard on(device); // the caller's current device is put back afterwards
+        if (on.ok(device)) {    // fails harmlessly when the runtime is already shutting down
             for (auto& row : ev)
                 for (cudaEvent_t& e : row)
                     if (e)
@@ -557,23 +581,30 @@ struct HostPipe {
 
 HostPipe* host_pipe(int device)
 {
-    static thread_local HostPipe pipe;
-    if (pipe.device == device)
-        return &pipe;
-    pipe.destroy();
-    bool ok = cudaStreamCreateWithFlags(&pipe.up, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&pipe.run, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&pipe.down, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaEventCreateWithFlags(&pipe.ready, cudaEventDisableTiming) == cudaSuccess;
-    for (auto& row : pipe.ev)
+    // one pipe per (host thread, device): a thread that alternates between handles on two GPUs keeps both sets of streams
+    static thread_local std::map<int, std::unique_ptr<HostPipe>> pipes;
+    auto it = pipes.find(device);
+    if (it != pipes.end())
+        return it->second.get();
+    // streams and events belong to the device that is current when they are created: make that the handle's device for the
+    // duration, whatever the thread used last, and put the caller's device back
+    DeviceGuard on(device);
+    if (!on.ok(device))
+        return nullptr;
+    std::unique_ptr<HostPipe> pipe(new HostPipe());
+    bool ok = cudaStreamCreateWithFlags(&pipe->up, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&pipe->run, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&pipe->down, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&pipe->ready, cudaEventDisableTiming) == cudaSuccess;
+    for (auto& row : pipe->ev)
         for (cudaEvent_t& e : row)
             ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
-    pipe.device = device; // so that destroy() releases whatever was created
-    if (!ok) {
-        pipe.destroy();
-        return nullptr;
-    }
-    return &pipe;
+    pipe->device = device; // so that destroy() releases whatever was created
+    if (!ok)
+        return nullptr; // ~HostPipe releases the partial set
+    HostPipe* raw = pipe.get();
+    pipes.emplace(device, std::move(pipe));
+    return raw;
 }
 
 // ---- pageable host buffers ------------------------------------------------------------------------------------------------
@@ -838,6 +869,7 @@ bool known_type(int t)
 int check_interp_call(const fb200_interp* h, size_t size, size_t* nz)
 {
     FB_REQUIRE(h != nullptr, "null interpolation handle");
+    FB_REQUIRE(!h->invalid, "interpolation handle is unusable: createReducedDomain failed while rebuilding its tables");
     const size_t in_level = h->inX * h->inY;
     FB_REQUIRE(in_level > 0, "interpolation with an empty source grid");
     *nz = size / in_level; // CachedInterpolation.cc:121: inZ = size / (inX*inY), remainder ignored
@@ -1040,17 +1072,32 @@ unsigned long long fb200_kernel_launches(void)
 namespace {
 // Page-locked host buffers with a size-keyed free list.  Page-locking costs about as much as copying the buffer, so the
 // buffers a host allocates per slice (interpolateValues returns a NEW array per call, src/CachedInterpolation.cc:123) are
-// recycled instead of being unpinned: up to FIMEX_B200_PINNED_CACHE_MB (default 8192) stay cached.
+// recycled instead of being unpinned: up to FIMEX_B200_PINNED_CACHE_MB stay cached (default: RAM / 8, at most 8192;
+// fb200_host_trim() releases them).
 struct PinnedCache {
     std::mutex mu;
     std::multimap<size_t, void*> free_blocks;      // capacity -> block
     std::unordered_map<void*, size_t> capacity_of; // every live block, cached or handed out
     size_t cached_bytes = 0;
-    size_t limit()
+    // FIMEX_B200_PINNED_CACHE_MB (parsed once, clamped to [0, physical RAM / 2]); default: an eighth of the physical RAM, at
+    // most 8 GiB -- with 8 ranks per node the caches together stay within the RAM whatever the host has
+    static size_t limit()
     {
-        if (const char* env = std::getenv("FIMEX_B200_PINNED_CACHE_MB"))
-            return (size_t)std::atoll(env) << 20;
-        return (size_t)8192 << 20;
+        static const size_t value = []() {
+            size_t phys = (size_t)64 << 30;
+            const long pages = sysconf(_SC_PHYS_PAGES), page = sysconf(_SC_PAGE_SIZE);
+            if (pages > 0 && page > 0)
+                phys = (size_t)pages * (size_t)page;
+            size_t lim = std::min<size_t>((size_t)8 << 30, phys / 8);
+            if (const char* env = std::getenv("FIMEX_B200_PINNED_CACHE_MB")) {
+                char* end = nullptr;
+                const long long mb = std::strtoll(env, &end, 10);
+                if (end != env && mb >= 0)
+                    lim = std::min<size_t>((size_t)mb << 20, phys / 2);
+            }
+            return lim;
+        }();
+        return value;
     }
     void* get(size_t bytes)
     {
@@ -1122,8 +1169,14 @@ extern "C" {
 
 void* fb200_host_alloc(size_t bytes)
 {
-    if (use_device(default_device()) != FB_OK)
+    // Portable page-locked memory is usable from every device, so the calling thread's current device is left alone (a slice
+    // call on a handle of another GPU asks for its bounce buffers from here, mid-call).  Only a thread that has never touched
+    // CUDA gets the library's default device, because cudaHostAlloc needs some context.
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        set_error("no usable CUDA device (this library has no CPU fallback)");
         return nullptr;
+    }
     void* p = pinned_cache().get(bytes);
     if (!p)
         set_error("cudaHostAlloc failed");
@@ -1347,6 +1400,7 @@ int fb200_interp_create_reduced_domain(fb200_interp* h, int* reduced, long long*
     if (reduced)
         *reduced = 0;
     FB_REQUIRE(!h->forward, "createReducedDomain is defined for CachedInterpolation only");
+    FB_REQUIRE(!h->invalid, "interpolation handle is unusable: an earlier createReducedDomain failed");
     if (use_device(h->device) != FB_OK)
         return MIFI_ERROR;
     if (h->reduced) { // "don't set twice", CachedInterpolation.cc:161-163
@@ -1379,6 +1433,9 @@ int fb200_interp_create_reduced_domain(fb200_interp* h, int* reduced, long long*
     const long long y1 = clamp(0, std::ceil(hiy) + EXT, (long long)h->inY - 1);
     if ((x1 - x0) < 1 || (y1 - y0) < 1)
         return MIFI_OK;
+    // from here on the handle is being rewritten (positions shifted, tables rebuilt): a failure leaves it unusable, and it
+    // says so on every later call instead of gathering through freed tables
+    h->invalid = true;
     if (launch_shift(h->d_px, (long long)h->npts, (double)x0, st) != FB_OK || launch_shift(h->d_py, (long long)h->npts, (double)y0, st) != FB_OK)
         return MIFI_ERROR;
     h->inX = (size_t)(x1 - x0 + 1);
@@ -1388,6 +1445,7 @@ int fb200_interp_create_reduced_domain(fb200_interp* h, int* reduced, long long*
     h->reduced = true;
     if (compile_tables(h, st) != FB_OK)
         return MIFI_ERROR;
+    h->invalid = false;
     if (reduced)
         *reduced = 1;
     if (xMin)

@@ -76,6 +76,8 @@ struct TileTable {
     uint4* d_meta = nullptr;  // [tile][256] 4 x (a | b << 12 | mode << 24)
     float4* d_xf = nullptr;   // [tile][256]
     float4* d_yf = nullptr;   // [tile][256]
+    int* d_slow = nullptr;    // ids of the tiles with more taps than the tap-major staging buffer holds (pole, seam)
+    int n_slow = 0;
     bool nn = false;          // nearest-neighbour table (one tap per point, no xf/yf)
     bool ready() const { return d_cells != nullptr; }
 };

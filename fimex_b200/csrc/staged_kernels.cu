@@ -30,7 +30,11 @@
 #include "convert.cuh"
 #include "interp_math.cuh"
 
+#include <cuda.h> // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
+
 #include <cstdlib>
+#include <cstring>
+#include <vector>
 
 namespace fb {
 
@@ -225,11 +229,12 @@ __global__ void __launch_bounds__(kThreads, (NF == 1 ? (NN ? FB_NN_CTAS : 3) : 2
                              const uint4* __restrict__ meta, const float4* __restrict__ xf4, const float4* __restrict__ yf4,
                              const float* __restrict__ in0, const float* __restrict__ in1, typename Out::type* __restrict__ out0,
                              typename Out::type* __restrict__ out1, const double2* __restrict__ cs, Out conv, int fill_in, float bad0,
-                             float bad1, int vec_ok)
+                             float bad1, int vec_ok, const int* __restrict__ tile_list)
 {
     extern __shared__ __align__(16) float s_dyn[]; // [kBuffers][NF fields][kStageFloats]: later batches land while batch b is consumed
     auto stage = [&](int buf, int f) { return s_dyn + (buf * NF + f) * kStageFloats; };
-    const int tile = blockIdx.x;
+    // tile_list: this launch covers only the listed tiles (the many-tap tiles the bulk-store kernel leaves out)
+    const int tile = tile_list ? __ldg(tile_list + blockIdx.x) : (int)blockIdx.x;
     const int t = threadIdx.x;
     const int ntaps = __ldg(ntaps_tab + tile);
     const int* my_taps = taps + (size_t)tile * kMaxTaps;
@@ -492,6 +497,213 @@ __global__ void __launch_bounds__(kThreads, (NF == 1 ? (NN ? FB_NN_CTAS : 3) : 2
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ gather, bulk-store form
+// Same staging and arithmetic as k_gather_bilinear_staged, but the results of a batch of LZ levels are parked in a shared-memory
+// OUTPUT tile [LZ][Tile::Y][Tile::X] and leave the SM through the bulk-copy engine (TMA), not through per-thread STG:
+//   TENSOR = false: one cp.async.bulk.global.shared::cta (UBLKCP) per tile row and level, issued by LZ * Tile::Y threads;
+//   TENSOR = true : one cp.async.bulk.tensor.3d (UTMASTG) per batch -- box Tile::X x Tile::Y x LZ over the [z][y][x] output,
+//                   the tensor map clips rows / columns / levels outside the grid.
+// Why (scratch/ubench/tma_store_bw.cu, 2000-wide rows, pure stores): a 64 x 16 tile written with per-thread 128-byte warp
+// stores reaches 5.5 TB/s, the same tile through bulk copies 6.2-6.4 TB/s (the copy engine writes each 256-byte row run as one
+// request stream, independent of the lane mapping); and the store leaves the instruction stream: 16 STS with immediate offsets
+// per thread and step instead of 16 STG + their 64-bit address arithmetic (18 % of the instructions of the STG kernel).
+// Tiles with more taps than the tap-major staging holds (pole, seam) are skipped here; the STG kernel runs on exactly those
+// (TileTable::d_slow).
+__device__ __forceinline__ void bulk_store_row(void* gmem, const void* smem, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem), "r"((unsigned)__cvta_generic_to_shared(smem)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store_box(const CUtensorMap* map, const void* smem, int x, int y, int z)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+                 "r"((unsigned)__cvta_generic_to_shared(smem)), "r"(x), "r"(y), "r"(z)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit()
+{
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_all() // every bulk store this thread issued has finished READING shared memory
+{
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_shared() // generic-proxy shared stores -> visible to the async proxy (the copy engine)
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+template <int LZ, bool TENSOR, class Out>
+__global__ void __launch_bounds__(kThreads, LZ == 4 ? 3 : 2)
+    k_gather_bilinear_bulk(const __grid_constant__ CUtensorMap omap, GatherGeom g, int tiles_x, const int* __restrict__ taps,
+                           const int* __restrict__ ntaps_tab, const uint4* __restrict__ meta, const float4* __restrict__ xf4,
+                           const float4* __restrict__ yf4, const float* __restrict__ in0, typename Out::type* __restrict__ out0, Out conv,
+                           int fill_in, float bad0, int per)
+{
+    typedef typename Out::type T;
+    typedef Tile<false> TL;
+    constexpr int kStride = LZ == 8 ? kLvlStride : 4; // words between consecutive taps of the tap-major staging buffer
+    static_assert(LZ == 4 || LZ == 8, "levels per batch");
+    static_assert(LZ * TL::Y <= kThreads, "one row copy per thread");
+    extern __shared__ __align__(128) float s_dyn[];
+    float* const s_stage = s_dyn;                                             // [2][kStageFloats]
+    T* const s_out = reinterpret_cast<T*>(s_dyn + 2 * kStageFloats);          // [2][LZ][TL::Y][TL::X]
+    const int tile = blockIdx.x;
+    const int t = threadIdx.x;
+    const int ntaps = __ldg(ntaps_tab + tile);
+    if (ntaps > kFastTaps)
+        return; // whole CTA: a many-tap tile, done by the STG kernel
+    const int* my_taps = taps + (size_t)tile * kMaxTaps;
+    const size_t slot = (size_t)tile * kThreads + t;
+    const uint4 m = __ldg(meta + slot);
+    const float4 fx = __ldg(xf4 + slot), fy = __ldg(yf4 + slot);
+    const unsigned mm[4] = {m.x, m.y, m.z, m.w};
+    const float xf[4] = {fx.x, fx.y, fx.z, fx.w}, yf[4] = {fy.x, fy.y, fy.z, fy.w};
+    int ia[4], ib[4], mode[4];
+    float wx0[4], wy0[4];
+    bool all_full = true;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        ia[k] = (int)(mm[k] & 0xfffu) * kStride;
+        ib[k] = (int)((mm[k] >> 12) & 0xfffu) * kStride;
+        mode[k] = (int)(mm[k] >> 24);
+        wx0[k] = __fsub_rn(1.f, xf[k]);
+        wy0[k] = __fsub_rn(1.f, yf[k]);
+        all_full = all_full && (mode[k] == FB_BL_FULL);
+    }
+    const int tx = tile % tiles_x, ty = tile / tiles_x;
+    const long long z0 = (long long)blockIdx.y * per;
+    const long long z1 = z0 + per < g.nz ? z0 + per : g.nz;
+    if (z0 >= z1)
+        return;
+    // position of this thread's point 0 inside a level of the output tile; point k sits TL::RowStep rows further down
+    const int spos = t;                  // == (t / TL::X) * TL::X + t % TL::X
+    constexpr int kRowJump = kThreads;   // == TL::RowStep * TL::X
+    // the row this thread copies out (TENSOR = false): level cr_l of the batch, tile row cr_y
+    const int cr_l = t / TL::Y, cr_y = t % TL::Y;
+    const int gx0 = tx * TL::X, gy = ty * TL::Y + cr_y;
+    const int cols = g.ox - gx0 < TL::X ? g.ox - gx0 : TL::X;
+    const bool copier = !TENSOR && t < LZ * TL::Y && gy < g.oy;
+    const int tap0 = (t < ntaps) ? __ldg(my_taps + t) : -1;
+
+    auto issue = [&](int buf, long long z, int nb) {
+        float* dst = s_stage + buf * kStageFloats;
+        const float* lv = in0 + z * g.in_level;
+        if (tap0 >= 0) {
+            const float* src = lv + tap0;
+            float* d = dst + t * kStride;
+#pragma unroll
+            for (int zi = 0; zi < LZ; ++zi)
+                if (zi < nb)
+                    cp_async_f32(d + zi, src + zi * g.in_level);
+        }
+        if (ntaps > kThreads) {
+            for (int r = t + kThreads; r < ntaps; r += kThreads) {
+                const float* src = lv + __ldg(my_taps + r);
+                for (int zi = 0; zi < nb; ++zi)
+                    cp_async_f32(dst + r * kStride + zi, src + zi * g.in_level);
+            }
+        }
+        cp_async_commit();
+    };
+    auto patch = [&](int buf, int nb) { // mifi_bad2nanf on the elements this thread copied itself
+        const float nanv = undef_f();
+        float* dst = s_stage + buf * kStageFloats;
+        for (int r = t; r < ntaps; r += kThreads)
+            for (int zi = 0; zi < nb; ++zi)
+                if (dst[r * kStride + zi] == bad0)
+                    dst[r * kStride + zi] = nanv;
+    };
+    auto send = [&](int buf, long long z, int nb) { // the finished output tile of batch (buf, z) leaves through the copy engine
+        const T* src = s_out + (size_t)buf * LZ * kTilePts;
+        if (TENSOR) {
+            if (t == 0) {
+                bulk_store_box(&omap, src, gx0, ty * TL::Y, (int)z);
+                bulk_commit();
+            }
+        } else if (copier && cr_l < nb) {
+            bulk_store_row(out0 + (z + cr_l) * g.out_level + (long long)gy * g.ox + gx0, src + (cr_l * TL::Y + cr_y) * TL::X,
+                           (unsigned)(cols * sizeof(T)));
+            bulk_commit();
+        }
+    };
+
+    issue(0, z0, (int)((z1 - z0) < LZ ? (z1 - z0) : LZ));
+    int buf = 0;
+    long long zprev = z0;
+    int nbprev = 0;
+    for (long long z = z0; z < z1; z += LZ, buf ^= 1) {
+        const int nb = (int)((z1 - z) < LZ ? (z1 - z) : LZ);
+        cp_async_wait_pending<0>();
+        if (fill_in)
+            patch(buf, nb);
+        bulk_wait_read_all(); // this thread's copies out of s_out[buf] (issued two batches ago) are done reading it
+        __syncthreads();      // batch z is staged; everyone has finished (and fenced) the output tile of the previous batch
+        if (z + LZ < z1)
+            issue(buf ^ 1, z + LZ, (int)((z1 - z - LZ) < LZ ? (z1 - z - LZ) : LZ));
+        if (nbprev)
+            send(buf ^ 1, zprev, nbprev);
+        const float* lvl = s_stage + buf * kStageFloats;
+        T* so = s_out + (size_t)buf * LZ * kTilePts + spos;
+        if (all_full) {
+#pragma unroll
+            for (int q = 0; q < LZ / 4; ++q) {
+                float r[4][4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float4 a0 = *reinterpret_cast<const float4*>(lvl + ia[k] + 4 * q);
+                    const float4 a1 = *reinterpret_cast<const float4*>(lvl + ia[k] + kStride + 4 * q);
+                    const float4 b0 = *reinterpret_cast<const float4*>(lvl + ib[k] + 4 * q);
+                    const float4 b1 = *reinterpret_cast<const float4*>(lvl + ib[k] + kStride + 4 * q);
+                    r[k][0] = bilinear_full(wx0[k], xf[k], wy0[k], yf[k], a0.x, a1.x, b0.x, b1.x);
+                    r[k][1] = bilinear_full(wx0[k], xf[k], wy0[k], yf[k], a0.y, a1.y, b0.y, b1.y);
+                    r[k][2] = bilinear_full(wx0[k], xf[k], wy0[k], yf[k], a0.z, a1.z, b0.z, b1.z);
+                    r[k][3] = bilinear_full(wx0[k], xf[k], wy0[k], yf[k], a0.w, a1.w, b0.w, b1.w);
+                }
+#pragma unroll
+                for (int l = 0; l < 4; ++l)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        so[(4 * q + l) * kTilePts + k * kRowJump] = conv(r[k][l]);
+            }
+        } else { // a point on an edge strip or outside the source grid: per-point mode (interpolation.c:904-953)
+            for (int zi = 0; zi < nb; ++zi) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float v = undef_f();
+                    const float* qa = lvl + ia[k] + zi;
+                    const float* qb = lvl + ib[k] + zi;
+                    switch (mode[k]) {
+                    case FB_BL_FULL:
+                        v = bilinear_full(wx0[k], xf[k], wy0[k], yf[k], qa[0], qa[kStride], qb[0], qb[kStride]);
+                        break;
+                    case FB_BL_XLIN:
+                        v = __fadd_rn(__fmul_rn(wx0[k], qa[0]), __fmul_rn(xf[k], qa[kStride]));
+                        break;
+                    case FB_BL_YLIN:
+                        v = __fadd_rn(__fmul_rn(wy0[k], qa[0]), __fmul_rn(yf[k], qb[0]));
+                        break;
+                    case FB_BL_NEAR:
+                        v = qa[0];
+                        break;
+                    default:
+                        break;
+                    }
+                    so[zi * kTilePts + k * kRowJump] = conv(v);
+                }
+            }
+        }
+        fence_async_shared();
+        zprev = z;
+        nbprev = nb;
+    }
+    __syncthreads();
+    send(buf ^ 1, zprev, nbprev);
+    bulk_wait_read_all(); // shared memory must outlive the copies that read it
+}
+
 } // namespace
 
 bool tile_table_supported(int ix, int iy, int ox, int oy)
@@ -523,11 +735,27 @@ int tile_table_build(bool nn, const double* d_px, const double* d_py, int ix, in
     }
     count_launch();
     FB_CUDA_CHECK(cudaGetLastError());
+    // the tiles whose tap list does not fit the tap-major staging buffer (over the pole, across the seam): the bulk-store
+    // gather leaves them to the STG kernel, which is launched on exactly this list
+    std::vector<int> ntaps(tiles), slow;
+    FB_CUDA_CHECK(cudaMemcpyAsync(ntaps.data(), tt->d_ncells, sizeof(int) * tiles, cudaMemcpyDeviceToHost, st));
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < tiles; ++i)
+        if (ntaps[i] > kFastTaps)
+            slow.push_back((int)i);
+    tt->n_slow = (int)slow.size();
+    if (!slow.empty()) {
+        FB_CUDA_CHECK(cudaMalloc(&tt->d_slow, sizeof(int) * slow.size()));
+        FB_CUDA_CHECK(cudaMemcpyAsync(tt->d_slow, slow.data(), sizeof(int) * slow.size(), cudaMemcpyHostToDevice, st));
+        FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
     return FB_OK;
 }
 
 void tile_table_free(TileTable* tt)
 {
+    if (tt->d_slow)
+        cudaFree(tt->d_slow);
     if (tt->d_cells)
         cudaFree(tt->d_cells);
     if (tt->d_ncells)
@@ -546,13 +774,13 @@ constexpr size_t kStageBytes = kBuffers * kStageFloats * sizeof(float); // per f
 
 template <bool NN, class Out>
 void launch_staged_as(dim3 grid, const GatherGeom& g, const TileTable& tt, const float* d_in, void* d_out, Out conv, const SliceConv& sc,
-                      cudaStream_t st)
+                      cudaStream_t st, const int* tile_list = nullptr)
 {
     typedef typename Out::type T;
     const int vec_ok = ((g.ox % 4) == 0 && (reinterpret_cast<uintptr_t>(d_out) & (4 * sizeof(T) - 1)) == 0) ? 1 : 0;
     k_gather_bilinear_staged<NN, 1, false, Out><<<grid, kThreads, kStageBytes, st>>>(g, tt.tiles_x, tt.d_cells, tt.d_ncells, tt.d_meta, tt.d_xf,
                                                                                       tt.d_yf, d_in, nullptr, static_cast<T*>(d_out), nullptr,
-                                                                                      nullptr, conv, sc.fill_in ? 1 : 0, sc.bad_in[0], 0.f, vec_ok);
+                                                                                      nullptr, conv, sc.fill_in ? 1 : 0, sc.bad_in[0], 0.f, vec_ok, tile_list);
 }
 
 template <bool NN, bool ROT>
@@ -566,22 +794,22 @@ cudaError_t launch_staged_vector(dim3 grid, const GatherGeom& g, const TileTable
     const uintptr_t align = reinterpret_cast<uintptr_t>(d_uo) | reinterpret_cast<uintptr_t>(d_vo);
     const int vec_ok = ((g.ox % 4) == 0 && (align & 15u) == 0) ? 1 : 0;
     kernel<<<grid, kThreads, 2 * kStageBytes, st>>>(g, tt.tiles_x, tt.d_cells, tt.d_ncells, tt.d_meta, tt.d_xf, tt.d_yf, d_u, d_v, d_uo, d_vo, d_cs,
-                                                    StorePlain(), sc.fill_in ? 1 : 0, sc.bad_in[0], sc.bad_in[1], vec_ok);
+                                                    StorePlain(), sc.fill_in ? 1 : 0, sc.bad_in[0], sc.bad_in[1], vec_ok, nullptr);
     return cudaSuccess;
 }
 
 template <bool NN>
 bool launch_staged_typed(dim3 grid, const GatherGeom& g, const TileTable& tt, const float* d_in, void* d_out, const SliceConv& sc,
-                         cudaStream_t st)
+                         cudaStream_t st, const int* tile_list = nullptr)
 {
     if (!sc.convert_out) {
-        launch_staged_as<NN>(grid, g, tt, d_in, d_out, StorePlain(), sc, st);
+        launch_staged_as<NN>(grid, g, tt, d_in, d_out, StorePlain(), sc, st, tile_list);
         return true;
     }
     switch (sc.out_type) {
 #define FB_CASE(TAG, T)                                                                                                                    \
     case TAG:                                                                                                                              \
-        launch_staged_as<NN>(grid, g, tt, d_in, d_out, StoreAs<T>{cast_fill<T>(sc.fill_out)}, sc, st);                                     \
+        launch_staged_as<NN>(grid, g, tt, d_in, d_out, StoreAs<T>{cast_fill<T>(sc.fill_out)}, sc, st, tile_list);                          \
         return true;
         FB_CASE(FB_T_FLOAT, float)
         FB_CASE(FB_T_DOUBLE, double)
@@ -616,12 +844,135 @@ bool staged_store_supports(int out_type)
     }
 }
 
+namespace {
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point: the library does not link libcuda
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder()
+{
+    static const EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// 3-D map of the [z][y][x] output for boxes of Tile::X x Tile::Y x lz elements
+bool output_tensor_map(void* d_out, const GatherGeom& g, size_t elem, int lz, CUtensorMap* map)
+{
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc)
+        return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)g.ox, (cuuint64_t)g.oy, (cuuint64_t)g.nz};
+    const cuuint64_t strides[2] = {(cuuint64_t)g.ox * elem, (cuuint64_t)g.out_level * elem};
+    const cuuint32_t box[3] = {(cuuint32_t)Tile<false>::X, (cuuint32_t)Tile<false>::Y, (cuuint32_t)lz};
+    const cuuint32_t es[3] = {1, 1, 1};
+    const CUtensorMapDataType dt = elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16; // moved as bits
+    return enc(map, dt, 3, d_out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// FIMEX_B200_BULK_STORE: 0 = per-thread STG (the round-1 kernel), 1 = row copies (UBLKCP), 2 = tensor boxes (UTMASTG);
+// FIMEX_B200_BULK_LEVELS: 4 or 8 levels per batch.  Read at every launch (A/B runs switch it inside one process).
+int env_int(const char* name, int dflt)
+{
+    const char* e = std::getenv(name);
+    return (e && *e) ? std::atoi(e) : dflt;
+}
+
+template <int LZ, bool TENSOR, class Out>
+cudaError_t launch_bulk_as(dim3 grid, const CUtensorMap& map, const GatherGeom& g, const TileTable& tt, const float* d_in, void* d_out, Out conv,
+                           const SliceConv& sc, int per, cudaStream_t st)
+{
+    typedef typename Out::type T;
+    auto kernel = k_gather_bilinear_bulk<LZ, TENSOR, Out>;
+    const size_t smem = 2 * kStageFloats * sizeof(float) + 2 * (size_t)LZ * kTilePts * sizeof(T);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess)
+        return e;
+    kernel<<<grid, kThreads, smem, st>>>(map, g, tt.tiles_x, tt.d_cells, tt.d_ncells, tt.d_meta, tt.d_xf, tt.d_yf, d_in, static_cast<T*>(d_out),
+                                         conv, sc.fill_in ? 1 : 0, sc.bad_in[0], per);
+    return cudaGetLastError();
+}
+
+template <class Out>
+cudaError_t launch_bulk_shape(int lz, bool tensor, dim3 grid, const CUtensorMap& map, const GatherGeom& g, const TileTable& tt, const float* d_in,
+                              void* d_out, Out conv, const SliceConv& sc, int per, cudaStream_t st)
+{
+    if (lz == 4)
+        return tensor ? launch_bulk_as<4, true>(grid, map, g, tt, d_in, d_out, conv, sc, per, st)
+                      : launch_bulk_as<4, false>(grid, map, g, tt, d_in, d_out, conv, sc, per, st);
+    return tensor ? launch_bulk_as<8, true>(grid, map, g, tt, d_in, d_out, conv, sc, per, st)
+                  : launch_bulk_as<8, false>(grid, map, g, tt, d_in, d_out, conv, sc, per, st);
+}
+
+} // namespace
+
 int launch_gather_bilinear_staged(const GatherGeom& g, const TileTable& tt, const float* d_in, void* d_out, const SliceConv& sc,
                                   cudaStream_t st)
 {
     if (g.out_level == 0 || g.nz == 0)
         return FB_OK;
     const unsigned tiles = (unsigned)tt.tiles_x * (unsigned)tt.tiles_y;
+    // ---- bilinear, 2- and 4-byte output elements: output tiles staged in shared memory, stored by the copy engine ----
+    // Opt-in (default 0): measured on config 2, same box (profiles/r02_bulk_store_ab.txt), the bulk-store forms are bit-identical
+    // but SLOWER than per-thread STG -- 12.8 ms (tensor boxes, 8 levels) / 14.6 ms (row copies) against 10.9 ms -- although the
+    // same tiles store faster in isolation (6.2-6.4 against 5.5 TB/s): the gather is bound by the shared-memory data pipe, and the
+    // output tile adds one STS and one copy-engine read of every value to the 4.45 tap-load wavefronts per 32 outputs.
+    const int mode = env_int("FIMEX_B200_BULK_STORE", 0);
+    size_t elem = 4;
+    bool bulk_type = !sc.convert_out || sc.out_type == FB_T_FLOAT;
+    if (sc.convert_out && (sc.out_type == FB_T_SHORT || sc.out_type == FB_T_USHORT)) {
+        elem = 2;
+        bulk_type = true;
+    }
+    if (sc.convert_out && (sc.out_type == FB_T_INT || sc.out_type == FB_T_UINT))
+        bulk_type = true;
+    const bool bulk_ok = !tt.nn && mode != 0 && bulk_type && (g.ox * elem) % 16 == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15u) == 0 &&
+                         (g.out_level * (long long)elem) % 16 == 0 && g.nz < 2147483647LL;
+    if (bulk_ok) {
+        const int lz = env_int("FIMEX_B200_BULK_LEVELS", 8) == 4 ? 4 : 8;
+        const bool tensor = mode == 2;
+        const int chunks = z_chunks(tiles, g.nz, env_int("FIMEX_B200_BULK_CHUNK", 128));
+        int per = (int)((g.nz + chunks - 1) / chunks);
+        per = (per + lz - 1) / lz * lz; // whole batches per chunk: a tensor box never reaches into the next chunk's levels
+        dim3 grid(tiles, (unsigned)((g.nz + per - 1) / per));
+        CUtensorMap map;
+        std::memset(&map, 0, sizeof(map));
+        FB_REQUIRE(!tensor || output_tensor_map(d_out, g, elem, lz, &map), "cuTensorMapEncodeTiled failed for the output tensor");
+        cudaError_t e = cudaErrorInvalidValue;
+        if (!sc.convert_out) {
+            e = launch_bulk_shape(lz, tensor, grid, map, g, tt, d_in, d_out, StorePlain(), sc, per, st);
+        } else {
+            switch (sc.out_type) {
+#define FB_CASE(TAG, T)                                                                                                                    \
+    case TAG:                                                                                                                              \
+        e = launch_bulk_shape(lz, tensor, grid, map, g, tt, d_in, d_out, StoreAs<T>{cast_fill<T>(sc.fill_out)}, sc, per, st);               \
+        break;
+                FB_CASE(FB_T_FLOAT, float)
+                FB_CASE(FB_T_SHORT, short)
+                FB_CASE(FB_T_USHORT, unsigned short)
+                FB_CASE(FB_T_INT, int)
+                FB_CASE(FB_T_UINT, unsigned int)
+#undef FB_CASE
+            default:
+                break;
+            }
+        }
+        FB_CUDA_CHECK(e);
+        count_launch();
+        if (tt.n_slow > 0) { // the many-tap tiles, through the STG kernel
+            dim3 sgrid((unsigned)tt.n_slow, z_chunks(tt.n_slow, g.nz, 128));
+            FB_REQUIRE(launch_staged_typed<false>(sgrid, g, tt, d_in, d_out, sc, st, tt.d_slow), "staged gather: unsupported output type");
+            count_launch();
+            FB_CUDA_CHECK(cudaGetLastError());
+        }
+        return FB_OK;
+    }
     // levels per CTA: same-box sweep on config 2 (ms per step), bilinear 64 / 96 / 128 / 160 -> 11.47 / 11.37 / 11.27 / 11.33,
     // nearest neighbour 48 / 64 / 96 -> 9.87 / 9.73 / 9.80
     dim3 grid(tiles, z_chunks(tiles, g.nz, tt.nn ? 64 : 128));

@@ -1176,3 +1176,30 @@ def test_concurrent_large_pageable_slices(oracle):
     assert not errors, errors
     for i in range(4):
         assert_bit_equal(got[i], want[i], f"thread {i}")
+
+
+@pytest.mark.parametrize("mode,levels", [("1", "8"), ("1", "4"), ("2", "8"), ("2", "4")])
+def test_bulk_store_forms_are_bit_identical(oracle, monkeypatch, mode, levels):
+    """FIMEX_B200_BULK_STORE=1 (cp.async.bulk row copies) / 2 (cp.async.bulk.tensor boxes): the bilinear gather with its output tile
+    staged in shared memory and stored by the copy engine -- opt-in (slower than per-thread stores on B200,
+    profiles/r02_bulk_store_ab.txt), same bits: float, fill-value float and int16 output, partial tiles, partial batches, a
+    many-tap tile (target coarser than the source) handled by the fallback launch"""
+    monkeypatch.setenv("FIMEX_B200_BULK_STORE", mode)
+    monkeypatch.setenv("FIMEX_B200_BULK_LEVELS", levels)
+    for (inX, inY, inZ, outX, outY, angle, zoom) in ((60, 50, 19, 200, 152, 17.0, 5.0), (90, 70, 70, 328, 77, -33.0, 6.5), (300, 40, 9, 256, 96, 3.0, 0.6)):
+        px, py = _smooth_positions(inX, inY, outX, outY, angle, zoom, 7)
+        rng = np.random.default_rng(inZ)
+        field = rng.normal(250, 30, (inZ, inY, inX)).astype(np.float32)
+        field[rng.random(field.shape) < 0.02] = np.nan
+        want = oracle.cached_interpolate(1, px, py, inX, inY, outX, outY, field)
+        ci = fb.CachedInterpolation("x", "y", Method.BILINEAR, px, py, inX, inY, outX, outY)
+        assert_bit_equal(ci.interpolateValues(field), want, f"bulk store mode {mode}, {levels} levels, plain float")
+        fill = np.float32(9.96921e+36)
+        filled = np.where(np.isnan(field), fill, field)
+        got = ci.getDataSlice(filled, float(fill))
+        assert_bit_equal(got, np.where(np.isnan(want), fill, want), f"bulk store mode {mode}: float with fill values")
+        packed = np.clip(np.round(np.nan_to_num(field, nan=250.0) * 10), -32000, 32000).astype(np.int16)
+        packed[np.isnan(field)] = -32767
+        want16 = oracle.from_float(oracle.cached_interpolate(1, px, py, inX, inY, outX, outY, oracle.as_float(packed, -32767.0)), -32767.0, np.int16)
+        got16 = ci.getDataSlice(packed, -32767.0)
+        assert got16.dtype == np.int16 and np.array_equal(got16, want16), f"bulk store mode {mode}: int16"
