@@ -25,6 +25,10 @@ from .cached import CachedForwardInterpolation, CachedInterpolation, CachedVecto
 from .interpolator import Interpolator, axis_spec_requires_start_end, spatial_axis_spec, tokenize_dotted
 from .processor import Processor
 
+#: opt-in arithmetic modes of the bicubic gather (environment, read at every launch): FIMEX_B200_BICUBIC_FP32=1 (fp32 weights and
+#: FMAs, <= 1e-5 relative, identical NaN masks), FIMEX_B200_BICUBIC_CONTRACT=1 (fp64 FMA chains); default: bit-identical
+BICUBIC_FP32_AVAILABLE = True
+
 __all__ = [
     "CachedInterpolation", "CachedForwardInterpolation", "CachedVectorReprojection", "Interpolator", "Processor", "spatial_axis_spec", "axis_spec_requires_start_end", "tokenize_dotted", "Method", "DataType", "cdm_type", "default_fill_value", "FimexB200Error",
     "MIFI_OK", "MIFI_ERROR", "PROJ_AXIS", "LONGITUDE", "LATITUDE", "MIFI_VECTOR_KEEP_SIZE", "load", "lib_path", "version", "last_error",

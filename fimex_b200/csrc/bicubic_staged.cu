@@ -51,6 +51,8 @@ constexpr int kStageElems = 8 * kT;                  // tap values staged per ba
 constexpr int kTapCap = kStageElems;                 // tiles with more distinct taps are computed directly
 constexpr int kFastTaps = kT;                        // at most this many taps: one tap per thread, 8 levels per batch
 constexpr int kStageDoubles = 2 * kFastTaps * 5;     // per buffer: max(256*9, 2*256*5, 2048) = 2560 doubles
+constexpr int kStageFloats32 = kFastTaps * 12;       // fp32 mode, per buffer: max(256*12, 2*256*4, 2048) = 3072 floats
+constexpr int stage_elems(bool fp32) { return fp32 ? kStageFloats32 : kStageDoubles; }
 constexpr int kMaxTapKeys = 16384;                   // 16 stencil taps for each of at most 896 distinct cells, padded to 2^k
 constexpr int kNoKey = 0x7fffffff;
 #ifndef FB_BIC_UNROLL
@@ -300,14 +302,34 @@ __global__ void __launch_bounds__(kT) k_compile_bicubic_tiles(const int* __restr
 constexpr size_t kCompileSmem = sizeof(unsigned long long) * kSortN + sizeof(int) * (kMaxTapKeys + 3 * kSortN + kTapCap);
 
 // ------------------------------------------------------------------------------------------------ gather
-struct Group {
-    double wx[4][4], wy[4][4];
-    int row[4]; // first tap of each stencil row, in doubles from the start of a field's staging area
+// Arithmetic of the gather (template tag ARITH):
+//   kExact    the reference's operation order in fp64, every multiply and add rounded separately, the accumulator re-rounded
+//             to fp32 after each stencil row: bit-identical (default)
+//   kContract fp64 FMA chains, one final rounding (opt-in FIMEX_B200_BICUBIC_CONTRACT=1)
+//   kFp32     opt-in FIMEX_B200_BICUBIC_FP32=1: the separable weights are computed in fp64 exactly as the reference computes
+//             them (interpolation.c:962-1000) and rounded to fp32 ONCE per point; taps stay fp32 (no conversion at all) and the
+//             20 multiply-adds per output are fp32 FMAs.  Not bit-identical; the NaN mask is (every tap enters every product
+//             chain), the values agree within 1e-5 of the largest tap of the 4x4 stencil -- north_star's bar for bicubic.  It
+//             takes the kernel off the fp64 pipe (35 fp64 instructions per output at 64 lanes/clk/SM) onto the fp32 pipe.
+enum { kExact = 0, kContract = 1, kFp32 = 2 };
+template <int ARITH>
+struct ArithTypes {
+    typedef double tap; // type of a staged tap and of a weight
+};
+template <>
+struct ArithTypes<kFp32> {
+    typedef float tap;
+};
+
+template <class W>
+struct GroupT {
+    W wx[4][4], wy[4][4];
+    int row[4]; // first tap of each stencil row, in elements from the start of a field's staging area
     int pt[4];  // output-tile slots
 };
 
-template <int S>
-__device__ __forceinline__ void load_group(Group& gr, const uint4* __restrict__ gmeta, const double2* __restrict__ gfrac, size_t gid)
+template <int S, class W>
+__device__ __forceinline__ void load_group(GroupT<W>& gr, const uint4* __restrict__ gmeta, const double2* __restrict__ gfrac, size_t gid)
 {
     const uint4 m = __ldg(gmeta + gid);
     gr.row[0] = (int)(m.x & 0xffffu) * S;
@@ -321,8 +343,14 @@ __device__ __forceinline__ void load_group(Group& gr, const uint4* __restrict__ 
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
         const double2 f = __ldg(gfrac + gid * 4 + p);
-        cubic_weights(f.x, gr.wx[p]);
-        cubic_weights(f.y, gr.wy[p]);
+        double wx[4], wy[4];
+        cubic_weights(f.x, wx); // fp64, the reference's own sums; rounded once when W is float
+        cubic_weights(f.y, wy);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            gr.wx[p][i] = (W)wx[i];
+            gr.wy[p][i] = (W)wy[i];
+        }
     }
 }
 
@@ -332,10 +360,11 @@ __device__ __forceinline__ void load_group(Group& gr, const uint4* __restrict__ 
 // the same sums as fp64 FMA chains with ONE final rounding to fp32 (20 fp64 instructions + 1 conversion) -- not bit-identical,
 // within 1e-5 of the field's magnitude (the tolerance the north star states for interpolated floats), since every
 // intermediate is at least as accurate as the reference's.
-template <int NF, bool ROT, int S, int NL, bool EXACT>
-__device__ __forceinline__ void compute_levels(const Group& gr, const double* __restrict__ st, int field_stride, float* __restrict__ s_out,
-                                               int out_field_stride, const double2* __restrict__ s_cs)
+template <int NF, bool ROT, int S, int NL, int ARITH>
+__device__ __forceinline__ void compute_levels(const GroupT<double>& gr, const double* __restrict__ st, int field_stride,
+                                               float* __restrict__ s_out, int out_field_stride, const double2* __restrict__ s_cs)
 {
+    constexpr bool EXACT = ARITH == kExact;
     float a[NL][NF][4];
     if (EXACT) {
 #pragma unroll
@@ -389,6 +418,63 @@ __device__ __forceinline__ void compute_levels(const Group& gr, const double* __
 #pragma unroll
             for (int l = 0; l < NL; ++l)
                 rotate_uv(a[l][0][p], a[l][NF - 1][p], c.x, c.y);
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < NL; ++l)
+#pragma unroll
+        for (int f = 0; f < NF; ++f)
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+                s_out[f * out_field_stride + l * kOutRow + gr.pt[p]] = a[l][f][p];
+}
+
+
+// kFp32: fp32 taps, fp32 weights, 20 FMAs per output.  NL = 4 reads four levels of a tap with one 128-bit shared load (the
+// staging buffer is tap-major with a 16-byte aligned stride); the rotation is done in fp32 as well.
+template <int NF, bool ROT, int S, int NL, int ARITH>
+__device__ __forceinline__ void compute_levels(const GroupT<float>& gr, const float* __restrict__ st, int field_stride, float* __restrict__ s_out,
+                                               int out_field_stride, const double2* __restrict__ s_cs)
+{
+    static_assert(NL == 1 || NL == 4, "one level or one 128-bit load of four");
+    float a[NL][NF][4];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        const float* sf = st + f * field_stride;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float* rp = sf + gr.row[r];
+            float v[4][NL];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (NL == 4) {
+                    const float4 q = *reinterpret_cast<const float4*>(rp + c * S);
+                    v[c][0] = q.x, v[c][1 % NL] = q.y, v[c][2 % NL] = q.z, v[c][3 % NL] = q.w;
+                } else {
+                    v[c][0] = rp[c * S];
+                }
+            }
+#pragma unroll
+            for (int l = 0; l < NL; ++l) {
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const float row = fmaf(gr.wx[p][3], v[3][l], fmaf(gr.wx[p][2], v[2][l], fmaf(gr.wx[p][1], v[1][l], gr.wx[p][0] * v[0][l])));
+                    a[l][f][p] = (r == 0) ? row * gr.wy[p][0] : fmaf(row, gr.wy[p][r], a[l][f][p]);
+                }
+            }
+        }
+    }
+    if (ROT) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const double2 c = s_cs[gr.pt[p]];
+            const float cc = (float)c.x, ss = (float)c.y;
+#pragma unroll
+            for (int l = 0; l < NL; ++l) {
+                const float u = a[l][0][p], w = a[l][NF - 1][p];
+                a[l][0][p] = fmaf(u, cc, -(w * ss));
+                a[l][NF - 1][p] = fmaf(u, ss, w * cc);
+            }
         }
     }
 #pragma unroll
@@ -478,17 +564,22 @@ __device__ void direct_tile(const GatherGeom& g, int tx, int ty, long long z0, l
 // FAST: at most 256 taps; 8/NF levels per batch; warp w stages (field, level) row w of the batch and later stores
 //       (field, level) row w of the output tile.
 // else: up to 2048/NF taps, one level per batch, every thread stages 8/NF taps per field.
-template <int NF, bool ROT, bool FAST, class Out, bool EXACT>
+template <int NF, bool ROT, bool FAST, class Out, int ARITH>
 __device__ __forceinline__ void staged_tile(const GatherGeom& g, int tx, int ty, long long z0, long long z1, int4 inf,
                                             const int* __restrict__ taps, const uint4* __restrict__ gmeta, const double2* __restrict__ gfrac,
                                             const double2* __restrict__ cs, const float* __restrict__ in0, const float* __restrict__ in1,
                                             typename Out::type* __restrict__ out0, typename Out::type* __restrict__ out1, bool vec_ok,
-                                            double* s_stage, float* s_out, double2* s_cs, const Out& conv, bool fill_in, float bad0,
-                                            float bad1)
+                                            typename ArithTypes<ARITH>::tap* s_stage, float* s_out, double2* s_cs, const Out& conv,
+                                            bool fill_in, float bad0, float bad1)
 {
     typedef typename Out::type OutT;
+    typedef typename ArithTypes<ARITH>::tap TapT;
     constexpr int L = FAST ? 8 / NF : 1;
-    constexpr int S = (L == 1) ? 1 : L + 1; // odd tap stride (in doubles): distinct taps of a warp land in distinct banks
+    // tap stride of the tap-major staging buffer.  fp64: odd (in doubles), so that the distinct taps of a warp land in distinct
+    // banks.  fp32: a multiple of 4 floats (128-bit loads of four levels) whose first eight multiples fall into eight different
+    // 16-byte bank groups: 12 for 8 levels, 4 for 4 levels.
+    constexpr int S = (L == 1) ? 1 : (ARITH == kFp32 ? (L == 8 ? 12 : 4) : L + 1);
+    constexpr int NLV = (ARITH == kFp32) ? 4 : kNL; // levels per inner step of a full batch
     constexpr int NREG = 8;
     static_assert(NF * L <= kOutRows, "output tile");
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -512,7 +603,7 @@ __device__ __forceinline__ void staged_tile(const GatherGeom& g, int tx, int ty,
             s_cs[slot] = c;
         }
     }
-    Group gr;
+    GroupT<TapT> gr;
     if (rounds == 1 && t < ngroups)
         load_group<S>(gr, gmeta, gfrac, (size_t)inf.z + t);
 
@@ -533,8 +624,8 @@ __device__ __forceinline__ void staged_tile(const GatherGeom& g, int tx, int ty,
             }
         }
     };
-    auto park = [&](int buf) { // the ONE fp32 -> fp64 conversion of each tap value
-        double* dst = s_stage + buf * kStageDoubles + my_zi;
+    auto park = [&](int buf) { // the ONE fp32 -> fp64 conversion of each tap value (none in fp32 mode)
+        TapT* dst = s_stage + buf * stage_elems(ARITH == kFp32) + my_zi;
 #pragma unroll
         for (int j = 0; j < NREG; ++j) {
             const int r = tap_of(j);
@@ -542,7 +633,7 @@ __device__ __forceinline__ void staged_tile(const GatherGeom& g, int tx, int ty,
                 float v = regs[j];
                 if (fill_in && v == (field_of(j) == 0 ? bad0 : bad1)) // mifi_bad2nanf, once per tap
                     v = undef_f();
-                dst[field_of(j) * field_stride + r * S] = (double)v;
+                dst[field_of(j) * field_stride + r * S] = (TapT)v;
             }
         }
     };
@@ -598,21 +689,21 @@ __device__ __forceinline__ void staged_tile(const GatherGeom& g, int tx, int ty,
     int buf = 0;
     for (long long z = z0; z < z1; z += L, buf ^= 1) {
         const int nb = (int)((z1 - z) < L ? (z1 - z) : L);
-        const double* st = s_stage + buf * kStageDoubles;
+        const TapT* st = s_stage + buf * stage_elems(ARITH == kFp32);
         float* tile = s_out + buf * (kOutRows * kOutRow);
         for (int rd = 0; rd < rounds; ++rd) {
             const int gi = rd * kT + t;
             if (gi < ngroups) {
                 if (rounds > 1)
                     load_group<S>(gr, gmeta, gfrac, (size_t)inf.z + gi);
-                if (L > 1 && nb == L) { // full batch: branch-free, two levels per step
+                if (L > 1 && nb == L) { // full batch: branch-free, NLV levels per step
 #pragma unroll kBicUnroll
-                    for (int zi = 0; zi < L; zi += kNL)
-                        compute_levels<NF, ROT, S, (L > 1 ? kNL : 1), EXACT>(gr, st + zi, field_stride, tile + zi * kOutRow, L * kOutRow, s_cs);
+                    for (int zi = 0; zi < L; zi += NLV)
+                        compute_levels<NF, ROT, S, (L > 1 ? NLV : 1), ARITH>(gr, st + zi, field_stride, tile + zi * kOutRow, L * kOutRow, s_cs);
                 } else {
 #pragma unroll 1
                     for (int zi = 0; zi < nb; ++zi)
-                        compute_levels<NF, ROT, S, 1, EXACT>(gr, st + zi, field_stride, tile + zi * kOutRow, L * kOutRow, s_cs);
+                        compute_levels<NF, ROT, S, 1, ARITH>(gr, st + zi, field_stride, tile + zi * kOutRow, L * kOutRow, s_cs);
                 }
             }
         }
@@ -627,7 +718,7 @@ __device__ __forceinline__ void staged_tile(const GatherGeom& g, int tx, int ty,
     }
 }
 
-template <int NF, bool ROT, class Out, bool EXACT>
+template <int NF, bool ROT, class Out, int ARITH>
 __global__ void __launch_bounds__(kT, 2) k_gather_bicubic_staged(GatherGeom g, int tiles_x, const int4* __restrict__ info,
                                                                  const int* __restrict__ taps, const uint4* __restrict__ gmeta,
                                                                  const double2* __restrict__ gfrac, const int* __restrict__ off_tab,
@@ -636,9 +727,10 @@ __global__ void __launch_bounds__(kT, 2) k_gather_bicubic_staged(GatherGeom g, i
                                                                  typename Out::type* __restrict__ out0, typename Out::type* __restrict__ out1,
                                                                  int vec_ok, long long per, Out conv, int fill_in, float bad0, float bad1)
 {
+    typedef typename ArithTypes<ARITH>::tap TapT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* s_stage = reinterpret_cast<double*>(smem_raw);                                     // [2][kStageDoubles]
-    float* s_out = reinterpret_cast<float*>(smem_raw + sizeof(double) * 2 * kStageDoubles);    // [2][8][kOutRow]
+    TapT* s_stage = reinterpret_cast<TapT*>(smem_raw);                                         // [2][stage_elems] taps (fp64, or fp32 in fp32 mode)
+    float* s_out = reinterpret_cast<float*>(smem_raw + sizeof(TapT) * 2 * stage_elems(ARITH == kFp32)); // [2][8][kOutRow]
     double2* s_cs = reinterpret_cast<double2*>(s_out + 2 * kOutRows * kOutRow);                // [kOutRow] (ROT)
     const int tile = blockIdx.x;
     const int4 inf = __ldg(info + tile);
@@ -650,15 +742,18 @@ __global__ void __launch_bounds__(kT, 2) k_gather_bicubic_staged(GatherGeom g, i
     if (inf.y < 0 || NF * inf.y > kStageElems)
         direct_tile<NF, ROT, Out>(g, tx, ty, z0, z1, off_tab, frac_tab, cs, in0, in1, out0, out1, conv, fill_in != 0, bad0, bad1);
     else if (inf.y <= kFastTaps)
-        staged_tile<NF, ROT, true, Out, EXACT>(g, tx, ty, z0, z1, inf, taps, gmeta, gfrac, cs, in0, in1, out0, out1, vec_ok != 0, s_stage, s_out, s_cs,
+        staged_tile<NF, ROT, true, Out, ARITH>(g, tx, ty, z0, z1, inf, taps, gmeta, gfrac, cs, in0, in1, out0, out1, vec_ok != 0, s_stage, s_out, s_cs,
                                         conv, fill_in != 0, bad0, bad1);
     else
-        staged_tile<NF, ROT, false, Out, EXACT>(g, tx, ty, z0, z1, inf, taps, gmeta, gfrac, cs, in0, in1, out0, out1, vec_ok != 0, s_stage, s_out,
+        staged_tile<NF, ROT, false, Out, ARITH>(g, tx, ty, z0, z1, inf, taps, gmeta, gfrac, cs, in0, in1, out0, out1, vec_ok != 0, s_stage, s_out,
                                          s_cs, conv, fill_in != 0, bad0, bad1);
 }
 
-constexpr size_t kGatherSmem = sizeof(double) * 2 * kStageDoubles + sizeof(float) * 2 * kOutRows * kOutRow;
-constexpr size_t kGatherSmemRot = kGatherSmem + sizeof(double2) * kOutRow;
+constexpr size_t gather_smem(int arith, bool rot)
+{
+    return (arith == kFp32 ? sizeof(float) : sizeof(double)) * 2 * stage_elems(arith == kFp32) + sizeof(float) * 2 * kOutRows * kOutRow +
+           (rot ? sizeof(double2) * kOutRow : 0);
+}
 
 } // namespace
 
@@ -737,25 +832,45 @@ int bicubic_tiles_build(const int* d_off, const double2* d_frac, int ix, int iy,
 }
 
 namespace {
-template <int NF, bool ROT, class Out, bool EXACT = true>
-int launch_bic(dim3 grid, size_t smem, const GatherGeom& g, const BicubicTiles& bt, const int* d_off, const double2* d_frac, const double2* d_cs,
+template <int NF, bool ROT, int ARITH, class Out>
+int launch_bic(dim3 grid, const GatherGeom& g, const BicubicTiles& bt, const int* d_off, const double2* d_frac, const double2* d_cs,
                const float* d_in0, const float* d_in1, void* d_out0, void* d_out1, int vec_ok, long long per, Out conv, const SliceConv& sc,
                cudaStream_t st)
 {
     typedef typename Out::type T;
-    FB_CUDA_CHECK(cudaFuncSetAttribute(k_gather_bicubic_staged<NF, ROT, Out, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_gather_bicubic_staged<NF, ROT, Out, EXACT><<<grid, kT, smem, st>>>(g, bt.tiles_x, bt.d_info, bt.d_taps, bt.d_gmeta, bt.d_gfrac, d_off, d_frac,
+    constexpr size_t smem = gather_smem(ARITH, ROT);
+    FB_CUDA_CHECK(cudaFuncSetAttribute(k_gather_bicubic_staged<NF, ROT, Out, ARITH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_gather_bicubic_staged<NF, ROT, Out, ARITH><<<grid, kT, smem, st>>>(g, bt.tiles_x, bt.d_info, bt.d_taps, bt.d_gmeta, bt.d_gfrac, d_off, d_frac,
                                                                          d_cs, d_in0, d_in1, static_cast<T*>(d_out0), static_cast<T*>(d_out1),
                                                                          vec_ok, per, conv, sc.fill_in ? 1 : 0, sc.bad_in[0], sc.bad_in[1]);
     return FB_OK;
 }
 
-// FIMEX_B200_BICUBIC_CONTRACT=1: fp64 FMA chains with one final rounding instead of the reference's operation order (plain float
-// output only; see compute_levels).  Read at every launch, default off: the shipped behaviour is bit-identical to the reference.
-bool bicubic_contract()
+// plain float output in one of the three arithmetic modes
+template <int NF, bool ROT>
+int launch_bic_plain(int arith, dim3 grid, const GatherGeom& g, const BicubicTiles& bt, const int* d_off, const double2* d_frac,
+                     const double2* d_cs, const float* d_in0, const float* d_in1, void* d_out0, void* d_out1, int vec_ok, long long per,
+                     const SliceConv& sc, cudaStream_t st)
 {
-    const char* env = std::getenv("FIMEX_B200_BICUBIC_CONTRACT");
-    return env && env[0] == '1';
+    switch (arith) {
+    case kFp32:
+        return launch_bic<NF, ROT, kFp32>(grid, g, bt, d_off, d_frac, d_cs, d_in0, d_in1, d_out0, d_out1, vec_ok, per, StorePlain(), sc, st);
+    case kContract:
+        return launch_bic<NF, ROT, kContract>(grid, g, bt, d_off, d_frac, d_cs, d_in0, d_in1, d_out0, d_out1, vec_ok, per, StorePlain(), sc, st);
+    default:
+        return launch_bic<NF, ROT, kExact>(grid, g, bt, d_off, d_frac, d_cs, d_in0, d_in1, d_out0, d_out1, vec_ok, per, StorePlain(), sc, st);
+    }
+}
+
+// FIMEX_B200_BICUBIC_FP32=1: fp32 weights and FMAs; FIMEX_B200_BICUBIC_CONTRACT=1: fp64 FMA chains with one final rounding
+// (see the ARITH tags above).  Read at every launch, default off: the shipped behaviour is bit-identical to the reference.
+int bicubic_arith()
+{
+    const char* env = std::getenv("FIMEX_B200_BICUBIC_FP32");
+    if (env && env[0] == '1')
+        return kFp32;
+    env = std::getenv("FIMEX_B200_BICUBIC_CONTRACT");
+    return (env && env[0] == '1') ? kContract : kExact;
 }
 } // namespace
 
@@ -788,30 +903,21 @@ int launch_gather_bicubic_staged(const GatherGeom& g, const BicubicTiles& bt, co
     const uintptr_t align = reinterpret_cast<uintptr_t>(d_out0) | (two ? reinterpret_cast<uintptr_t>(d_out1) : 0);
     const int vec_ok = ((g.ox % 4) == 0 && (align & (4 * elem - 1)) == 0) ? 1 : 0;
     int rc = FB_ERROR;
-    const bool contract = bicubic_contract();
+    const int arith = bicubic_arith();
     if (two) {
         FB_REQUIRE(!sc.convert_out, "bicubic vector gather writes plain floats");
-        if (d_cs && contract)
-            rc = launch_bic<2, true, StorePlain, false>(grid, kGatherSmemRot, g, bt, d_off, d_frac, d_cs, d_in0, d_in1, d_out0, d_out1, vec_ok, per,
-                                                        StorePlain(), sc, st);
-        else if (d_cs)
-            rc = launch_bic<2, true>(grid, kGatherSmemRot, g, bt, d_off, d_frac, d_cs, d_in0, d_in1, d_out0, d_out1, vec_ok, per, StorePlain(), sc, st);
-        else if (contract)
-            rc = launch_bic<2, false, StorePlain, false>(grid, kGatherSmem, g, bt, d_off, d_frac, d_cs, d_in0, d_in1, d_out0, d_out1, vec_ok, per,
-                                                         StorePlain(), sc, st);
-        else
-            rc = launch_bic<2, false>(grid, kGatherSmem, g, bt, d_off, d_frac, d_cs, d_in0, d_in1, d_out0, d_out1, vec_ok, per, StorePlain(), sc, st);
-    } else if (!sc.convert_out && contract) {
-        rc = launch_bic<1, false, StorePlain, false>(grid, kGatherSmem, g, bt, d_off, d_frac, d_cs, d_in0, d_in1, d_out0, d_out1, vec_ok, per,
-                                                     StorePlain(), sc, st);
+        rc = d_cs ? launch_bic_plain<2, true>(arith, grid, g, bt, d_off, d_frac, d_cs, d_in0, d_in1, d_out0, d_out1, vec_ok, per, sc, st)
+                  : launch_bic_plain<2, false>(arith, grid, g, bt, d_off, d_frac, d_cs, d_in0, d_in1, d_out0, d_out1, vec_ok, per, sc, st);
     } else if (!sc.convert_out) {
-        rc = launch_bic<1, false>(grid, kGatherSmem, g, bt, d_off, d_frac, d_cs, d_in0, d_in1, d_out0, d_out1, vec_ok, per, StorePlain(), sc, st);
+        rc = launch_bic_plain<1, false>(arith, grid, g, bt, d_off, d_frac, d_cs, d_in0, d_in1, d_out0, d_out1, vec_ok, per, sc, st);
     } else {
         switch (sc.out_type) {
 #define FB_CASE(TAG, T)                                                                                                                    \
     case TAG:                                                                                                                              \
-        rc = launch_bic<1, false>(grid, kGatherSmem, g, bt, d_off, d_frac, d_cs, d_in0, d_in1, d_out0, d_out1, vec_ok, per,               \
-                                  StoreAs<T>{cast_fill<T>(sc.fill_out)}, sc, st);                                                          \
+        rc = arith == kFp32 ? launch_bic<1, false, kFp32>(grid, g, bt, d_off, d_frac, d_cs, d_in0, d_in1, d_out0, d_out1, vec_ok, per,     \
+                                                          StoreAs<T>{cast_fill<T>(sc.fill_out)}, sc, st)                                   \
+                            : launch_bic<1, false, kExact>(grid, g, bt, d_off, d_frac, d_cs, d_in0, d_in1, d_out0, d_out1, vec_ok, per,    \
+                                                           StoreAs<T>{cast_fill<T>(sc.fill_out)}, sc, st);                                 \
         break;
             FB_CASE(FB_T_FLOAT, float)
             FB_CASE(FB_T_DOUBLE, double)

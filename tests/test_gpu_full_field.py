@@ -167,3 +167,49 @@ def test_full_field_bicubic_vector_polar_stereographic(oracle, reference):
     differing, compared = _compare_levels(reference, Method.BICUBIC, gx, gy, inX, inY, 3000, 3000, [u, v], [uo, vo], nan_payload=False,
                                           chunk=8, post=rotate)
     assert compared == 2 * NZ * 9_000_000 and differing == 0, f"{differing} of {compared} values differ from the reference"
+
+
+def test_full_field_bicubic_fp32_mode_error(reference, monkeypatch):
+    """config 4 in the opt-in fp32 arithmetic (FIMEX_B200_BICUBIC_FP32=1): the whole 137 x 3000 x 3000 field of each component
+    against the reference: identical NaN masks, and max |error| <= 1e-5 x D, D = the largest |tap| of the point's own 4 x 4
+    stencil (for the rotated pair: of both components) -- the denominator of north_star's "<= 1e-5 relative"."""
+    import torch
+    import torch.nn.functional as F
+    ax = -3748750.0 + 2500.0 * np.arange(3000)
+    ci = fb.CachedInterpolation.fromProjection(Method.BICUBIC, STERE, ax, ax, False, False, SRC_LL, LON, LAT, True)
+    assert ci.createReducedDomain()
+    cvr = fb.CachedVectorReprojection.fromProjection(fb.MIFI_VECTOR_KEEP_SIZE, SRC_LL, STERE, ax, ax, fb.PROJ_AXIS, fb.PROJ_AXIS)
+    inX, inY = ci.getInX(), ci.getInY()
+    gx, gy = ci.points()
+    matrix = cvr.getMatrix()
+    g = torch.Generator(device="cuda").manual_seed(44)
+    u = (torch.randn((NZ, inY, inX), generator=g, device="cuda") * 10).contiguous()
+    v = (torch.randn((NZ, inY, inX), generator=g, device="cuda") * 10 + 3).contiguous()
+    monkeypatch.setenv("FIMEX_B200_BICUBIC_FP32", "1")
+    uo, vo = ci.interpolateVector(u, v, cvr)
+    monkeypatch.delenv("FIMEX_B200_BICUBIC_FP32")
+    # D per target point and level: max over the stencil of max(|u|, |v|)
+    x0 = torch.from_numpy(np.floor(gx).astype(np.int64) - 1).cuda()
+    y0 = torch.from_numpy(np.floor(gy).astype(np.int64) - 1).cuda()
+    valid = (x0 >= 0) & (x0 + 3 < inX) & (y0 >= 0) & (y0 + 3 < inY)
+    flat = (y0.clamp(0, inY - 4) * (inX - 3) + x0.clamp(0, inX - 4))
+    worst, chunk = 0.0, 8
+    for z0 in range(0, NZ, chunk):
+        z1 = min(NZ, z0 + chunk)
+        nz = z1 - z0
+        hu, hv = u[z0:z1].cpu().numpy(), v[z0:z1].cpu().numpy()
+        wu = reference.cached_interpolate(2, gx, gy, inX, inY, 3000, 3000, hu, nthreads=_cores())
+        wv = reference.cached_interpolate(2, gx, gy, inX, inY, 3000, 3000, hv, nthreads=_cores())
+        wu, wv = reference.vector_reproject_by_matrix(matrix, wu, wv, 3000, 3000, nz)
+        amax = torch.maximum(u[z0:z1].abs(), v[z0:z1].abs())
+        win = F.max_pool2d(amax[None], kernel_size=4, stride=1)[0].reshape(nz, -1)  # [nz][(inY-3)*(inX-3)]
+        D = win[:, flat]  # [nz][9e6]
+        for w, out in ((wu, uo), (wv, vo)):
+            w = torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32)).cuda().view(nz, -1)
+            got = out[z0:z1].reshape(nz, -1)
+            assert torch.equal(torch.isnan(got), torch.isnan(w)), "NaN masks differ"
+            assert torch.equal(torch.isnan(w[0]), ~valid)
+            err = ((got.double() - w.double()).abs() / D.double())[:, valid]
+            worst = max(worst, float(err.max().item()))
+    assert worst <= 1e-5, worst
+    print(f"config 4, fp32 bicubic + rotation: max |error| / (largest |tap| of the stencil) = {worst:.3e} over 2 x {NZ} x 9e6 values")

@@ -1203,3 +1203,56 @@ def test_bulk_store_forms_are_bit_identical(oracle, monkeypatch, mode, levels):
         want16 = oracle.from_float(oracle.cached_interpolate(1, px, py, inX, inY, outX, outY, oracle.as_float(packed, -32767.0)), -32767.0, np.int16)
         got16 = ci.getDataSlice(packed, -32767.0)
         assert got16.dtype == np.int16 and np.array_equal(got16, want16), f"bulk store mode {mode}: int16"
+
+
+def _stencil_absmax(field, gx, gy):
+    """max |tap| over the 4 x 4 bicubic stencil of every target point (NaN where the stencil leaves the grid): the scale the
+    fp32 mode's error is measured against"""
+    nz, iy, ix = field.shape
+    a = np.abs(np.nan_to_num(field, nan=0.0)).max(axis=0)
+    win = np.lib.stride_tricks.sliding_window_view(a, (4, 4)).max(axis=(2, 3))  # [iy-3][ix-3], window starting at (y, x)
+    x0, y0 = np.floor(gx).astype(np.int64) - 1, np.floor(gy).astype(np.int64) - 1
+    ok = (x0 >= 0) & (x0 + 3 < ix) & (y0 >= 0) & (y0 + 3 < iy)
+    d = np.full(gx.shape, np.nan)
+    d[ok] = win[y0[ok], x0[ok]]
+    return d
+
+
+def test_bicubic_fp32_mode_is_opt_in_and_within_tolerance(oracle, monkeypatch):
+    """FIMEX_B200_BICUBIC_FP32=1: weights computed in fp64 as the reference does, rounded to fp32 once, 20 fp32 FMAs per output.
+    Default stays bit-identical; the mode keeps the NaN mask exactly and every value within 1e-5 of the largest |tap| of the
+    point's own 4 x 4 stencil (north_star: <= 1e-5 relative for bicubic) -- scalar, fill-value and int16 slices, u/v with rotation."""
+    lon, lat, ax = _config2_like(300)
+    rng = np.random.default_rng(18)
+    field = rng.normal(250, 30, (19, lat.size, lon.size)).astype(np.float32)
+    field[rng.random(field.shape) < 0.002] = np.nan
+    u = rng.normal(0, 12, (5, lat.size, lon.size)).astype(np.float32)
+    v = rng.normal(0, 12, (5, lat.size, lon.size)).astype(np.float32)
+    ci = fb.CachedInterpolation.fromProjection(Method.BICUBIC, ROTPOLE, ax, ax, True, True, SRC_LL, lon, lat, True)
+    cvr = fb.CachedVectorReprojection.fromProjection(fb.MIFI_VECTOR_KEEP_SIZE, SRC_LL, ROTPOLE, ax, ax, fb.LONGITUDE, fb.LATITUDE)
+    monkeypatch.delenv("FIMEX_B200_BICUBIC_FP32", raising=False)
+    monkeypatch.delenv("FIMEX_B200_BICUBIC_CONTRACT", raising=False)
+    gx, gy = ci.points()
+    exact = ci.interpolateValues(field)
+    assert_bit_equal(exact, oracle.cached_interpolate(2, gx, gy, lon.size, lat.size, ax.size, ax.size, field), "bicubic exact (default)")
+    eu, ev = ci.interpolateVector(u, v, cvr)
+    monkeypatch.setenv("FIMEX_B200_BICUBIC_FP32", "1")
+    fast = ci.interpolateValues(field)
+    fu, fv = ci.interpolateVector(u, v, cvr)
+    fill = np.float32(9.96921e+36)
+    fast_fill = ci.getDataSlice(np.where(np.isnan(field), fill, field), float(fill))
+    monkeypatch.delenv("FIMEX_B200_BICUBIC_FP32")
+    assert np.array_equal(np.isnan(fast), np.isnan(exact))
+    ok = ~np.isnan(exact)
+    assert ok.sum() > 0.5 * ok.size
+    scale = _stencil_absmax(field, gx, gy).reshape(1, ax.size, ax.size)
+    err = np.abs(fast.astype(np.float64) - exact.astype(np.float64)) / scale
+    assert np.nanmax(err[ok]) <= 1e-5, np.nanmax(err[ok])
+    assert (fast[ok] != exact[ok]).any()  # the mode was really taken
+    assert np.array_equal(fast_fill == fill, ~ok) and np.array_equal(fast_fill[ok], fast[ok])  # the adapters around it are unchanged
+    su = np.maximum(_stencil_absmax(u, gx, gy), _stencil_absmax(v, gx, gy)).reshape(1, ax.size, ax.size)
+    for f, e in ((fu, eu), (fv, ev)):
+        m = ~np.isnan(e)
+        assert np.array_equal(np.isnan(f), ~m)
+        assert np.nanmax((np.abs(f.astype(np.float64) - e.astype(np.float64)) / su)[m]) <= 2e-5  # two components enter each rotated value
+    assert_bit_equal(ci.interpolateValues(field), exact, "bicubic exact again")
