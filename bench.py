@@ -422,7 +422,11 @@ def main_b200(args):
             host_in = d_in[sel].cpu().numpy()
             want = o.cached_interpolate(method_id, px[idx], py[idx], inX, inY, idx.size, 1, host_in).reshape(len(lv), -1)
             got = d_out.view(nlev, -1)[sel][:, torch.from_numpy(idx).to(dev)].cpu().numpy()
-            same = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
+            if method_id == 2 and (os.environ.get("FIMEX_B200_BICUBIC_FP32", "")[:1] == "1" or os.environ.get("FIMEX_B200_BICUBIC_CONTRACT", "")[:1] == "1"):
+                # the opt-in arithmetic modes are not bit-identical: same NaN mask, values within 1e-5 of the field's magnitude
+                same = (np.isnan(got) == np.isnan(want)) & (np.isnan(want) | (np.abs(got - want) <= 1e-5 * float(np.nanmax(np.abs(host_in)))))
+            else:
+                same = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
         else:
             host_in = o.as_float(d_in[sel].cpu().numpy(), fill)
             np_type = {torch.float32: np.float32, torch.int16: np.int16}[d_in.dtype]

@@ -11,6 +11,7 @@ The product is ``fimex_b200/lib/libfimex_b200.so`` (hand-written sm_100a CUDA be
 * :mod:`fimex_b200.interpolator` -- the table-producing part of ``CDMInterpolator::changeProjection*`` and the
   per-slice driver ``getDataSlice`` for in-memory slices;
 * :mod:`fimex_b200.processor` -- ``CDMProcessor::rotateVectorToLatLon`` / ``rotateDirectionToLatLon`` on the same rotation kernels;
+* :mod:`fimex_b200.merger` -- ``CDMMerger`` (inner grid merged into an outer one with border smoothing) on the same interpolations;
 * :mod:`fimex_b200.slab`    -- one-process-per-GPU slab partition of the (time x level) stack with a single
   NCCL broadcast of the cached tables.
 """
@@ -24,13 +25,14 @@ from .capi import (DataType, cdm_type, default_fill_value, LATITUDE, LONGITUDE, 
 from .cached import CachedForwardInterpolation, CachedInterpolation, CachedVectorReprojection
 from .interpolator import Interpolator, axis_spec_requires_start_end, spatial_axis_spec, tokenize_dotted
 from .processor import Processor
+from .merger import Merger, extend_inner_axis, linear_border_smoothing
 
 #: opt-in arithmetic modes of the bicubic gather (environment, read at every launch): FIMEX_B200_BICUBIC_FP32=1 (fp32 weights and
 #: FMAs, <= 1e-5 relative, identical NaN masks), FIMEX_B200_BICUBIC_CONTRACT=1 (fp64 FMA chains); default: bit-identical
 BICUBIC_FP32_AVAILABLE = True
 
 __all__ = [
-    "CachedInterpolation", "CachedForwardInterpolation", "CachedVectorReprojection", "Interpolator", "Processor", "spatial_axis_spec", "axis_spec_requires_start_end", "tokenize_dotted", "Method", "DataType", "cdm_type", "default_fill_value", "FimexB200Error",
+    "CachedInterpolation", "CachedForwardInterpolation", "CachedVectorReprojection", "Interpolator", "Processor", "Merger", "extend_inner_axis", "linear_border_smoothing", "spatial_axis_spec", "axis_spec_requires_start_end", "tokenize_dotted", "Method", "DataType", "cdm_type", "default_fill_value", "FimexB200Error",
     "MIFI_OK", "MIFI_ERROR", "PROJ_AXIS", "LONGITUDE", "LATITUDE", "MIFI_VECTOR_KEEP_SIZE", "load", "lib_path", "version", "last_error",
     "set_device", "kernel_launches", "mifi_interpolate_f", "mifi_points2position", "mifi_project_axes", "mifi_project_values",
     "mifi_get_vector_reproject_matrix", "mifi_get_vector_reproject_matrix_field", "mifi_get_vector_reproject_matrix_points",

@@ -50,19 +50,22 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, extra_flags=None, lib_out: str = None, objdir_name: str = "obj") -> str:
+    """extra_flags / out / objdir_name: experiment builds (-DFB_... macros) next to the shipped library, e.g.
+    build(force=True, extra_flags=["-DFB_BLQ_CTAS=2"], lib_out=".../libfimex_b200_ctas2.so", objdir_name="obj_ctas2"); load one with
+    FIMEX_B200_LIB=<path> in the environment"""
+    if not force and not needs_build() and lib_out is None:
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     objs = []
-    objdir = os.path.join(LIBDIR, "obj")
+    objdir = os.path.join(LIBDIR, objdir_name)
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
     procs = []
     for s in SOURCES:
         o = os.path.join(objdir, os.path.splitext(s)[0] + ".o")
         objs.append(o)
-        cmd = [nvcc] + _host_cxx() + NVCC_FLAGS + ["-x", "cu", "-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [nvcc] + _host_cxx() + NVCC_FLAGS + list(extra_flags or []) + ["-x", "cu", "-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     failed = False
@@ -70,19 +73,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
         out, _ = p.communicate()
         log.append(f"==== {s}\n{out}")
         failed = failed or p.returncode != 0
-    with open(os.path.join(LIBDIR, "build.log"), "w") as f:
+    with open(os.path.join(LIBDIR, "build.log" if lib_out is None else os.path.basename(lib_out) + ".log"), "w") as f:
         f.write("\n".join(log))
     if failed:
         sys.stderr.write("\n".join(log))
         raise RuntimeError("nvcc failed; see fimex_b200/lib/build.log")
-    link = [nvcc] + _host_cxx() + ["-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-Xlinker", "-Bsymbolic"]
+    link = [nvcc] + _host_cxx() + ["-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib_out or LIB] + objs + ["-Xlinker", "-Bsymbolic"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
         raise RuntimeError("link failed")
     if verbose:
         print("\n".join(log))
-    return LIB
+    return lib_out or LIB
 
 
 if __name__ == "__main__":

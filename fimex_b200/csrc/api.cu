@@ -2211,8 +2211,33 @@ int mifi_vector_reproject_values_f(int method, const char* proj_input, const cha
     return rc;
 }
 
+// The per-point kernels of include/fimex/interpolation.h:231-291 exist for link-level compatibility and for tests: each call
+// builds a one-point table, uploads the WHOLE field and launches a kernel.  A host that keeps the reference's function-pointer
+// loop (src/CachedInterpolation.cc:133-141) instead of forwarding interpolateValues to fb200_interp_interpolate_values would
+// call this millions of times per slice -- say so, once, instead of being silently slow (there is no CPU fallback to switch to).
+static void warn_if_called_in_a_loop()
+{
+    static std::atomic<unsigned> calls{0};
+    static std::atomic<long long> window_start{0};
+    static std::atomic<bool> warned{false};
+    if (warned.load(std::memory_order_relaxed))
+        return;
+    const long long now = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    long long start = window_start.load(std::memory_order_relaxed);
+    if (now - start > 1000) { // a new one-second window
+        window_start.store(now, std::memory_order_relaxed);
+        calls.store(0, std::memory_order_relaxed);
+    }
+    if (calls.fetch_add(1, std::memory_order_relaxed) + 1 > 1000 && !warned.exchange(true)) {
+        fprintf(stderr, "fimex_b200: WARNING: mifi_get_values*_f called more than 1000 times within a second.  These per-point entry points "
+                        "upload the whole field on every call; forward CachedInterpolation::interpolateValues to "
+                        "fb200_interp_interpolate_values (see INTEGRATION.md) instead of looping over target points on the host.\n");
+    }
+}
+
 static int one_point(int method, const float* infield, float* outvalues, double x, double y, int ix, int iy, int iz)
 {
+    warn_if_called_in_a_loop();
     fb200_interp* h = nullptr;
     if (fb200_cached_interpolation_create(method, &x, &y, (size_t)ix, (size_t)iy, 1, 1, &h) != MIFI_OK)
         return MIFI_ERROR;

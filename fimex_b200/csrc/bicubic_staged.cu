@@ -65,7 +65,10 @@ constexpr int kBicUnroll = FB_BIC_UNROLL;
 constexpr int kNL = FB_BIC_NL;
 
 // output-tile slot of tile point p = y*32 + x: 4-float column groups are XOR-permuted by the row, so that the points of
-// one source cell (a block of neighbouring rows and columns) spread over the banks; rows stay readable as float4
+// one source cell (a block of neighbouring rows and columns) spread over the banks; rows stay readable as float4.
+// (What is left is the conflict rate of 32 effectively random banks: 2.9 wavefronts per store instruction, measured 2.6.  A
+// simulation of config 2's tiles gives 2.8-3.0 for every permutation tried -- xor or add of k * row over all five column bits,
+// rotating the point order inside a group by the group index -- so the layout is not the lever)
 __host__ __device__ __forceinline__ int out_slot(int p)
 {
     return (p & ~31) | ((p & 31) ^ (((p >> 5) & 7) << 2));
@@ -320,6 +323,18 @@ template <>
 struct ArithTypes<kFp32> {
     typedef float tap;
 };
+// weight type held in registers per group: fp32 mode keeps every weight twice, (w, w), the second operand of Blackwell's
+// packed fma.rn.f32x2 (FFMA2): two LEVELS of a tap per instruction, 10 instead of 20 FP instructions per output
+template <int ARITH>
+struct WeightType {
+    typedef double type;
+};
+template <>
+struct WeightType<kFp32> {
+    typedef float2 type;
+};
+__device__ __forceinline__ void set_weight(double& w, double v) { w = v; }
+__device__ __forceinline__ void set_weight(float2& w, double v) { w = make_float2((float)v, (float)v); }
 
 template <class W>
 struct GroupT {
@@ -348,8 +363,8 @@ __device__ __forceinline__ void load_group(GroupT<W>& gr, const uint4* __restric
         cubic_weights(f.y, wy);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            gr.wx[p][i] = (W)wx[i];
-            gr.wy[p][i] = (W)wy[i];
+            set_weight(gr.wx[p][i], wx[i]);
+            set_weight(gr.wy[p][i], wy[i]);
         }
     }
 }
@@ -430,36 +445,61 @@ __device__ __forceinline__ void compute_levels(const GroupT<double>& gr, const d
 }
 
 
-// kFp32: fp32 taps, fp32 weights, 20 FMAs per output.  NL = 4 reads four levels of a tap with one 128-bit shared load (the
-// staging buffer is tap-major with a 16-byte aligned stride); the rotation is done in fp32 as well.
+// kFp32: fp32 taps, fp32 weights, 20 multiply-adds per output.  NL = 4 reads four levels of a tap with one 128-bit shared load
+// (the staging buffer is tap-major with a 16-byte aligned stride) and does the arithmetic on level PAIRS with packed
+// fma.rn.f32x2; NL = 1 (partial batches, many-tap tiles) is scalar.  The rotation is done in fp32 as well.
 template <int NF, bool ROT, int S, int NL, int ARITH>
-__device__ __forceinline__ void compute_levels(const GroupT<float>& gr, const float* __restrict__ st, int field_stride, float* __restrict__ s_out,
+__device__ __forceinline__ void compute_levels(const GroupT<float2>& gr, const float* __restrict__ st, int field_stride, float* __restrict__ s_out,
                                                int out_field_stride, const double2* __restrict__ s_cs)
 {
     static_assert(NL == 1 || NL == 4, "one level or one 128-bit load of four");
     float a[NL][NF][4];
+    if (NL == 4) {
+        float2 acc[2][NF][4]; // [level pair][field][point]
 #pragma unroll
-    for (int f = 0; f < NF; ++f) {
-        const float* sf = st + f * field_stride;
+        for (int f = 0; f < NF; ++f) {
+            const float* sf = st + f * field_stride;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const float* rp = sf + gr.row[r];
-            float v[4][NL];
+            for (int r = 0; r < 4; ++r) {
+                const float* rp = sf + gr.row[r];
+                float2 v[4][2];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (NL == 4) {
+                for (int c = 0; c < 4; ++c) {
                     const float4 q = *reinterpret_cast<const float4*>(rp + c * S);
-                    v[c][0] = q.x, v[c][1 % NL] = q.y, v[c][2 % NL] = q.z, v[c][3 % NL] = q.w;
-                } else {
-                    v[c][0] = rp[c * S];
+                    v[c][0] = make_float2(q.x, q.y);
+                    v[c][1] = make_float2(q.z, q.w);
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        const float2 row = __ffma2_rn(gr.wx[p][3], v[3][h],
+                                                      __ffma2_rn(gr.wx[p][2], v[2][h], __ffma2_rn(gr.wx[p][1], v[1][h], __fmul2_rn(gr.wx[p][0], v[0][h]))));
+                        acc[h][f][p] = (r == 0) ? __fmul2_rn(row, gr.wy[p][0]) : __ffma2_rn(row, gr.wy[p][r], acc[h][f][p]);
+                    }
                 }
             }
+        }
 #pragma unroll
-            for (int l = 0; l < NL; ++l) {
+        for (int f = 0; f < NF; ++f)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                a[0][f][p] = acc[0][f][p].x;
+                a[1 % NL][f][p] = acc[0][f][p].y;
+                a[2 % NL][f][p] = acc[1][f][p].x;
+                a[3 % NL][f][p] = acc[1][f][p].y;
+            }
+    } else {
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            const float* sf = st + f * field_stride;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float* rp = sf + gr.row[r];
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
-                    const float row = fmaf(gr.wx[p][3], v[3][l], fmaf(gr.wx[p][2], v[2][l], fmaf(gr.wx[p][1], v[1][l], gr.wx[p][0] * v[0][l])));
-                    a[l][f][p] = (r == 0) ? row * gr.wy[p][0] : fmaf(row, gr.wy[p][r], a[l][f][p]);
+                    const float row = fmaf(gr.wx[p][3].x, rp[3 * S], fmaf(gr.wx[p][2].x, rp[2 * S], fmaf(gr.wx[p][1].x, rp[S], gr.wx[p][0].x * rp[0])));
+                    a[0][f][p] = (r == 0) ? row * gr.wy[p][0].x : fmaf(row, gr.wy[p][r].x, a[0][f][p]);
                 }
             }
         }
@@ -603,7 +643,7 @@ __device__ __forceinline__ void staged_tile(const GatherGeom& g, int tx, int ty,
             s_cs[slot] = c;
         }
     }
-    GroupT<TapT> gr;
+    GroupT<typename WeightType<ARITH>::type> gr;
     if (rounds == 1 && t < ngroups)
         load_group<S>(gr, gmeta, gfrac, (size_t)inf.z + t);
 

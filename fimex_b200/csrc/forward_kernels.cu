@@ -127,7 +127,65 @@ __device__ __forceinline__ float aggregate_cell(const float* __restrict__ lv, co
     return res;
 }
 
-template <int AGG, bool UNDEF>
+// ZL levels of one target cell at a time (sum / mean / max / min): the permutation entry of every segment element is read ONCE
+// and its ZL values -- independent gathers, one per level -- are in flight together; every level keeps its own sequential
+// accumulator, so each level's result is exactly what aggregate_cell gives for it.
+template <int AGG, bool UNDEF, int ZL>
+__device__ __forceinline__ void aggregate_cell_levels(const float* __restrict__ lv, long long n_in, const int* __restrict__ perm, int beg, int end,
+                                                      const float (&v0)[ZL], float (&res)[ZL])
+{
+    static_assert(AGG != AG_MEDIAN, "median goes level by level");
+    float acc[ZL];
+    long long cnt[ZL];
+    bool have[ZL];
+#pragma unroll
+    for (int l = 0; l < ZL; ++l) {
+        res[l] = undef_f();
+        acc[l] = 0.f;
+        cnt[l] = 0;
+        have[l] = false;
+    }
+    if (beg >= end)
+        return;
+    auto feed = [&](int l, float v) {
+        if (!(UNDEF || !isnan(v)))
+            return;
+        if (AGG == AG_SUM || AGG == AG_MEAN) {
+            acc[l] = __fadd_rn(acc[l], v); // std::accumulate(begin, end, 0.f): sequential, input order
+            ++cnt[l];
+        } else if (!have[l]) {
+            acc[l] = v;
+            have[l] = true;
+        } else if (AGG == AG_MAX ? (acc[l] < v) : (v < acc[l])) { // std::max_element / min_element
+            acc[l] = v;
+        }
+    };
+#pragma unroll
+    for (int l = 0; l < ZL; ++l)
+        feed(l, v0[l]);
+    for (int k = beg + 1; k < end; ++k) {
+        const float* p = lv + __ldg(perm + k);
+        float v[ZL];
+#pragma unroll
+        for (int l = 0; l < ZL; ++l)
+            v[l] = __ldg(p + l * n_in);
+#pragma unroll
+        for (int l = 0; l < ZL; ++l)
+            feed(l, v[l]);
+    }
+#pragma unroll
+    for (int l = 0; l < ZL; ++l) {
+        if (AGG == AG_SUM || AGG == AG_MEAN) {
+            if (cnt[l] > 0)
+                res[l] = (AGG == AG_MEAN) ? __fdiv_rn(acc[l], __ll2float_rn(cnt[l])) : acc[l];
+        } else if (have[l]) {
+            res[l] = acc[l];
+        }
+    }
+}
+
+// ZL = levels per thread and pass (1 for single-level slices, 4 otherwise; the median always works level by level)
+template <int AGG, bool UNDEF, int ZL>
 __global__ void __launch_bounds__(kThreads) k_forward(const int* __restrict__ perm, const int* __restrict__ offsets,
                                                     const float* __restrict__ in, float* __restrict__ out, long long n_in,
                                                     long long n_cells, long long nz, int vec_ok)
@@ -152,15 +210,7 @@ __global__ void __launch_bounds__(kThreads) k_forward(const int* __restrict__ pe
     for (int j = 0; j < kCells; ++j)
         first[j] = off[j] < off[j + 1] ? __ldg(perm + off[j]) : -1; // the same for every level
     const long long valid = n_cells - c0;
-    for (long long z = blockIdx.y; z < nz; z += gridDim.y) {
-        const float* lv = in + z * n_in;
-        float v0[kCells], res[kCells];
-#pragma unroll
-        for (int j = 0; j < kCells; ++j)
-            v0[j] = first[j] >= 0 ? __ldg(lv + first[j]) : 0.f; // kCells independent gathers in flight
-#pragma unroll
-        for (int j = 0; j < kCells; ++j)
-            res[j] = aggregate_cell<AGG, UNDEF>(lv, perm, off[j], off[j + 1], v0[j]);
+    auto store = [&](long long z, const float (&res)[kCells]) {
         float* o = out + z * n_cells + c0;
         if (vec_ok && valid >= kCells) {
 #pragma unroll
@@ -172,17 +222,62 @@ __global__ void __launch_bounds__(kThreads) k_forward(const int* __restrict__ pe
                 if (j < valid)
                     __stcs(o + j, res[j]);
         }
+    };
+    for (long long z = (long long)blockIdx.y * ZL; z < nz; z += (long long)gridDim.y * ZL) {
+        const float* lv = in + z * n_in;
+        if (ZL > 1 && AGG != AG_MEDIAN && z + ZL <= nz) {
+            float v0[kCells][ZL], res[kCells][ZL];
+#pragma unroll
+            for (int j = 0; j < kCells; ++j)
+#pragma unroll
+                for (int l = 0; l < ZL; ++l)
+                    v0[j][l] = first[j] >= 0 ? __ldg(lv + l * n_in + first[j]) : 0.f; // kCells * ZL independent gathers in flight
+            if (AGG != AG_MEDIAN) {
+#pragma unroll
+                for (int j = 0; j < kCells; ++j)
+                    aggregate_cell_levels<(AGG == AG_MEDIAN ? AG_SUM : AGG), UNDEF, ZL>(lv, n_in, perm, off[j], off[j + 1], v0[j], res[j]);
+            }
+#pragma unroll
+            for (int l = 0; l < ZL; ++l) {
+                float r[kCells];
+#pragma unroll
+                for (int j = 0; j < kCells; ++j)
+                    r[j] = res[j][l];
+                store(z + l, r);
+            }
+            continue;
+        }
+        for (long long zz = z; zz < nz && zz < z + ZL; ++zz, lv += n_in) { // single levels: ZL == 1, the tail of the stack, the median
+            float v0[kCells], res[kCells];
+#pragma unroll
+            for (int j = 0; j < kCells; ++j)
+                v0[j] = first[j] >= 0 ? __ldg(lv + first[j]) : 0.f; // kCells independent gathers in flight
+#pragma unroll
+            for (int j = 0; j < kCells; ++j)
+                res[j] = aggregate_cell<AGG, UNDEF>(lv, perm, off[j], off[j + 1], v0[j]);
+            store(zz, res);
+        }
     }
 }
 
 template <int AGG>
-int launch_agg(bool undef, dim3 grid, cudaStream_t st, const ForwardPlan& p, const float* in, float* out, long long nz)
+int launch_agg(bool undef, int gx, cudaStream_t st, const ForwardPlan& p, const float* in, float* out, long long nz)
 {
     const int vec_ok = ((p.n_cells % 4) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) ? 1 : 0;
-    if (undef)
-        k_forward<AGG, true><<<grid, kThreads, 0, st>>>(p.d_perm, p.d_offsets, in, out, p.n_in, p.n_cells, nz, vec_ok);
-    else
-        k_forward<AGG, false><<<grid, kThreads, 0, st>>>(p.d_perm, p.d_offsets, in, out, p.n_in, p.n_cells, nz, vec_ok);
+    if (nz >= 4 && AGG != AG_MEDIAN) { // several levels: four per thread and pass
+        const long long passes = (nz + 3) / 4;
+        dim3 grid(gx, (unsigned)(passes < 64 ? passes : 64));
+        if (undef)
+            k_forward<AGG, true, 4><<<grid, kThreads, 0, st>>>(p.d_perm, p.d_offsets, in, out, p.n_in, p.n_cells, nz, vec_ok);
+        else
+            k_forward<AGG, false, 4><<<grid, kThreads, 0, st>>>(p.d_perm, p.d_offsets, in, out, p.n_in, p.n_cells, nz, vec_ok);
+    } else {
+        dim3 grid(gx, (unsigned)(nz < 64 ? nz : 64));
+        if (undef)
+            k_forward<AGG, true, 1><<<grid, kThreads, 0, st>>>(p.d_perm, p.d_offsets, in, out, p.n_in, p.n_cells, nz, vec_ok);
+        else
+            k_forward<AGG, false, 1><<<grid, kThreads, 0, st>>>(p.d_perm, p.d_offsets, in, out, p.n_in, p.n_cells, nz, vec_ok);
+    }
     count_launch();
     FB_CUDA_CHECK(cudaGetLastError());
     return FB_OK;
@@ -250,7 +345,7 @@ int launch_forward(int method, const ForwardPlan& plan, const float* d_in, float
         return FB_OK;
     const bool undef = method >= FB_FWD_UNDEF_SUM;
     const int gx = ceil_div(ceil_div(plan.n_cells, kCells), kThreads);
-    dim3 grid(gx, (unsigned)(nz < 64 ? nz : 64));
+    const int grid = gx;
     switch (method) {
     case FB_FWD_SUM:
     case FB_FWD_UNDEF_SUM:

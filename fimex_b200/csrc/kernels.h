@@ -78,6 +78,7 @@ struct TileTable {
     float4* d_yf = nullptr;   // [tile][256]
     int* d_slow = nullptr;    // ids of the tiles with more taps than the tap-major staging buffer holds (pole, seam)
     int n_slow = 0;
+    bool quad = false;        // tile geometry: 128 x 8, a thread owns 4 x-neighbours (nearest neighbour; bilinear by default)
     bool nn = false;          // nearest-neighbour table (one tap per point, no xf/yf)
     bool ready() const { return d_cells != nullptr; }
 };

@@ -45,7 +45,7 @@ namespace {
 #endif
 constexpr int kThreads = FB_CTA_THREADS;
 constexpr int kTilePts = 4 * kThreads;
-// Tile shapes (1024 target points, 4 per thread).  Measured on B200 (scratch/ubench/store_bw.cu, pure stores, 64-level
+// Tile shapes (1024 target points, 4 per thread).  Measured on B200 (profiles/ubench/store_bw.cu, pure stores, 64-level
 // chunks): tiles whose rows are 128 B wide reach 5.66 TB/s, 256 B rows 6.35 TB/s, 512 B rows written with 128-bit stores
 // 7.1 TB/s -- the wider the contiguous run a CTA writes per row, the fewer DRAM pages are open at once.  The width a
 // bilinear warp can cover is limited by shared-memory banks instead: the 32 lanes of a load should see fewer than 32
@@ -62,16 +62,24 @@ constexpr int kBuffers = FB_STAGE_BUFFERS;
 #ifndef FB_NN_CTAS
 #define FB_NN_CTAS 3 // resident CTAs per SM the nearest-neighbour kernel is compiled for (experiments: -DFB_NN_CTAS=4)
 #endif
+#ifndef FB_BLQ_CTAS
+#define FB_BLQ_CTAS 3 // resident CTAs per SM the quad-layout bilinear kernel is compiled for (experiments: -DFB_BLQ_CTAS=2)
+#endif
+#ifndef FB_BLQ_LV
+#define FB_BLQ_LV 4 // levels per shared load of the quad-layout bilinear kernel: 4 (LDS.128) or 2 (LDS.64, 16 fewer live registers)
+#endif
 #ifndef FB_BL_TILE_X
 #define FB_BL_TILE_X 64 // bilinear tile width: 32 or 64 (experiments: -DFB_BL_TILE_X=32)
 #endif
-template <bool NN>
+// Tile<QUAD>: QUAD = a thread owns 4 x-neighbours of one row (128 x 8 tiles: nearest neighbour; bilinear with
+// FIMEX_B200_BILINEAR_QUAD=1); !QUAD = lane = x, a thread owns one column of 4 rows (64 x 16 tiles: bilinear by default)
+template <bool QUAD>
 struct Tile {
-    static constexpr int X = NN ? 128 : FB_BL_TILE_X, Y = kTilePts / X;
-    static constexpr int RowStep = NN ? 0 : kThreads / X; // bilinear: rows between point k and point k+1 of a thread
+    static constexpr int X = QUAD ? 128 : FB_BL_TILE_X, Y = kTilePts / X;
+    static constexpr int RowStep = QUAD ? 0 : kThreads / X; // column layout: rows between point k and point k+1 of a thread
     // position of point k of thread t inside the tile
-    static __device__ __forceinline__ int px(int t, int k) { return NN ? 4 * (t & 31) + k : (t % X); }
-    static __device__ __forceinline__ int py(int t, int k) { return NN ? (t >> 5) : (t / X) + RowStep * k; }
+    static __device__ __forceinline__ int px(int t, int k) { return QUAD ? 4 * (t & 31) + k : (t % X); }
+    static __device__ __forceinline__ int py(int t, int k) { return QUAD ? (t >> 5) : (t / X) + RowStep * k; }
 };
 constexpr int kMaxTaps = 4 * kTilePts;                              // worst case: every point has its own 4 taps
 constexpr int kStageFloats = 16 * kThreads;                          // one staging buffer (16 KB), two of them
@@ -83,7 +91,7 @@ constexpr int kLvlStride = 12;
 constexpr int kFastTaps = kStageFloats / kLvlStride;                // tiles with at most 341 taps use it (all but pole/seam tiles)
 
 // ------------------------------------------------------------------------------------------------ table compiler
-template <bool NN>
+template <bool NN, bool QUAD>
 __global__ void __launch_bounds__(kThreads) k_compile_tiles(const double* __restrict__ px, const double* __restrict__ py, int ox, int oy,
                                                           int ix, int iy, int tiles_x, int* __restrict__ taps, int* __restrict__ ntaps,
                                                           uint4* __restrict__ meta, float4* __restrict__ xf4, float4* __restrict__ yf4)
@@ -99,7 +107,7 @@ __global__ void __launch_bounds__(kThreads) k_compile_tiles(const double* __rest
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         int4 e = make_int4(0, 0, 0, FB_BL_NAN);
-        const int x = tx * Tile<NN>::X + Tile<NN>::px(t, k), y = ty * Tile<NN>::Y + Tile<NN>::py(t, k);
+        const int x = tx * Tile<QUAD>::X + Tile<QUAD>::px(t, k), y = ty * Tile<QUAD>::Y + Tile<QUAD>::py(t, k);
         if (y < oy && x < ox) {
             const long long i = (long long)y * ox + x;
             e = NN ? classify_nn(px[i], py[i], ix, iy) : classify_bilinear(px[i], py[i], ix, iy);
@@ -223,8 +231,11 @@ __device__ __forceinline__ void cp_async_wait_pending()
 // NaN -> fill, round + cast to the variable's type).  fill_in: mifi_bad2nanf fused into the staging (values equal to
 // bad0 / bad1 become NaN before any point reads them).  NF = 2: both components of a vector through one table pass
 // (CDMInterpolator.cc:255-276), ROT: rotated in the epilogue (mifi_vector_reproject_values_by_matrix_f, interpolation.c:790-812).
-template <bool NN, int NF, bool ROT, class Out>
-__global__ void __launch_bounds__(kThreads, (NF == 1 ? (NN ? FB_NN_CTAS : 3) : 2) * (256 / kThreads))
+// QUAD: geometry (see Tile).  NN implies QUAD.  For bilinear, QUAD also switches the common branch to the tap-reuse form:
+// the 4 points of a thread are x-neighbours, so point k mostly reads the cell of point k-1 again (nothing is loaded) or the
+// cell one column to the right (its left taps are the right taps already in registers: two loads instead of four).
+template <bool NN, int NF, bool ROT, class Out, bool QUAD>
+__global__ void __launch_bounds__(kThreads, (NF == 1 ? (NN ? FB_NN_CTAS : (QUAD ? FB_BLQ_CTAS : 3)) : 2) * (256 / kThreads))
     k_gather_bilinear_staged(GatherGeom g, int tiles_x, const int* __restrict__ taps, const int* __restrict__ ntaps_tab,
                              const uint4* __restrict__ meta, const float4* __restrict__ xf4, const float4* __restrict__ yf4,
                              const float* __restrict__ in0, const float* __restrict__ in1, typename Out::type* __restrict__ out0,
@@ -256,15 +267,26 @@ __global__ void __launch_bounds__(kThreads, (NF == 1 ? (NN ? FB_NN_CTAS : 3) : 2
         wy0[k] = __fsub_rn(1.f, yf[k]);
         all_full = all_full && (mode[k] == (NN ? FB_BL_NEAR : FB_BL_FULL));
     }
+    // bilinear in the quad layout: how point k's cell relates to point k-1's (list indices: the right-hand neighbour of a tap is
+    // the next list entry).  same: nothing to load; shift: one column to the right, the old right taps become the left taps
+    bool same[4] = {false, false, false, false}, shift[4] = {false, false, false, false};
+    if (QUAD && !NN) {
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+            same[k] = ia[k] == ia[k - 1] && ib[k] == ib[k - 1];
+            shift[k] = ia[k] == ia[k - 1] + 1 && ib[k] == ib[k - 1] + 1;
+        }
+    }
     const int tx = tile % tiles_x, ty = tile / tiles_x;
     // which of the thread's 4 points exist (the grid need not be a multiple of the tile), and their element offsets in a level
-    const int x0 = tx * Tile<NN>::X + Tile<NN>::px(t, 0), y0 = ty * Tile<NN>::Y + Tile<NN>::py(t, 0);
-    const unsigned rstep = (unsigned)Tile<NN>::RowStep * (unsigned)g.ox; // bilinear: from point k to point k+1 of a thread
-    auto poff = [&](int k) -> unsigned { return NN ? (unsigned)k : (unsigned)k * rstep; };
-    // points k < nvalid exist (k runs along x for nearest neighbour, down the rows for bilinear)
+    static_assert(QUAD || !NN, "nearest neighbour uses the quad geometry");
+    const int x0 = tx * Tile<QUAD>::X + Tile<QUAD>::px(t, 0), y0 = ty * Tile<QUAD>::Y + Tile<QUAD>::py(t, 0);
+    const unsigned rstep = (unsigned)Tile<QUAD>::RowStep * (unsigned)g.ox; // column layout: from point k to point k+1 of a thread
+    auto poff = [&](int k) -> unsigned { return QUAD ? (unsigned)k : (unsigned)k * rstep; };
+    // points k < nvalid exist (k runs along x in the quad layout, down the rows in the column layout)
     int nvalid = 0;
     if (y0 < g.oy && x0 < g.ox)
-        nvalid = NN ? g.ox - x0 : (g.oy - y0 + Tile<NN>::RowStep - 1) / (NN ? 1 : Tile<NN>::RowStep);
+        nvalid = QUAD ? g.ox - x0 : (g.oy - y0 + Tile<QUAD>::RowStep - 1) / (QUAD ? 1 : Tile<QUAD>::RowStep);
     const unsigned vmask = nvalid >= 4 ? 0xfu : (1u << nvalid) - 1u;
     const long long per = (g.nz + gridDim.y - 1) / gridDim.y;
     const long long z0 = (long long)blockIdx.y * per;
@@ -377,10 +399,10 @@ __global__ void __launch_bounds__(kThreads, (NF == 1 ? (NN ? FB_NN_CTAS : 3) : 2
             // Several levels at a time: the staged levels of a tap are contiguous, so one LDS.128 brings four of them -- a quarter
             // of the load instructions (9 % fewer instructions overall).  The L1TEX cycles stay what they were: 4.45 shared-load
             // wavefronts per 32 outputs and level either way (ncu), i.e. the merging of equal addresses that a 128-bit load
-            // shows in scratch/ubench/lds_width.cu does not happen for the irregular runs of equal taps a rotated grid produces.
+            // shows in profiles/ubench/lds_width.cu does not happen for the irregular runs of equal taps a rotated grid produces.
             // LV levels per step: 4; 2 for a rotated vector pair, whose 2 x 4 x LV results and the fp64 rotation
             // have to fit the 128 registers of 2 CTAs per SM
-            constexpr int LV = (NF == 2 && ROT) ? 2 : 4;
+            constexpr int LV = (NF == 2 && ROT) ? 2 : ((QUAD && !NN && NF == 1) ? FB_BLQ_LV : 4);
             auto ldv = [](const float* p, float (&v)[LV]) {
                 if constexpr (LV == 4) {
                     const float4 t4 = *reinterpret_cast<const float4*>(p);
@@ -394,6 +416,31 @@ __global__ void __launch_bounds__(kThreads, (NF == 1 ? (NN ? FB_NN_CTAS : 3) : 2
                 float r[NF][4][LV]; // [field][point][level]
 #pragma unroll
                 for (int f = 0; f < NF; ++f) {
+                    if (QUAD && !NN) { // x-neighbours: keep the taps of the previous point and load only what changed
+                        float a0[LV], a1[LV], b0[LV], b1[LV];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float* qa = pa[k] + f * kStageFloats + LV * q;
+                            const float* qb = pb[k] + f * kStageFloats + LV * q;
+                            if (k > 0 && shift[k]) {
+#pragma unroll
+                                for (int l = 0; l < LV; ++l)
+                                    a0[l] = a1[l], b0[l] = b1[l];
+                            }
+                            if (k == 0 || !same[k]) { // right-hand taps: a new cell, whichever way it was reached
+                                ldv(qa + kLvlStride, a1);
+                                ldv(qb + kLvlStride, b1);
+                            }
+                            if (k == 0 || !(same[k] || shift[k])) { // left-hand taps: only when the cell is not the neighbour's
+                                ldv(qa, a0);
+                                ldv(qb, b0);
+                            }
+#pragma unroll
+                            for (int l = 0; l < LV; ++l)
+                                r[f][k][l] = bilinear_full(wx0[k], xf[k], wy0[k], yf[k], a0[l], a1[l], b0[l], b1[l]);
+                        }
+                        continue;
+                    }
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const float* qa = pa[k] + f * kStageFloats + LV * q;
@@ -422,7 +469,7 @@ __global__ void __launch_bounds__(kThreads, (NF == 1 ? (NN ? FB_NN_CTAS : 3) : 2
 #pragma unroll
                         for (int f = 0; f < NF; ++f) {
                             typename Out::type* dst = (f == 0 ? base0 : base1) + off0;
-                            if (NN && vec_ok) {
+                            if (QUAD && vec_ok) {
                                 store_vec4<typename Out::type>(dst, conv(r[f][0][l]), conv(r[f][1][l]), conv(r[f][2][l]), conv(r[f][3][l]));
                             } else {
                                 __stcs(dst, conv(r[f][0][l]));
@@ -504,7 +551,7 @@ __global__ void __launch_bounds__(kThreads, (NF == 1 ? (NN ? FB_NN_CTAS : 3) : 2
 //   TENSOR = false: one cp.async.bulk.global.shared::cta (UBLKCP) per tile row and level, issued by LZ * Tile::Y threads;
 //   TENSOR = true : one cp.async.bulk.tensor.3d (UTMASTG) per batch -- box Tile::X x Tile::Y x LZ over the [z][y][x] output,
 //                   the tensor map clips rows / columns / levels outside the grid.
-// Why (scratch/ubench/tma_store_bw.cu, 2000-wide rows, pure stores): a 64 x 16 tile written with per-thread 128-byte warp
+// Why (profiles/ubench/tma_store_bw.cu, 2000-wide rows, pure stores): a 64 x 16 tile written with per-thread 128-byte warp
 // stores reaches 5.5 TB/s, the same tile through bulk copies 6.2-6.4 TB/s (the copy engine writes each 256-byte row run as one
 // request stream, independent of the lane mapping); and the store leaves the instruction stream: 16 STS with immediate offsets
 // per thread and step instead of 16 STG + their 64-bit address arithmetic (18 % of the instructions of the STG kernel).
@@ -716,7 +763,14 @@ bool tile_table_supported(int ix, int iy, int ox, int oy)
 int tile_table_build(bool nn, const double* d_px, const double* d_py, int ix, int iy, int ox, int oy, TileTable* tt, cudaStream_t st)
 {
     tile_table_free(tt);
-    const int tile_x = nn ? Tile<true>::X : Tile<false>::X, tile_y = nn ? Tile<true>::Y : Tile<false>::Y;
+    // bilinear: the column layout (lane = x, a thread owns 4 rows) unless FIMEX_B200_BILINEAR_QUAD=1 asks for the quad layout
+    // (a thread owns 4 x-neighbours, taps reused in registers, 128-bit stores).  Opt-in after a same-box A/B on config 2
+    // (profiles/r02_bilinear_quad_ab.txt): bit-identical, 22 % fewer shared-load wavefronts and the better store pattern, but
+    // 12.6 ms against 10.9 ms -- the per-lane predicated re-loads and register moves raise the instruction count from 17.5 to
+    // 25 per output and the kernel becomes issue-bound.
+    const char* env = std::getenv("FIMEX_B200_BILINEAR_QUAD");
+    const bool quad = nn || (env && env[0] == '1');
+    const int tile_x = quad ? Tile<true>::X : Tile<false>::X, tile_y = quad ? Tile<true>::Y : Tile<false>::Y;
     tt->tiles_x = (ox + tile_x - 1) / tile_x;
     tt->tiles_y = (oy + tile_y - 1) / tile_y;
     const size_t tiles = (size_t)tt->tiles_x * tt->tiles_y;
@@ -724,14 +778,19 @@ int tile_table_build(bool nn, const double* d_px, const double* d_py, int ix, in
     FB_CUDA_CHECK(cudaMalloc(&tt->d_ncells, sizeof(int) * tiles));
     FB_CUDA_CHECK(cudaMalloc(&tt->d_meta, sizeof(uint4) * tiles * kThreads));
     tt->nn = nn;
+    tt->quad = quad;
     if (nn) {
-        k_compile_tiles<true><<<(unsigned)tiles, kThreads, 0, st>>>(d_px, d_py, ox, oy, ix, iy, tt->tiles_x, tt->d_cells, tt->d_ncells,
-                                                                    tt->d_meta, nullptr, nullptr);
+        k_compile_tiles<true, true><<<(unsigned)tiles, kThreads, 0, st>>>(d_px, d_py, ox, oy, ix, iy, tt->tiles_x, tt->d_cells, tt->d_ncells,
+                                                                          tt->d_meta, nullptr, nullptr);
     } else {
         FB_CUDA_CHECK(cudaMalloc(&tt->d_xf, sizeof(float4) * tiles * kThreads));
         FB_CUDA_CHECK(cudaMalloc(&tt->d_yf, sizeof(float4) * tiles * kThreads));
-        k_compile_tiles<false><<<(unsigned)tiles, kThreads, 0, st>>>(d_px, d_py, ox, oy, ix, iy, tt->tiles_x, tt->d_cells, tt->d_ncells,
-                                                                     tt->d_meta, tt->d_xf, tt->d_yf);
+        if (quad)
+            k_compile_tiles<false, true><<<(unsigned)tiles, kThreads, 0, st>>>(d_px, d_py, ox, oy, ix, iy, tt->tiles_x, tt->d_cells,
+                                                                               tt->d_ncells, tt->d_meta, tt->d_xf, tt->d_yf);
+        else
+            k_compile_tiles<false, false><<<(unsigned)tiles, kThreads, 0, st>>>(d_px, d_py, ox, oy, ix, iy, tt->tiles_x, tt->d_cells,
+                                                                                tt->d_ncells, tt->d_meta, tt->d_xf, tt->d_yf);
     }
     count_launch();
     FB_CUDA_CHECK(cudaGetLastError());
@@ -778,16 +837,24 @@ void launch_staged_as(dim3 grid, const GatherGeom& g, const TileTable& tt, const
 {
     typedef typename Out::type T;
     const int vec_ok = ((g.ox % 4) == 0 && (reinterpret_cast<uintptr_t>(d_out) & (4 * sizeof(T) - 1)) == 0) ? 1 : 0;
-    k_gather_bilinear_staged<NN, 1, false, Out><<<grid, kThreads, kStageBytes, st>>>(g, tt.tiles_x, tt.d_cells, tt.d_ncells, tt.d_meta, tt.d_xf,
-                                                                                      tt.d_yf, d_in, nullptr, static_cast<T*>(d_out), nullptr,
-                                                                                      nullptr, conv, sc.fill_in ? 1 : 0, sc.bad_in[0], 0.f, vec_ok, tile_list);
+    T* out = static_cast<T*>(d_out);
+    const int fill_in = sc.fill_in ? 1 : 0;
+    if (NN || tt.quad)
+        k_gather_bilinear_staged<NN, 1, false, Out, true><<<grid, kThreads, kStageBytes, st>>>(g, tt.tiles_x, tt.d_cells, tt.d_ncells, tt.d_meta,
+                                                                                                tt.d_xf, tt.d_yf, d_in, nullptr, out, nullptr, nullptr,
+                                                                                                conv, fill_in, sc.bad_in[0], 0.f, vec_ok, tile_list);
+    else
+        k_gather_bilinear_staged<false, 1, false, Out, false><<<grid, kThreads, kStageBytes, st>>>(g, tt.tiles_x, tt.d_cells, tt.d_ncells, tt.d_meta,
+                                                                                                    tt.d_xf, tt.d_yf, d_in, nullptr, out, nullptr,
+                                                                                                    nullptr, conv, fill_in, sc.bad_in[0], 0.f, vec_ok,
+                                                                                                    tile_list);
 }
 
-template <bool NN, bool ROT>
-cudaError_t launch_staged_vector(dim3 grid, const GatherGeom& g, const TileTable& tt, const double2* d_cs, const float* d_u, const float* d_v,
-                                 float* d_uo, float* d_vo, const SliceConv& sc, cudaStream_t st)
+template <bool NN, bool ROT, bool QUAD>
+cudaError_t launch_staged_vector_as(dim3 grid, const GatherGeom& g, const TileTable& tt, const double2* d_cs, const float* d_u, const float* d_v,
+                                    float* d_uo, float* d_vo, const SliceConv& sc, cudaStream_t st)
 {
-    auto kernel = k_gather_bilinear_staged<NN, 2, ROT, StorePlain>;
+    auto kernel = k_gather_bilinear_staged<NN, 2, ROT, StorePlain, QUAD>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kStageBytes));
     if (e != cudaSuccess)
         return e;
@@ -796,6 +863,15 @@ cudaError_t launch_staged_vector(dim3 grid, const GatherGeom& g, const TileTable
     kernel<<<grid, kThreads, 2 * kStageBytes, st>>>(g, tt.tiles_x, tt.d_cells, tt.d_ncells, tt.d_meta, tt.d_xf, tt.d_yf, d_u, d_v, d_uo, d_vo, d_cs,
                                                     StorePlain(), sc.fill_in ? 1 : 0, sc.bad_in[0], sc.bad_in[1], vec_ok, nullptr);
     return cudaSuccess;
+}
+
+template <bool NN, bool ROT>
+cudaError_t launch_staged_vector(dim3 grid, const GatherGeom& g, const TileTable& tt, const double2* d_cs, const float* d_u, const float* d_v,
+                                 float* d_uo, float* d_vo, const SliceConv& sc, cudaStream_t st)
+{
+    if (NN || tt.quad)
+        return launch_staged_vector_as<NN, ROT, true>(grid, g, tt, d_cs, d_u, d_v, d_uo, d_vo, sc, st);
+    return launch_staged_vector_as<false, ROT, false>(grid, g, tt, d_cs, d_u, d_v, d_uo, d_vo, sc, st);
 }
 
 template <bool NN>
@@ -932,7 +1008,7 @@ int launch_gather_bilinear_staged(const GatherGeom& g, const TileTable& tt, cons
     }
     if (sc.convert_out && (sc.out_type == FB_T_INT || sc.out_type == FB_T_UINT))
         bulk_type = true;
-    const bool bulk_ok = !tt.nn && mode != 0 && bulk_type && (g.ox * elem) % 16 == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15u) == 0 &&
+    const bool bulk_ok = !tt.nn && !tt.quad && mode != 0 && bulk_type && (g.ox * elem) % 16 == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15u) == 0 &&
                          (g.out_level * (long long)elem) % 16 == 0 && g.nz < 2147483647LL;
     if (bulk_ok) {
         const int lz = env_int("FIMEX_B200_BULK_LEVELS", 8) == 4 ? 4 : 8;

@@ -102,9 +102,11 @@ int fb200_get_device(void);
 /* number of kernels this library has launched so far in the process (bench.py's gpu_launches) */
 unsigned long long fb200_kernel_launches(void);
 /* Page-locked host buffers for full-rate PCIe copies in the host-buffer calls (pageable buffers work too, at a third of
- * the rate).  Freed buffers stay page-locked in a size-keyed cache (FIMEX_B200_PINNED_CACHE_MB, default 8192) and are handed
- * out again, because locking pages costs about as much as copying them and the reference allocates a new output array per
- * interpolateValues call (src/CachedInterpolation.cc:123).  fb200_host_trim releases the cache.  Thread-safe. */
+ * the rate).  Freed buffers stay page-locked in a size-keyed cache and are handed out again, because locking pages costs
+ * about as much as copying them and the reference allocates a new output array per interpolateValues call
+ * (src/CachedInterpolation.cc:123).  The cache keeps at most FIMEX_B200_PINNED_CACHE_MB (parsed once; default: an eighth of
+ * the physical RAM, at most 8192 MB; 0 disables caching); fb200_host_trim releases it.  The buffers are portable
+ * (usable from every device); the calls never change the calling thread's current device.  Thread-safe. */
 void* fb200_host_alloc(size_t bytes);
 void fb200_host_free(void* p);
 void fb200_host_trim(void);

@@ -17,9 +17,13 @@
 #include "../fimex_b200.h"
 
 #include <cstddef>
+#include <cstring>
+#include <list>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace MetNoFimexB200 {
@@ -67,6 +71,14 @@ public:
     virtual void getDataSlice(int inType, const void* inData, size_t size, double badValue, int outType, void* outData, size_t& newSize) const
     {
         if (fb200_interp_get_data_slice(handle_, inType, inData, size, badValue, outType, outData, &newSize) != MIFI_OK)
+            throw CDMException(std::string("error during interpolation: ") + fb200_last_error());
+    }
+    /** The vector branch of CDMInterpolator::getDataSlice (src/CDMInterpolator.cc:259-283) for BOTH components in one pass:
+     *  fill -> NaN, interpolate u and v through one table, rotate (vector may be null), NaN -> fill + cast. */
+    virtual void getVectorSlice(const fb200_vector* vector, int inType, const void* uIn, const void* vIn, size_t size, double badU, double badV,
+                                int outType, void* uOut, void* vOut, size_t& newSize) const
+    {
+        if (fb200_interp_get_vector_slice(handle_, vector, inType, uIn, vIn, size, badU, badV, outType, uOut, vOut, &newSize) != MIFI_OK)
             throw CDMException(std::string("error during interpolation: ") + fb200_last_error());
     }
     virtual size_t getInX() const { return fb200_interp_in_x(handle_); }
@@ -186,6 +198,95 @@ private:
     int ox, oy;
     CachedVectorReprojection(const CachedVectorReprojection&);
     CachedVectorReprojection& operator=(const CachedVectorReprojection&);
+};
+
+/** The other half of an x/y vector pair, parked between the two getDataSlice calls of a pair.
+ *
+ *  The reference interpolates and rotates BOTH components on each component's call and throws one of them away
+ *  (src/CDMInterpolator.cc:259-276): 2x redundant work.  With this cache the first call of a pair computes both halves with
+ *  CachedInterpolationInterface::getVectorSlice, returns its own and parks the counterpart under a key that names the pair and
+ *  the slice (e.g. "x_wind|y_wind|<unLimDimPos>"); the counterpart's call takes it out instead of computing again.
+ *
+ *  A parked half is handed out once.  Bounded (oldest entries are dropped), so a host that never asks for the counterpart only
+ *  loses the saving.  Thread-safe: getDataSlice is called concurrently from OpenMP tasks (src/NetCDF_CDMWriter.cc:749-753).
+ *  The host drops the cache when the interpolation changes (CDMInterpolator::changeProjection). */
+class VectorPairCache
+{
+public:
+    typedef std::shared_ptr<unsigned char[]> bytes;
+    explicit VectorPairCache(size_t slots = 8) : slots_(slots ? slots : 1) {}
+
+    /** park `size` bytes of the counterpart (direction 0 = x, 1 = y) of the pair `key` */
+    void park(const std::string& key, int direction, const void* data, size_t size)
+    {
+        bytes copy(new unsigned char[size ? size : 1]);
+        std::memcpy(copy.get(), data, size);
+        std::lock_guard<std::mutex> lock(mu_);
+        while (entries_.size() >= slots_)
+            entries_.pop_front(); // oldest first
+        entries_.push_back(Entry{key, direction, size, copy});
+    }
+    /** take the parked half out (true and `size` bytes copied to `out`), or false if it is not there (any more) */
+    bool take(const std::string& key, int direction, void* out, size_t size)
+    {
+        bytes found;
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            for (std::list<Entry>::iterator it = entries_.begin(); it != entries_.end(); ++it) {
+                if (it->direction == direction && it->size == size && it->key == key) {
+                    found = it->data;
+                    entries_.erase(it);
+                    break;
+                }
+            }
+        }
+        if (!found)
+            return false;
+        std::memcpy(out, found.get(), size);
+        return true;
+    }
+    void clear()
+    {
+        std::lock_guard<std::mutex> lock(mu_);
+        entries_.clear();
+    }
+    size_t size() const
+    {
+        std::lock_guard<std::mutex> lock(mu_);
+        return entries_.size();
+    }
+
+    /** One component of an x/y pair as CDMInterpolator::getDataSlice returns it, both halves computed at most once:
+     *  `direction` 0: `data` is the x component and `counterpart` the y component, 1: the other way round. */
+    void getDataSlice(const CachedInterpolationInterface& ci, const fb200_vector* vector, const std::string& key, int direction, int inType,
+                      const void* data, const void* counterpart, size_t size, double bad, double badCounterpart, int outType, size_t outElemSize,
+                      void* out, size_t& newSize)
+    {
+        newSize = fb200_interp_new_size(ci.handle(), size);
+        const size_t outBytes = newSize * outElemSize;
+        if (take(key, direction, out, outBytes))
+            return;
+        bytes other(new unsigned char[outBytes ? outBytes : 1]);
+        if (direction == 0)
+            ci.getVectorSlice(vector, inType, data, counterpart, size, bad, badCounterpart, outType, out, other.get(), newSize);
+        else
+            ci.getVectorSlice(vector, inType, counterpart, data, size, badCounterpart, bad, outType, other.get(), out, newSize);
+        std::lock_guard<std::mutex> lock(mu_);
+        while (entries_.size() >= slots_)
+            entries_.pop_front();
+        entries_.push_back(Entry{key, 1 - direction, outBytes, other});
+    }
+
+private:
+    struct Entry {
+        std::string key;
+        int direction;
+        size_t size;
+        bytes data;
+    };
+    size_t slots_;
+    mutable std::mutex mu_;
+    std::list<Entry> entries_;
 };
 
 } // namespace MetNoFimexB200

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -306,6 +307,62 @@ static void test_rotate_vector_to_latlon()
             CHECK(std::fabs(ub[i] - u[i]) < 2e-3 && std::fabs(vb[i] - v[i]) < 2e-3);
 }
 
+// both components of an x/y pair are interpolated and rotated ONCE; the counterpart's getDataSlice call
+// is served from the pair cache (the reference computes the pair twice, src/CDMInterpolator.cc:259-276)
+static void test_vector_pair_cache()
+{
+    using namespace MetNoFimexB200;
+    const size_t inX = 6, inY = 5, outX = 3, outY = 2, n = outX * outY;
+    std::vector<double> px = {2.25, 2.5, 2.75, 2.25, 2.5, 2.75};
+    std::vector<double> py = {1.5, 1.5, 1.5, 2.0, 2.0, 2.0};
+    CachedInterpolation ci("x", "y", FB200_INTERPOL_BILINEAR, px, py, inX, inY, outX, outY);
+    std::shared_ptr<double[]> m(new double[4 * n]);
+    for (size_t i = 0; i < n; ++i) { // 90 degrees: u' = -v, v' = u
+        m[4 * i] = 0.;
+        m[4 * i + 1] = 1.;
+        m[4 * i + 2] = -1.;
+        m[4 * i + 3] = 1.5707963267948966;
+    }
+    CachedVectorReprojection cvr(MIFI_VECTOR_KEEP_SIZE, m, (int)outX, (int)outY);
+    std::vector<float> u(inX * inY), v(inX * inY);
+    for (size_t i = 0; i < u.size(); ++i) {
+        u[i] = (float)i;
+        v[i] = 100.f - (float)i;
+    }
+    u[8] = 9.96921e+36f; // a tap of none of the targets' cells? (x=2, y=1): tap of the first row of targets -> fill values there
+    const double fill = 9.9692099683868690e+36;
+    std::vector<float> wantU(n), wantV(n);
+    size_t ns = 0;
+    ci.getVectorSlice(cvr.handle(), FB200_FLOAT, u.data(), v.data(), u.size(), fill, fill, FB200_FLOAT, wantU.data(), wantV.data(), ns);
+    CHECK(ns == n);
+    VectorPairCache cache(2);
+    const unsigned long long before = fb200_kernel_launches();
+    std::vector<float> gotU(n), gotV(n);
+    cache.getDataSlice(ci, cvr.handle(), "x_wind|y_wind|0", 0, FB200_FLOAT, u.data(), v.data(), u.size(), fill, fill, FB200_FLOAT, sizeof(float),
+                       gotU.data(), ns);
+    const unsigned long long mid = fb200_kernel_launches();
+    CHECK(mid > before && cache.size() == 1);
+    cache.getDataSlice(ci, cvr.handle(), "x_wind|y_wind|0", 1, FB200_FLOAT, v.data(), u.data(), u.size(), fill, fill, FB200_FLOAT, sizeof(float),
+                       gotV.data(), ns);
+    CHECK(fb200_kernel_launches() == mid); // the second half cost no kernel at all
+    CHECK(cache.size() == 0);              // handed out once
+    for (size_t i = 0; i < n; ++i) {
+        CHECK(std::memcmp(&gotU[i], &wantU[i], 4) == 0);
+        CHECK(std::memcmp(&gotV[i], &wantV[i], 4) == 0);
+    }
+    CHECK(gotU[0] == 9.96921e+36f); // the undefined tap reaches both rotated components as the fill value
+    // a different slice of the same pair is a different key; asking for y first works the same way
+    cache.getDataSlice(ci, cvr.handle(), "x_wind|y_wind|1", 1, FB200_FLOAT, v.data(), u.data(), u.size(), fill, fill, FB200_FLOAT, sizeof(float),
+                       gotV.data(), ns);
+    CHECK(cache.size() == 1);
+    std::vector<float> again(n);
+    CHECK(!cache.take("x_wind|y_wind|0", 0, again.data(), n * sizeof(float)));
+    CHECK(cache.take("x_wind|y_wind|1", 0, again.data(), n * sizeof(float)));
+    for (size_t i = 0; i < n; ++i)
+        CHECK(std::memcmp(&again[i], &wantU[i], 4) == 0);
+    cache.clear();
+}
+
 int main()
 {
     test_mifi_points2position();
@@ -319,6 +376,7 @@ int main()
     test_cached_classes();
     test_get_data_slice();
     test_rotate_vector_to_latlon();
+    test_vector_pair_cache();
     std::printf("%d checks, %d failures\n", checks, failures);
     return failures == 0 ? 0 : 1;
 }

@@ -81,6 +81,13 @@ def main():
         assert rc == 1
         out["hirlam_golden_x_wind_rotated"], out["hirlam_golden_y_wind_rotated"] = u.reshape(4, 3, 4), v.reshape(4, 3, 4)
 
+    # test_merger (test/testMerger.cc:44-77): ga_2t_1 of test_merge_inner.nc merged into test_merge_outer.nc
+    for tag, fn in (("inner", "test/test_merge_inner.nc"), ("outer", "test/test_merge_outer.nc")):
+        nc = netcdf_file(os.path.join(ref, fn), "r", mmap=False)
+        out[f"merge_{tag}_proj4"] = np.array(nc.variables["projection_regular_ll"].proj4.decode())
+        for name in ("longitude", "latitude", "ga_2t_1"):
+            out[f"merge_{tag}_{name}"] = native(nc.variables[name].data)
+
     dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "interpolator_fixtures.npz")
     np.savez_compressed(dst, **out)
     for k, v in out.items():

@@ -335,3 +335,34 @@ def test_config1_hirlam12_real_file(fx, oracle):
                                     fx["hirlam_target_x"], fx["hirlam_target_y"], fb.LONGITUDE, fb.LATITUDE)
     assert rc == fb.MIFI_OK
     assert_bit_equal(out.reshape(4, 3, 4), fx["hirlam_golden_air_potential_temperature"], "hirlam12 mifi_interpolate_f")
+
+
+def test_merger(fx, oracle):
+    """test/testMerger.cc:44-77 (test_merger) on the reference's own files: ga_2t_1 of test_merge_inner.nc merged into
+    test_merge_outer.nc on the inner grid extended over the outer one (61 x 113), bilinear, linear border smoothing.  The
+    reference's three known answers -- middle, transition zone, outer -- within its own tolerance 1e-3, and the whole merged
+    field against the same chain evaluated with the CPU oracle's kernels."""
+    proj = str(fx["merge_inner_proj4"])
+    assert proj == str(fx["merge_outer_proj4"])
+    xi, yi = fx["merge_inner_longitude"].astype(np.float64), fx["merge_inner_latitude"].astype(np.float64)
+    xo, yo = fx["merge_outer_longitude"].astype(np.float64), fx["merge_outer_latitude"].astype(np.float64)
+    vi, vo = fx["merge_inner_ga_2t_1"][0, 0], fx["merge_outer_ga_2t_1"][0, 0]
+    merger = fb.Merger(proj, xi, yi, proj, xo, yo, True)
+    merger.setTargetGridFromInner()
+    got = merger.getDataSlice(vi, vo)
+    NLON, NLAT = 61, 113
+    assert got.shape == (NLAT, NLON) and got.dtype == np.float64
+    for ilon, ilat, expected in ((28, 56, 288.104), (24, 56, 288.467), (8, 56, 289.937)):
+        assert abs(got[ilat, ilon] - expected) < 0.001, (ilon, ilat, got[ilat, ilon])
+
+    def interp(src_x, src_y, field, tx, ty):
+        rc, x, y = oracle.project_axes(proj, proj, np.radians(tx), np.radians(ty))
+        px = oracle.points2position(x, np.radians(src_x), 1)
+        py = oracle.points2position(y, np.radians(src_y), 2)
+        return oracle.cached_interpolate(1, px, py, src_x.size, src_y.size, tx.size, ty.size, field.astype(np.float32)[None])[0].astype(np.float64)
+
+    smooth = fb.linear_border_smoothing(vi, interp(xo, yo, vo, xi, yi))
+    top, base = interp(xi, yi, smooth, merger.target_x, merger.target_y), interp(xo, yo, vo, merger.target_x, merger.target_y)
+    want = np.where(np.isnan(top), base, top)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert np.array_equal(got[~np.isnan(got)], want[~np.isnan(want)])

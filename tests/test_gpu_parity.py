@@ -463,9 +463,10 @@ def test_vector_matrix_against_oracle(oracle, target, axes, types):
 @pytest.mark.parametrize("method", [Method.FORWARD_MEAN, Method.FORWARD_MAX, Method.FORWARD_SUM, Method.FORWARD_MIN, Method.FORWARD_MEDIAN,
                                     Method.FORWARD_UNDEF_MEAN, Method.FORWARD_UNDEF_MAX, Method.FORWARD_UNDEF_SUM, Method.FORWARD_UNDEF_MIN])
 @pytest.mark.parametrize("dense", [False, True])
-def test_forward_bit_exact(oracle, method, dense):
+@pytest.mark.parametrize("inZ", [3, 11])  # 11: two passes of four levels per thread + a tail of three single levels
+def test_forward_bit_exact(oracle, method, dense, inZ):
     rng = np.random.default_rng(int(method) * 2 + dense)
-    inX, inY, inZ = 211, 57, 3
+    inX, inY = 211, 57
     outX, outY = (19, 13) if dense else (160, 90)  # dense: ~50 points per cell; sparse: many empty cells
     n = inX * inY
     px = rng.uniform(-2, outX + 1, n)
