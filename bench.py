@@ -446,9 +446,11 @@ def main_b200(args):
     alg_bytes = out_elem * n_out * nlev + in_elem * n_fp * nlev + 16 * n_out  # store + compulsory load + two fp64 positions
     kernel_ms = float(np.mean(per_launch_ms))
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    kernel_name = {0: "k_gather_bilinear_staged<NN>", 1: "k_gather_bilinear_bulk", 2: "k_gather_bicubic_staged"}[method_id]
-    if method_id == 1 and os.environ.get("FIMEX_B200_BULK_STORE", "1") == "0":
-        kernel_name = "k_gather_bilinear_staged"
+    kernel_name = {0: "k_gather_bilinear_staged<NN>", 1: "k_gather_bilinear_staged", 2: "k_gather_bicubic_staged"}[method_id]
+    if method_id == 1 and os.environ.get("FIMEX_B200_BULK_STORE", "0") in ("1", "2") and os.environ.get("FIMEX_B200_BILINEAR_QUAD", "0") != "1":
+        kernel_name = "k_gather_bilinear_bulk"  # opt-in experiment
+    elif method_id == 1 and os.environ.get("FIMEX_B200_BILINEAR_QUAD", "0") == "1":
+        kernel_name = "k_gather_bilinear_staged<QUAD>"  # opt-in experiment
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_src, "kernel": kernel_name,
                 "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_output_value": alg_bytes / values_per_rank,

@@ -13,12 +13,22 @@
  * (pj_init.c, pj_ell_set.c, pj_datum_set.c, pj_transform.c, pj_fwd.c, pj_inv.c, adjlon.c, dmstor.c,
  * aasincos.c, pj_tsfn.c, pj_phi2.c, pj_msfn.c, PJ_latlong.c, PJ_ob_tran.c, PJ_stere.c, PJ_lcc.c) as
  * recalled from its documentation / Snyder, "Map Projections - A Working Manual" (USGS PP 1395).
- * PROJ itself is not available in this image (no source, no binary, no pyproj), so:
- *
- *   PARITY UNPINNED for rotated-pole (ob_tran), Lambert conformal (lcc), ellipsoidal stere and datum
- *   shifts: no reference test pins their coordinates.  Spherical polar-stereographic
- *   <-> lat/long is pinned (weakly) by the reference's own tests test/testInterpolation.cc:265-278,
- *   280-393, 396-512, 515-654, which tests/test_oracle_golden.py re-runs against this file.
+ * PROJ itself is not available in this image (no source, no binary, no pyproj), so this file cannot be compared with
+ * libproj's output.  It is pinned instead by INDEPENDENT known answers (tests/proj_known_answers.py,
+ * tests/test_proj_known_answers.py; the same assertions run against the GPU transforms):
+ *   - Snyder's printed numerical examples, to the printed digits: Lambert conformal conic on the sphere and on the Clarke
+ *     1866 ellipsoid (pp. 295-297), oblique stereographic on the sphere (pp. 312-313), polar stereographic on the
+ *     International ellipsoid (p. 315), forward and inverse;
+ *   - Snyder's equations (14-x, 15-x, 21-x) written out in numpy, on 2e4 random points per case, <= 1e-9 degree of arc:
+ *     lcc and polar stere on sphere / WGS84 / Clarke 1866 / International, oblique stere on the sphere;
+ *   - rotated pole (ob_tran +o_proj=longlat) against an explicit 3-D change of basis built from the CF definition of the
+ *     rotated pole, 1e5 random points, <= 6e-12 degree (<= 2e-11 degree of arc at the poles), and the very mesh of BASELINE
+ *     config 2;
+ *   - the reference's own tests at the PROJ boundary (test/testInterpolation.cc:265-278, 280-393, 396-512, 515-654;
+ *     test/testInterpolator.cc:398-472), re-run in tests/test_oracle_golden.py and tests/test_gpu_parity.py.
+ *   What remains UNPINNED: datum shifts (+towgs84 with non-zero parameters, +nadgrids) and the last-ulp behaviour of libproj
+ *   itself (libm differences) -- no configuration of BASELINE.json or of the reference's tests uses a datum shift
+ *   (SURVEY.md 8c').
  *
  * Supported grammar: +proj=latlong|longlat|latlon|lonlat, ob_tran (+o_proj one of
  * the four lat/long names, +o_lat_p, +o_lon_p), stere (+lat_0 +lon_0 +lat_ts | +k|+k_0), lcc (+lat_1

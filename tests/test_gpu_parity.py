@@ -1257,3 +1257,35 @@ def test_bicubic_fp32_mode_is_opt_in_and_within_tolerance(oracle, monkeypatch):
         assert np.array_equal(np.isnan(f), ~m)
         assert np.nanmax((np.abs(f.astype(np.float64) - e.astype(np.float64)) / su)[m]) <= 2e-5  # two components enter each rotated value
     assert_bit_equal(ci.interpolateValues(field), exact, "bicubic exact again")
+
+
+def test_bilinear_quad_layout_is_bit_identical(oracle, monkeypatch):
+    """FIMEX_B200_BILINEAR_QUAD=1 (read when the tables are built): a thread owns 4 x-neighbours and re-uses the taps of the
+    previous point -- opt-in (slower on B200, profiles/r02_bilinear_quad_ab.txt), same bits: scalar, fill values, int16, u/v with
+    rotation, partial tiles and batches, a many-tap tile"""
+    monkeypatch.setenv("FIMEX_B200_BILINEAR_QUAD", "1")
+    for (inX, inY, inZ, outX, outY, angle, zoom) in ((60, 50, 19, 200, 152, 17.0, 5.0), (90, 70, 70, 331, 77, -33.0, 6.5), (300, 40, 9, 256, 96, 3.0, 0.6)):
+        px, py = _smooth_positions(inX, inY, outX, outY, angle, zoom, 11)
+        rng = np.random.default_rng(inZ + 1)
+        field = rng.normal(250, 30, (inZ, inY, inX)).astype(np.float32)
+        field[rng.random(field.shape) < 0.02] = np.nan
+        want = oracle.cached_interpolate(1, px, py, inX, inY, outX, outY, field)
+        ci = fb.CachedInterpolation("x", "y", Method.BILINEAR, px, py, inX, inY, outX, outY)
+        assert_bit_equal(ci.interpolateValues(field), want, "quad layout, plain float")
+        fill = np.float32(9.96921e+36)
+        got = ci.getDataSlice(np.where(np.isnan(field), fill, field), float(fill))
+        assert_bit_equal(got, np.where(np.isnan(want), fill, want), "quad layout: float with fill values")
+        packed = np.clip(np.round(np.nan_to_num(field, nan=250.0) * 10), -32000, 32000).astype(np.int16)
+        packed[np.isnan(field)] = -32767
+        want16 = oracle.from_float(oracle.cached_interpolate(1, px, py, inX, inY, outX, outY, oracle.as_float(packed, -32767.0)), -32767.0, np.int16)
+        assert np.array_equal(ci.getDataSlice(packed, -32767.0), want16), "quad layout: int16"
+        m = np.zeros((outX * outY, 4))
+        ang = rng.uniform(0, 2 * np.pi, outX * outY)
+        m[:, 0], m[:, 1], m[:, 2], m[:, 3] = np.cos(ang), np.sin(ang), -np.sin(ang), ang
+        cvr = fb.CachedVectorReprojection(fb.MIFI_VECTOR_KEEP_SIZE, m.ravel(), outX, outY)
+        v = rng.normal(0, 10, field.shape).astype(np.float32)
+        gu, gv = ci.interpolateVector(np.nan_to_num(field, nan=1.0), v, cvr)
+        wu, wv = oracle.vector_reproject_by_matrix(m.ravel(), oracle.cached_interpolate(1, px, py, inX, inY, outX, outY, np.nan_to_num(field, nan=1.0)),
+                                                   oracle.cached_interpolate(1, px, py, inX, inY, outX, outY, v), outX, outY, inZ)
+        assert_bit_equal(gu, wu, "quad layout: rotated u")
+        assert_bit_equal(gv, wv, "quad layout: rotated v")
