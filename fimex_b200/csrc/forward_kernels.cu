@@ -51,7 +51,9 @@ enum { AG_SUM = 0, AG_MEAN = 1, AG_MEDIAN = 2, AG_MAX = 3, AG_MIN = 4 };
 #define FB_FWD_CELLS 4
 #endif
 constexpr int kCells = FB_FWD_CELLS; // target cells per thread: their first gathers are issued together (the kernel is bound by the
-                          // dependent chain offsets -> permutation -> value, not by bandwidth)
+                          // dependent chain offsets -> permutation -> value, not by bandwidth).  Measured and rejected (round 2, config 5):
+                          // a second table with the first input index of every cell, read next to the offsets, shortens the chain to
+                          // two loads but adds 72 MB of table traffic per slice: 0.093 ms instead of 0.081 (mean), 0.090 / 0.078 (max)
 
 // one target cell: aggregate its CSR segment [beg, end) in ascending input order; v0 = value of the first entry (prefetched)
 template <int AGG, bool UNDEF>
