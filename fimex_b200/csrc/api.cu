@@ -1128,8 +1128,16 @@ struct PinnedCache {
         {
             std::lock_guard<std::mutex> lock(mu);
             auto it = capacity_of.find(p);
-            if (it == capacity_of.end()) { // not ours (or already released): plain free
-                cudaFreeHost(p);
+            if (it == capacity_of.end()) { // not ours (or already released)
+                // page-locked memory from elsewhere (cudaHostAlloc / cudaMallocHost) is released as such; anything else -- malloc,
+                // new[], a device pointer, a pointer freed twice -- is left alone and reported instead of being handed to cudaFreeHost
+                cudaPointerAttributes a;
+                if (cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeHost) {
+                    cudaFreeHost(p);
+                } else {
+                    cudaGetLastError();
+                    set_error("fb200_host_free: pointer was not allocated by fb200_host_alloc (ignored)");
+                }
                 return;
             }
             cap = it->second;

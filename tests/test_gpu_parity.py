@@ -971,6 +971,12 @@ def test_pinned_host_buffers_are_recycled():
     assert d
     lib.fb200_host_free(d)
     lib.fb200_host_trim()
+    # a pointer that did not come from fb200_host_alloc is left alone (and reported), not handed to cudaFreeHost
+    foreign = np.zeros(1024, dtype=np.float32)
+    lib.fb200_host_free(foreign.ctypes.data_as(C.c_void_p))
+    assert b"not allocated by fb200_host_alloc" in lib.fb200_last_error()
+    assert foreign.sum() == 0
+    lib.fb200_host_free(None)
 
 
 # ---- test_interpolator_vector_backforth (test/testInterpolator.cc:398-472) ----------------------------------------
