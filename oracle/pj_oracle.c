@@ -22,7 +22,7 @@
  *   - Snyder's equations (14-x, 15-x, 21-x) written out in numpy, on 2e4 random points per case, <= 1e-9 degree of arc:
  *     lcc and polar stere on sphere / WGS84 / Clarke 1866 / International, oblique stere on the sphere;
  *   - rotated pole (ob_tran +o_proj=longlat) against an explicit 3-D change of basis built from the CF definition of the
- *     rotated pole, 1e5 random points, <= 6e-12 degree (<= 2e-11 degree of arc at the poles), and the very mesh of BASELINE
+ *     rotated pole, 1e5 random points, <= 1e-12 degree away from the poles of both frames (<= 2e-11 degree of arc at them), and the very mesh of BASELINE
  *     config 2;
  *   - the reference's own tests at the PROJ boundary (test/testInterpolation.cc:265-278, 280-393, 396-512, 515-654;
  *     test/testInterpolator.cc:398-472), re-run in tests/test_oracle_golden.py and tests/test_gpu_parity.py.
