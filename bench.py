@@ -247,11 +247,19 @@ def workload_name(method):
     return f"ERA5-shape {NX}x{NY}x{NZ}x{NT} float32 -> {OUT_N}x{OUT_N} rotated-pole {OUT_STEP_DEG} deg (~2.5 km), {method}"
 
 
-def kernel_source_hash():
-    """sha256 (first 16 hex digits) of the gather kernels' source: profiles/traffic.json is only quoted for the kernel it was measured on"""
+KERNEL_SOURCES = {  # the files a measured-traffic entry of profiles/traffic.json is tied to
+    "k_gather_bilinear_staged": ("staged_kernels.cu", "interp_math.cuh", "convert.cuh", "tables.cuh"),
+    "k_gather_bilinear_staged<NN>": ("staged_kernels.cu", "interp_math.cuh", "convert.cuh", "tables.cuh"),
+    "k_gather_bicubic_staged": ("bicubic_staged.cu", "interp_math.cuh", "convert.cuh"),
+}
+
+
+def kernel_source_hash(kernel="k_gather_bilinear_staged"):
+    """sha256 (first 16 hex digits) of the sources of one gather kernel: profiles/traffic.json is only quoted for the kernel it
+    was measured on"""
     import hashlib
     h = hashlib.sha256()
-    for f in ("staged_kernels.cu", "bicubic_staged.cu", "interp_math.cuh", "convert.cuh"):
+    for f in KERNEL_SOURCES.get(kernel, ("staged_kernels.cu", "bicubic_staged.cu", "interp_math.cuh", "convert.cuh")):
         with open(os.path.join(ROOT, "fimex_b200", "csrc", f), "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()[:16]
@@ -465,7 +473,7 @@ def main_b200(args):
             with open(traffic_file) as f:
                 tr = json.load(f)
             ent = tr.get(kernel_name)
-            if isinstance(ent, dict) and ent.get("source_sha16") == kernel_source_hash() and ent.get("variant", "plain") == args.variant:
+            if isinstance(ent, dict) and ent.get("source_sha16") == kernel_source_hash(kernel_name) and ent.get("variant", "plain") == args.variant:
                 roofline["traffic"] = ent["bytes_per_launch"]
                 roofline["traffic_source"] = ent.get("how")
         except Exception:

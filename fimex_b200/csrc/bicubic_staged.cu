@@ -66,9 +66,10 @@ constexpr int kNL = FB_BIC_NL;
 
 // output-tile slot of tile point p = y*32 + x: 4-float column groups are XOR-permuted by the row, so that the points of
 // one source cell (a block of neighbouring rows and columns) spread over the banks; rows stay readable as float4.
-// (What is left is the conflict rate of 32 effectively random banks: 2.9 wavefronts per store instruction, measured 2.6.  A
-// simulation of config 2's tiles gives 2.8-3.0 for every permutation tried -- xor or add of k * row over all five column bits,
-// rotating the point order inside a group by the group index -- so the layout is not the lever)
+// (What is left is the conflict rate of 32 effectively random banks: 2.8 wavefronts per store instruction in a simulation of
+// config 2's tiles, 2.6 measured, and 2.8-3.0 for every other FIXED permutation tried -- xor or add of k * row over all five
+// column bits, rotating the point order inside a group by the group index.  What does help is scheduling the point order
+// per warp against the banks actually taken: step G of the table compiler)
 __host__ __device__ __forceinline__ int out_slot(int p)
 {
     return (p & ~31) | ((p & 31) ^ (((p >> 5) & 7) << 2));
@@ -300,9 +301,72 @@ __global__ void __launch_bounds__(kT) k_compile_bicubic_tiles(const int* __restr
             }
         }
     }
+    // G. order of the points inside each group.  In the gather, lane l of a warp stores point j of its group in step j; the 32
+    // slots of a step fall into the 32 banks of the output tile like random numbers (2.8 wavefronts per store instruction).  The
+    // order inside a group is free, so every warp of 32 consecutive groups is scheduled greedily: group after group takes the
+    // rotation of its 4 points that collides least with the banks already taken in each step (1.9 wavefronts in a simulation of
+    // config 2's tiles; all 24 permutations or further sweeps gain < 3 % more).  The arithmetic per point is unchanged.
+    __syncthreads(); // the groups written above (global memory, this block) are complete
+    for (int w = t; w * 32 < ngroups; w += kT) {
+        unsigned char occ[4][32];
+        for (int p = 0; p < 4; ++p)
+            for (int b = 0; b < 32; ++b)
+                occ[p][b] = 0;
+        const int g1 = (w * 32 + 32 < ngroups) ? w * 32 + 32 : ngroups;
+        for (int gi = w * 32; gi < g1; ++gi) {
+            const size_t gid = (size_t)inf.z + gi;
+            unsigned short* m16 = reinterpret_cast<unsigned short*>(gmeta + gid);
+            unsigned short sl[4];
+            double2 fr[4];
+            for (int p = 0; p < 4; ++p) {
+                sl[p] = m16[4 + p];
+                fr[p] = gfrac[gid * 4 + p];
+            }
+            int best = 0, best_cost = 1 << 30;
+            for (int r = 0; r < 4; ++r) {
+                int cost = 0;
+                for (int p = 0; p < 4; ++p) {
+                    const unsigned short v = sl[(p + r) & 3];
+                    if (v != (unsigned short)kDump)
+                        cost += occ[p][v & 31];
+                }
+                if (cost < best_cost) {
+                    best_cost = cost;
+                    best = r;
+                }
+            }
+            for (int p = 0; p < 4; ++p) {
+                const unsigned short v = sl[(p + best) & 3];
+                m16[4 + p] = v;
+                gfrac[gid * 4 + p] = fr[(p + best) & 3];
+                if (v != (unsigned short)kDump)
+                    ++occ[p][v & 31];
+            }
+        }
+    }
 }
 
 constexpr size_t kCompileSmem = sizeof(unsigned long long) * kSortN + sizeof(int) * (kMaxTapKeys + 3 * kSortN + kTapCap);
+
+// 4-byte asynchronous global -> shared copy (LDGSTS) and its group control: the fp32 mode stages its taps with these (no
+// conversion is needed, so the values never pass through registers)
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_src)
+{
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_and_wait_all()
+{
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+__device__ __forceinline__ void cp_async_commit()
+{
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
 
 // ------------------------------------------------------------------------------------------------ gather
 // Arithmetic of the gather (template tag ARITH):
@@ -359,8 +423,8 @@ __device__ __forceinline__ void load_group(GroupT<W>& gr, const uint4* __restric
     for (int p = 0; p < 4; ++p) {
         const double2 f = __ldg(gfrac + gid * 4 + p);
         double wx[4], wy[4];
-        cubic_weights(f.x, wx); // fp64, the reference's own sums; rounded once when W is float
-        cubic_weights(f.y, wy);
+        cubic_weights(f.x, wx); // fp64, the reference's own sums; rounded once when W is float2.  (A table of the rounded weights,
+        cubic_weights(f.y, wy); // 32 bytes per point, was measured: 25.2 ms instead of 24.0 -- recomputing per chunk is faster.)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             set_weight(gr.wx[p][i], wx[i]);
@@ -678,6 +742,48 @@ __device__ __forceinline__ void staged_tile(const GatherGeom& g, int tx, int ty,
         }
     };
 
+    // fp32 mode: the same (field, level, tap) assignment, copied global -> shared asynchronously; batch b+1 is in flight while
+    // batch b is consumed.  mifi_bad2nanf is patched in by the thread that copied the value, after the copies have landed.
+    // (the source offsets of this thread's taps are the same for every batch: read once, not behind every copy)
+    int tap_off[NREG];
+    if constexpr (ARITH == kFp32) {
+#pragma unroll
+        for (int j = 0; j < NREG; ++j) {
+            const int r = tap_of(j);
+            tap_off[j] = r < ntaps ? __ldg(taps + inf.x + r) : -1;
+        }
+    }
+    auto stage_async = [&](int buf, long long z) {
+        if constexpr (ARITH == kFp32) {
+            if (z + my_zi < z1) {
+                float* dst = reinterpret_cast<float*>(s_stage) + buf * stage_elems(true) + my_zi;
+#pragma unroll
+                for (int j = 0; j < NREG; ++j) {
+                    if (tap_off[j] >= 0) {
+                        const float* base = (field_of(j) == 0 ? in0 : in1) + (z + my_zi) * g.in_level;
+                        cp_async_f32(dst + field_of(j) * field_stride + tap_of(j) * S, base + tap_off[j]);
+                    }
+                }
+            }
+        }
+    };
+    auto patch_async = [&](int buf, long long z) {
+        if constexpr (ARITH == kFp32) {
+            if (fill_in && z + my_zi < z1) {
+                float* dst = reinterpret_cast<float*>(s_stage) + buf * stage_elems(true) + my_zi;
+#pragma unroll
+                for (int j = 0; j < NREG; ++j) {
+                    const int r = tap_of(j);
+                    if (r < ntaps) {
+                        float* p = dst + field_of(j) * field_stride + r * S;
+                        if (*p == (field_of(j) == 0 ? bad0 : bad1))
+                            *p = undef_f();
+                    }
+                }
+            }
+        }
+    };
+
     // store phase: warp w writes (field, level) row w of the finished output tile, 7 x 128-bit per lane.  Lane l owns
     // tile rows (l >> 3) + 4k; the column group alternates between two values with the parity of k (out_slot()).
     const int st_f = warp / L, st_zi = warp % L;
@@ -721,16 +827,27 @@ __device__ __forceinline__ void staged_tile(const GatherGeom& g, int tx, int ty,
         }
     };
 
-    load(z0);
-    park(0);
-    if (z0 + L < z1)
-        load(z0 + L);
+    if constexpr (ARITH == kFp32) {
+        stage_async(0, z0);
+        cp_async_commit_and_wait_all();
+        patch_async(0, z0);
+    } else {
+        load(z0);
+        park(0);
+        if (z0 + L < z1)
+            load(z0 + L);
+    }
     __syncthreads();
     int buf = 0;
     for (long long z = z0; z < z1; z += L, buf ^= 1) {
         const int nb = (int)((z1 - z) < L ? (z1 - z) : L);
         const TapT* st = s_stage + buf * stage_elems(ARITH == kFp32);
         float* tile = s_out + buf * (kOutRows * kOutRow);
+        if constexpr (ARITH == kFp32) { // the next batch lands in the other buffer while this one is consumed
+            if (z + L < z1)
+                stage_async(buf ^ 1, z + L);
+            cp_async_commit();
+        }
         for (int rd = 0; rd < rounds; ++rd) {
             const int gi = rd * kT + t;
             if (gi < ngroups) {
@@ -747,7 +864,11 @@ __device__ __forceinline__ void staged_tile(const GatherGeom& g, int tx, int ty,
                 }
             }
         }
-        if (z + L < z1) {
+        if constexpr (ARITH == kFp32) {
+            cp_async_wait_all();
+            if (z + L < z1)
+                patch_async(buf ^ 1, z + L);
+        } else if (z + L < z1) {
             park(buf ^ 1);
             if (z + 2 * L < z1)
                 load(z + 2 * L);
