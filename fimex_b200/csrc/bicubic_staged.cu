@@ -34,7 +34,11 @@
 #include "interp_math.cuh"
 #include "convert.cuh"
 
+#include <cuda.h> // CUtensorMap (types only; the encoder comes through cudaGetDriverEntryPoint, libcuda is not linked)
+
 #include <cstdlib>
+#include <cstring>
+#include <type_traits>
 #include <vector>
 
 namespace fb {
@@ -46,6 +50,8 @@ constexpr int kTX = 32, kTY = 28, kTP = kTX * kTY;   // tile of 896 target point
 constexpr int kSortN = 1024;                         // tile points padded to a power of two for the bitonic sort
 constexpr int kDump = kTP;                           // output-tile slot of padding points
 constexpr int kOutRow = kTP + 4;                     // floats per (field, level) of the output tile (multiple of 4)
+constexpr int kOutRowTma = 1024;                     // the same when the tile leaves through the copy engine: every (field, level) row on its own
+                                                     // 4096-byte boundary, so that out_slot() IS the 128-byte swizzle of a tensor-map store
 constexpr int kOutRows = 8;                          // (field, level) rows of the output tile
 constexpr int kStageElems = 8 * kT;                  // tap values staged per batch: 8 registers per thread
 constexpr int kTapCap = kStageElems;                 // tiles with more distinct taps are computed directly
@@ -439,9 +445,40 @@ __device__ __forceinline__ void load_group(GroupT<W>& gr, const uint4* __restric
 // the same sums as fp64 FMA chains with ONE final rounding to fp32 (20 fp64 instructions + 1 conversion) -- not bit-identical,
 // within 1e-5 of the field's magnitude (the tolerance the north star states for interpolated floats), since every
 // intermediate is at least as accurate as the reference's.
-template <int NF, bool ROT, int S, int NL, int ARITH>
+// fp64 arithmetic + rotation + copy-engine stores: 40 KB of taps + 64 KB of output tiles + 14 KB of (cos, sin) would not leave room
+// for two CTAs per SM, so that one combination reads (cos, sin) from global memory instead
+constexpr bool cs_in_shared(int arith, bool rot, bool tmaout)
+{
+    return rot && !(tmaout && arith != 2 /* kFp32 */);
+}
+
+// (cos, sin) of the rotation by output-tile slot: from the shared-memory copy of the tile's values, or -- where that copy would
+// push two CTAs per SM over the shared-memory limit (exact arithmetic + copy-engine stores) -- from global memory through L1
+// (the same 4 addresses per thread in every batch of a chunk)
+struct CsSrc {
+    const double2* smem;  // [kOutRow] by slot, or null
+    const double2* glob;  // the (cos, sin) table of the whole target grid
+    long long base;       // index of the tile's first point
+    int ox;
+    __device__ __forceinline__ double2 get(int slot) const
+    {
+        if (smem)
+            return smem[slot];
+        if (slot >= kTP)
+            return make_double2(1., 0.); // padding slot
+        const int p = out_slot(slot); // out_slot is an involution: slot -> tile point y * 32 + x
+        return __ldg(glob + base + (long long)(p >> 5) * ox + (p & 31));
+    }
+};
+
+// TileConv: what is applied to a result on its way into the output tile -- nothing (the store phase converts), or, when the tile
+// leaves through the copy engine as it is, the float form of interpolationArray2Data (NaN -> fill, -0 -> +0)
+struct TileRaw {
+    __device__ __forceinline__ float operator()(float v) const { return v; }
+};
+template <int NF, bool ROT, int S, int NL, int ARITH, int OR, class TileConv>
 __device__ __forceinline__ void compute_levels(const GroupT<double>& gr, const double* __restrict__ st, int field_stride,
-                                               float* __restrict__ s_out, int out_field_stride, const double2* __restrict__ s_cs)
+                                               float* __restrict__ s_out, int out_field_stride, const CsSrc& s_cs, const TileConv& tc)
 {
     constexpr bool EXACT = ARITH == kExact;
     float a[NL][NF][4];
@@ -493,7 +530,7 @@ __device__ __forceinline__ void compute_levels(const GroupT<double>& gr, const d
     if (ROT) {
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-            const double2 c = s_cs[gr.pt[p]];
+            const double2 c = s_cs.get(gr.pt[p]);
 #pragma unroll
             for (int l = 0; l < NL; ++l)
                 rotate_uv(a[l][0][p], a[l][NF - 1][p], c.x, c.y);
@@ -505,16 +542,16 @@ __device__ __forceinline__ void compute_levels(const GroupT<double>& gr, const d
         for (int f = 0; f < NF; ++f)
 #pragma unroll
             for (int p = 0; p < 4; ++p)
-                s_out[f * out_field_stride + l * kOutRow + gr.pt[p]] = a[l][f][p];
+                s_out[f * out_field_stride + l * OR + gr.pt[p]] = tc(a[l][f][p]);
 }
 
 
 // kFp32: fp32 taps, fp32 weights, 20 multiply-adds per output.  NL = 4 reads four levels of a tap with one 128-bit shared load
 // (the staging buffer is tap-major with a 16-byte aligned stride) and does the arithmetic on level PAIRS with packed
 // fma.rn.f32x2; NL = 1 (partial batches, many-tap tiles) is scalar.  The rotation is done in fp32 as well.
-template <int NF, bool ROT, int S, int NL, int ARITH>
+template <int NF, bool ROT, int S, int NL, int ARITH, int OR, class TileConv>
 __device__ __forceinline__ void compute_levels(const GroupT<float2>& gr, const float* __restrict__ st, int field_stride, float* __restrict__ s_out,
-                                               int out_field_stride, const double2* __restrict__ s_cs)
+                                               int out_field_stride, const CsSrc& s_cs, const TileConv& tc)
 {
     static_assert(NL == 1 || NL == 4, "one level or one 128-bit load of four");
     float a[NL][NF][4];
@@ -571,7 +608,7 @@ __device__ __forceinline__ void compute_levels(const GroupT<float2>& gr, const f
     if (ROT) {
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-            const double2 c = s_cs[gr.pt[p]];
+            const double2 c = s_cs.get(gr.pt[p]);
             const float cc = (float)c.x, ss = (float)c.y;
 #pragma unroll
             for (int l = 0; l < NL; ++l) {
@@ -587,7 +624,7 @@ __device__ __forceinline__ void compute_levels(const GroupT<float2>& gr, const f
         for (int f = 0; f < NF; ++f)
 #pragma unroll
             for (int p = 0; p < 4; ++p)
-                s_out[f * out_field_stride + l * kOutRow + gr.pt[p]] = a[l][f][p];
+                s_out[f * out_field_stride + l * OR + gr.pt[p]] = tc(a[l][f][p]);
 }
 
 // Tiles whose taps do not fit the staging buffers: every point reads its 16 taps from global memory (the arithmetic of
@@ -668,17 +705,38 @@ __device__ void direct_tile(const GatherGeom& g, int tx, int ty, long long z0, l
 // FAST: at most 256 taps; 8/NF levels per batch; warp w stages (field, level) row w of the batch and later stores
 //       (field, level) row w of the output tile.
 // else: up to 2048/NF taps, one level per batch, every thread stages 8/NF taps per field.
-template <int NF, bool ROT, bool FAST, class Out, int ARITH>
+// copy-engine helpers for the output tile (TMAOUT): one cp.async.bulk.tensor.3d (UTMASTG) per (field, level) row of the tile
+__device__ __forceinline__ void tma_store_tile(const CUtensorMap* map, const void* smem, int x, int y, int z)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+                 "r"((unsigned)__cvta_generic_to_shared(smem)), "r"(x), "r"(y), "r"(z)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_wait_read_all()
+{
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_shared()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// TMAOUT: plain float output whose rows are 16-byte aligned: the finished (field, level) rows of the output tile are stored by
+// the copy engine (tensor map with the 128-byte swizzle, which is exactly out_slot(); partial tiles are clipped by the map) while
+// the warps go on with the next batch -- no read-back, no store instructions, no edge cases in the store phase.
+template <int NF, bool ROT, bool FAST, class Out, int ARITH, bool TMAOUT>
 __device__ __forceinline__ void staged_tile(const GatherGeom& g, int tx, int ty, long long z0, long long z1, int4 inf,
                                             const int* __restrict__ taps, const uint4* __restrict__ gmeta, const double2* __restrict__ gfrac,
                                             const double2* __restrict__ cs, const float* __restrict__ in0, const float* __restrict__ in1,
                                             typename Out::type* __restrict__ out0, typename Out::type* __restrict__ out1, bool vec_ok,
                                             typename ArithTypes<ARITH>::tap* s_stage, float* s_out, double2* s_cs, const Out& conv,
-                                            bool fill_in, float bad0, float bad1)
+                                            bool fill_in, float bad0, float bad1, const CUtensorMap* map0, const CUtensorMap* map1)
 {
     typedef typename Out::type OutT;
     typedef typename ArithTypes<ARITH>::tap TapT;
     constexpr int L = FAST ? 8 / NF : 1;
+    constexpr int OR = TMAOUT ? kOutRowTma : kOutRow; // floats per (field, level) row of the output tile
     // tap stride of the tap-major staging buffer.  fp64: odd (in doubles), so that the distinct taps of a warp land in distinct
     // banks.  fp32: a multiple of 4 floats (128-bit loads of four levels) whose first eight multiples fall into eight different
     // 16-byte bank groups: 12 for 8 levels, 4 for 4 levels.
@@ -692,9 +750,22 @@ __device__ __forceinline__ void staged_tile(const GatherGeom& g, int tx, int ty,
     const int rounds = (ngroups + kT - 1) / kT;
 
     // output tiles: NaN everywhere; points outside the 4x4 support are in no group and stay NaN (:1022-1026)
-    for (int i = t; i < 2 * kOutRows * kOutRow; i += kT)
-        s_out[i] = undef_f();
-    if (ROT) {
+    // with TMAOUT the tile holds the FINAL values (Out is float-valued there: StorePlain or StoreAs<float>), otherwise raw results
+    // that the store phase converts
+    typename std::conditional<TMAOUT, Out, TileRaw>::type tile_conv = [&]() {
+        if constexpr (TMAOUT)
+            return conv;
+        else
+            return TileRaw();
+    }();
+    for (int i = t; i < 2 * kOutRows * OR; i += kT)
+        s_out[i] = tile_conv(undef_f());
+    CsSrc cs_src;
+    cs_src.smem = s_cs;
+    cs_src.glob = cs;
+    cs_src.base = (long long)(ty * kTY) * g.ox + (long long)tx * kTX;
+    cs_src.ox = g.ox;
+    if (ROT && s_cs != nullptr) {
         for (int p = t; p < kOutRow; p += kT) {
             double2 c = make_double2(1., 0.);
             int slot = p;
@@ -796,7 +867,7 @@ __device__ __forceinline__ void staged_tile(const GatherGeom& g, int tx, int ty,
     auto store_out = [&](const float* tile, long long z, int nb) {
         if (warp >= NF * L || st_zi >= nb)
             return;
-        const float* src = tile + (st_f * L + st_zi) * kOutRow + lane * 4;
+        const float* src = tile + (st_f * L + st_zi) * OR + lane * 4;
         OutT* lvl = st_out + (z + st_zi) * g.out_level + st_row0;
         if (whole) {
 #pragma unroll
@@ -842,7 +913,7 @@ __device__ __forceinline__ void staged_tile(const GatherGeom& g, int tx, int ty,
     for (long long z = z0; z < z1; z += L, buf ^= 1) {
         const int nb = (int)((z1 - z) < L ? (z1 - z) : L);
         const TapT* st = s_stage + buf * stage_elems(ARITH == kFp32);
-        float* tile = s_out + buf * (kOutRows * kOutRow);
+        float* tile = s_out + buf * (kOutRows * OR);
         if constexpr (ARITH == kFp32) { // the next batch lands in the other buffer while this one is consumed
             if (z + L < z1)
                 stage_async(buf ^ 1, z + L);
@@ -856,11 +927,11 @@ __device__ __forceinline__ void staged_tile(const GatherGeom& g, int tx, int ty,
                 if (L > 1 && nb == L) { // full batch: branch-free, NLV levels per step
 #pragma unroll kBicUnroll
                     for (int zi = 0; zi < L; zi += NLV)
-                        compute_levels<NF, ROT, S, (L > 1 ? NLV : 1), ARITH>(gr, st + zi, field_stride, tile + zi * kOutRow, L * kOutRow, s_cs);
+                        compute_levels<NF, ROT, S, (L > 1 ? NLV : 1), ARITH, OR>(gr, st + zi, field_stride, tile + zi * OR, L * OR, cs_src, tile_conv);
                 } else {
 #pragma unroll 1
                     for (int zi = 0; zi < nb; ++zi)
-                        compute_levels<NF, ROT, S, 1, ARITH>(gr, st + zi, field_stride, tile + zi * kOutRow, L * kOutRow, s_cs);
+                        compute_levels<NF, ROT, S, 1, ARITH, OR>(gr, st + zi, field_stride, tile + zi * OR, L * OR, cs_src, tile_conv);
                 }
             }
         }
@@ -873,14 +944,30 @@ __device__ __forceinline__ void staged_tile(const GatherGeom& g, int tx, int ty,
             if (z + 2 * L < z1)
                 load(z + 2 * L);
         }
+        if constexpr (TMAOUT) {
+            fence_async_shared(); // this thread's tile writes, for the copy engine
+            if (lane == 0)
+                tma_wait_read_all(); // the store issued after the previous barrier has finished reading the OTHER tile, which the
+                                     // next iteration overwrites
+        }
         __syncthreads(); // this batch's output tile is complete and the next batch is parked; the other output tile (being
                          // stored by slower warps) is not written before the next barrier
-        store_out(tile, z, nb);
+        if constexpr (TMAOUT) {
+            if (lane == 0 && warp < NF * L && st_zi < nb)
+                tma_store_tile(st_f == 0 ? map0 : map1, tile + (st_f * L + st_zi) * OR, tx * kTX, ty * kTY, (int)(z + st_zi));
+        } else {
+            store_out(tile, z, nb);
+        }
+    }
+    if constexpr (TMAOUT) {
+        if (lane == 0)
+            tma_wait_read_all(); // shared memory must outlive the copies that read it
     }
 }
 
-template <int NF, bool ROT, class Out, int ARITH>
-__global__ void __launch_bounds__(kT, 2) k_gather_bicubic_staged(GatherGeom g, int tiles_x, const int4* __restrict__ info,
+template <int NF, bool ROT, class Out, int ARITH, bool TMAOUT>
+__global__ void __launch_bounds__(kT, 2) k_gather_bicubic_staged(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+                                                                 GatherGeom g, int tiles_x, const int4* __restrict__ info,
                                                                  const int* __restrict__ taps, const uint4* __restrict__ gmeta,
                                                                  const double2* __restrict__ gfrac, const int* __restrict__ off_tab,
                                                                  const double2* __restrict__ frac_tab, const double2* __restrict__ cs,
@@ -889,10 +976,11 @@ __global__ void __launch_bounds__(kT, 2) k_gather_bicubic_staged(GatherGeom g, i
                                                                  int vec_ok, long long per, Out conv, int fill_in, float bad0, float bad1)
 {
     typedef typename ArithTypes<ARITH>::tap TapT;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int OR = TMAOUT ? kOutRowTma : kOutRow;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     TapT* s_stage = reinterpret_cast<TapT*>(smem_raw);                                         // [2][stage_elems] taps (fp64, or fp32 in fp32 mode)
-    float* s_out = reinterpret_cast<float*>(smem_raw + sizeof(TapT) * 2 * stage_elems(ARITH == kFp32)); // [2][8][kOutRow]
-    double2* s_cs = reinterpret_cast<double2*>(s_out + 2 * kOutRows * kOutRow);                // [kOutRow] (ROT)
+    float* s_out = reinterpret_cast<float*>(smem_raw + sizeof(TapT) * 2 * stage_elems(ARITH == kFp32)); // [2][8][OR]; 1024-byte aligned (TMAOUT)
+    double2* s_cs = cs_in_shared(ARITH, ROT, TMAOUT) ? reinterpret_cast<double2*>(s_out + 2 * kOutRows * OR) : nullptr; // [kOutRow] (ROT)
     const int tile = blockIdx.x;
     const int4 inf = __ldg(info + tile);
     const int tx = tile % tiles_x, ty = tile / tiles_x;
@@ -903,17 +991,22 @@ __global__ void __launch_bounds__(kT, 2) k_gather_bicubic_staged(GatherGeom g, i
     if (inf.y < 0 || NF * inf.y > kStageElems)
         direct_tile<NF, ROT, Out>(g, tx, ty, z0, z1, off_tab, frac_tab, cs, in0, in1, out0, out1, conv, fill_in != 0, bad0, bad1);
     else if (inf.y <= kFastTaps)
-        staged_tile<NF, ROT, true, Out, ARITH>(g, tx, ty, z0, z1, inf, taps, gmeta, gfrac, cs, in0, in1, out0, out1, vec_ok != 0, s_stage, s_out, s_cs,
-                                        conv, fill_in != 0, bad0, bad1);
+        staged_tile<NF, ROT, true, Out, ARITH, TMAOUT>(g, tx, ty, z0, z1, inf, taps, gmeta, gfrac, cs, in0, in1, out0, out1, vec_ok != 0, s_stage,
+                                                       s_out, s_cs, conv, fill_in != 0, bad0, bad1, &map0, &map1);
     else
-        staged_tile<NF, ROT, false, Out, ARITH>(g, tx, ty, z0, z1, inf, taps, gmeta, gfrac, cs, in0, in1, out0, out1, vec_ok != 0, s_stage, s_out,
-                                         s_cs, conv, fill_in != 0, bad0, bad1);
+        staged_tile<NF, ROT, false, Out, ARITH, TMAOUT>(g, tx, ty, z0, z1, inf, taps, gmeta, gfrac, cs, in0, in1, out0, out1, vec_ok != 0, s_stage,
+                                                        s_out, s_cs, conv, fill_in != 0, bad0, bad1, &map0, &map1);
 }
 
-constexpr size_t gather_smem(int arith, bool rot)
+constexpr size_t gather_smem(int arith, bool rot, bool tmaout)
 {
-    return (arith == kFp32 ? sizeof(float) : sizeof(double)) * 2 * stage_elems(arith == kFp32) + sizeof(float) * 2 * kOutRows * kOutRow +
-           (rot ? sizeof(double2) * kOutRow : 0);
+    return (arith == kFp32 ? sizeof(float) : sizeof(double)) * 2 * stage_elems(arith == kFp32) +
+           sizeof(float) * 2 * kOutRows * (tmaout ? kOutRowTma : kOutRow) + (cs_in_shared(arith, rot, tmaout) ? sizeof(double2) * kOutRow : 0);
+}
+// two CTAs per SM must still fit (228 KB per SM, 1 KB reserved per CTA)
+constexpr bool tma_store_fits(int arith, bool rot)
+{
+    return 2 * (gather_smem(arith, rot, true) + 1024) <= 228 * 1024;
 }
 
 } // namespace
@@ -993,18 +1086,75 @@ int bicubic_tiles_build(const int* d_off, const double2* d_frac, int ix, int iy,
 }
 
 namespace {
+// cuTensorMapEncodeTiled through the runtime's driver entry point: the library does not link libcuda
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder()
+{
+    static const EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// [z][y][x] float output as a 3-D tensor of 32 x 28 x 1 boxes with the 128-byte swizzle (== out_slot())
+bool output_tile_map(void* d_out, const GatherGeom& g, CUtensorMap* map)
+{
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc || !d_out)
+        return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)g.ox, (cuuint64_t)g.oy, (cuuint64_t)g.nz};
+    const cuuint64_t strides[2] = {(cuuint64_t)g.ox * sizeof(float), (cuuint64_t)g.out_level * sizeof(float)};
+    const cuuint32_t box[3] = {(cuuint32_t)kTX, (cuuint32_t)kTY, 1u};
+    const cuuint32_t es[3] = {1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, d_out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int NF, bool ROT, int ARITH, class Out, bool TMAOUT>
+int launch_bic_as(dim3 grid, const CUtensorMap& map0, const CUtensorMap& map1, const GatherGeom& g, const BicubicTiles& bt, const int* d_off,
+                  const double2* d_frac, const double2* d_cs, const float* d_in0, const float* d_in1, void* d_out0, void* d_out1, int vec_ok,
+                  long long per, Out conv, const SliceConv& sc, cudaStream_t st)
+{
+    typedef typename Out::type T;
+    constexpr size_t smem = gather_smem(ARITH, ROT, TMAOUT);
+    auto kernel = k_gather_bicubic_staged<NF, ROT, Out, ARITH, TMAOUT>;
+    FB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<grid, kT, smem, st>>>(map0, map1, g, bt.tiles_x, bt.d_info, bt.d_taps, bt.d_gmeta, bt.d_gfrac, d_off, d_frac, d_cs, d_in0, d_in1,
+                                   static_cast<T*>(d_out0), static_cast<T*>(d_out1), vec_ok, per, conv, sc.fill_in ? 1 : 0, sc.bad_in[0],
+                                   sc.bad_in[1]);
+    return FB_OK;
+}
+
+// FIMEX_B200_BICUBIC_TMA=0: per-thread stores for every output (A/B; the copy-engine store is the default where it applies)
+bool bicubic_tma_wanted()
+{
+    const char* env = std::getenv("FIMEX_B200_BICUBIC_TMA");
+    return !(env && env[0] == '0');
+}
+
 template <int NF, bool ROT, int ARITH, class Out>
 int launch_bic(dim3 grid, const GatherGeom& g, const BicubicTiles& bt, const int* d_off, const double2* d_frac, const double2* d_cs,
                const float* d_in0, const float* d_in1, void* d_out0, void* d_out1, int vec_ok, long long per, Out conv, const SliceConv& sc,
                cudaStream_t st)
 {
-    typedef typename Out::type T;
-    constexpr size_t smem = gather_smem(ARITH, ROT);
-    FB_CUDA_CHECK(cudaFuncSetAttribute(k_gather_bicubic_staged<NF, ROT, Out, ARITH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_gather_bicubic_staged<NF, ROT, Out, ARITH><<<grid, kT, smem, st>>>(g, bt.tiles_x, bt.d_info, bt.d_taps, bt.d_gmeta, bt.d_gfrac, d_off, d_frac,
-                                                                         d_cs, d_in0, d_in1, static_cast<T*>(d_out0), static_cast<T*>(d_out1),
-                                                                         vec_ok, per, conv, sc.fill_in ? 1 : 0, sc.bad_in[0], sc.bad_in[1]);
-    return FB_OK;
+    CUtensorMap map0, map1;
+    std::memset(&map0, 0, sizeof(map0));
+    std::memset(&map1, 0, sizeof(map1));
+    // float output (plain, or with NaN -> fill), rows and levels 16-byte aligned, two CTAs per SM still fit: the output tile leaves
+    // through the copy engine
+    if constexpr ((std::is_same<Out, StorePlain>::value || std::is_same<Out, StoreAs<float>>::value) && tma_store_fits(ARITH, ROT)) {
+        if (vec_ok && g.nz < 2147483647LL && bicubic_tma_wanted() && output_tile_map(d_out0, g, &map0) &&
+            (NF == 1 || output_tile_map(d_out1, g, &map1)))
+            return launch_bic_as<NF, ROT, ARITH, Out, true>(grid, map0, map1, g, bt, d_off, d_frac, d_cs, d_in0, d_in1, d_out0, d_out1, vec_ok, per,
+                                                            conv, sc, st);
+    }
+    return launch_bic_as<NF, ROT, ARITH, Out, false>(grid, map0, map1, g, bt, d_off, d_frac, d_cs, d_in0, d_in1, d_out0, d_out1, vec_ok, per, conv,
+                                                     sc, st);
 }
 
 // plain float output in one of the three arithmetic modes
