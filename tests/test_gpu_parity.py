@@ -1295,3 +1295,36 @@ def test_bilinear_quad_layout_is_bit_identical(oracle, monkeypatch):
                                                    oracle.cached_interpolate(1, px, py, inX, inY, outX, outY, v), outX, outY, inZ)
         assert_bit_equal(gu, wu, "quad layout: rotated u")
         assert_bit_equal(gv, wv, "quad layout: rotated v")
+
+
+@pytest.mark.parametrize("tma", ["0", "1"])
+def test_bicubic_store_paths_are_bit_identical(oracle, monkeypatch, tma):
+    """the bicubic gather's two ways out of its shared-memory output tile -- copy engine (cp.async.bulk.tensor.3d, default for
+    float output whose rows are 16-byte aligned) and per-thread stores (FIMEX_B200_BICUBIC_TMA=0; always for other types and
+    unaligned rows): same bits, scalar / fill values / u, v with rotation, whole and partial tiles, partial batches"""
+    monkeypatch.setenv("FIMEX_B200_BICUBIC_TMA", tma)
+    monkeypatch.delenv("FIMEX_B200_BICUBIC_FP32", raising=False)
+    for (inX, inY, inZ, outX, outY, angle, zoom) in ((60, 50, 19, 200, 152, 17.0, 5.0), (90, 70, 70, 332, 77, -33.0, 6.5), (64, 48, 9, 100, 61, 40.0, 3.0)):
+        px, py = _smooth_positions(inX, inY, outX, outY, angle, zoom, 5)
+        rng = np.random.default_rng(inZ + 7)
+        field = rng.normal(250, 30, (inZ, inY, inX)).astype(np.float32)
+        field[rng.random(field.shape) < 0.01] = np.nan
+        want = oracle.cached_interpolate(2, px, py, inX, inY, outX, outY, field)
+        ci = fb.CachedInterpolation("x", "y", Method.BICUBIC, px, py, inX, inY, outX, outY)
+        assert_bit_equal(ci.interpolateValues(field), want, f"bicubic TMA={tma}, plain float")
+        fill = np.float32(9.96921e+36)
+        got = ci.getDataSlice(np.where(np.isnan(field), fill, field), float(fill))
+        assert_bit_equal(got, np.where(np.isnan(want), fill, want), f"bicubic TMA={tma}: float with fill values")
+        m = np.zeros((outX * outY, 4))
+        ang = rng.uniform(0, 2 * np.pi, outX * outY)
+        m[:, 0], m[:, 1], m[:, 2], m[:, 3] = np.cos(ang), np.sin(ang), -np.sin(ang), ang
+        cvr = fb.CachedVectorReprojection(fb.MIFI_VECTOR_KEEP_SIZE, m.ravel(), outX, outY)
+        u = np.nan_to_num(field, nan=1.0)
+        v = rng.normal(0, 10, field.shape).astype(np.float32)
+        gu, gv = ci.interpolateVector(u, v, cvr)
+        wu, wv = oracle.vector_reproject_by_matrix(m.ravel(), oracle.cached_interpolate(2, px, py, inX, inY, outX, outY, u),
+                                                   oracle.cached_interpolate(2, px, py, inX, inY, outX, outY, v), outX, outY, inZ)
+        assert_bit_equal(gu, wu, f"bicubic TMA={tma}: rotated u")
+        assert_bit_equal(gv, wv, f"bicubic TMA={tma}: rotated v")
+        pu, pv = ci.interpolateVector(u, v, None)
+        assert_bit_equal(pu, oracle.cached_interpolate(2, px, py, inX, inY, outX, outY, u), f"bicubic TMA={tma}: u, no rotation")
