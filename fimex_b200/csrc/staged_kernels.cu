@@ -89,6 +89,10 @@ constexpr int kNoTap = 0x7fffffff;
 // the 8 lanes of a quarter warp (consecutive r) start in banks 0, 12, 24, 4, 16, 28, 8, 20: four banks each, no conflict.
 constexpr int kLvlStride = 12;
 constexpr int kFastTaps = kStageFloats / kLvlStride;                // tiles with at most 341 taps use it (all but pole/seam tiles)
+#ifndef FB_NN_BULK_DEFAULT
+#define FB_NN_BULK_DEFAULT 0 // nearest neighbour: 0 = per-thread stores, 1 / 2 = output tile stored by the copy engine (FIMEX_B200_NN_BULK)
+#endif
+constexpr int kNnBulkDefault = FB_NN_BULK_DEFAULT;
 
 // ------------------------------------------------------------------------------------------------ table compiler
 template <bool NN, bool QUAD>
@@ -582,6 +586,17 @@ __device__ __forceinline__ void fence_async_shared() // generic-proxy shared sto
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// four 32-bit values of one level into the shared-memory output tile with one 128-bit store
+template <class T>
+__device__ __forceinline__ void store_tile4(T* dst, T a, T b, T c, T d)
+{
+    static_assert(sizeof(T) == 4, "32-bit elements");
+    uint4 w;
+    w.x = *reinterpret_cast<unsigned*>(&a), w.y = *reinterpret_cast<unsigned*>(&b), w.z = *reinterpret_cast<unsigned*>(&c),
+    w.w = *reinterpret_cast<unsigned*>(&d);
+    *reinterpret_cast<uint4*>(dst) = w;
+}
+
 template <int LZ, bool TENSOR, class Out>
 __global__ void __launch_bounds__(kThreads, LZ == 4 ? 3 : 2)
     k_gather_bilinear_bulk(const __grid_constant__ CUtensorMap omap, GatherGeom g, int tiles_x, const int* __restrict__ taps,
@@ -741,6 +756,137 @@ __global__ void __launch_bounds__(kThreads, LZ == 4 ? 3 : 2)
                     so[zi * kTilePts + k * kRowJump] = conv(v);
                 }
             }
+        }
+        fence_async_shared();
+        zprev = z;
+        nbprev = nb;
+    }
+    __syncthreads();
+    send(buf ^ 1, zprev, nbprev);
+    bulk_wait_read_all(); // shared memory must outlive the copies that read it
+}
+
+
+// ------------------------------------------------------------------------------------------------ nearest neighbour, bulk-store form
+// The copied values of a batch of 8 levels are parked in a shared-memory output tile [8][8][128] (a thread's 4 x-neighbours are
+// one 128-bit shared store per level) and leave through the copy engine as 128 x 8 x 8 boxes (TENSOR) or 512-byte row copies.
+// Unlike the bilinear gather, nearest neighbour loads ONE tap per output, so the shared-memory pipe has room for the extra
+// store and the copy engine's read (3 wavefronts per 32 outputs instead of 2), and the better store pattern shows:
+// profiles/r02_nn_bulk_ab.txt.
+template <bool TENSOR, class Out>
+__global__ void __launch_bounds__(kThreads, 2)
+    k_gather_nn_bulk(const __grid_constant__ CUtensorMap omap, GatherGeom g, int tiles_x, const int* __restrict__ taps,
+                     const int* __restrict__ ntaps_tab, const uint4* __restrict__ meta, const float* __restrict__ in0,
+                     typename Out::type* __restrict__ out0, Out conv, int fill_in, float bad0, int per)
+{
+    typedef typename Out::type T;
+    typedef Tile<true> TL;
+    constexpr int LZ = kMaxBatch;
+    static_assert(sizeof(T) == 4, "32-bit output elements");
+    static_assert(LZ * TL::Y <= kThreads, "one row copy per thread");
+    extern __shared__ __align__(128) float s_dyn[];
+    float* const s_stage = s_dyn;                                    // [2][kStageFloats]
+    T* const s_out = reinterpret_cast<T*>(s_dyn + 2 * kStageFloats); // [2][LZ][TL::Y][TL::X]
+    const int tile = blockIdx.x;
+    const int t = threadIdx.x;
+    const int ntaps = __ldg(ntaps_tab + tile);
+    if (ntaps > kFastTaps)
+        return; // a many-tap tile: done by the STG kernel (TileTable::d_slow)
+    const int* my_taps = taps + (size_t)tile * kMaxTaps;
+    const uint4 m = __ldg(meta + (size_t)tile * kThreads + t);
+    const unsigned mm[4] = {m.x, m.y, m.z, m.w};
+    int ia[4];
+    bool hit[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        ia[k] = (int)(mm[k] & 0xfffu) * kLvlStride;
+        hit[k] = (int)(mm[k] >> 24) == FB_BL_NEAR; // else outside the source grid: MIFI_UNDEFINED_F (interpolation.c:872-875)
+    }
+    const int tx = tile % tiles_x, ty = tile / tiles_x;
+    const long long z0 = (long long)blockIdx.y * per;
+    const long long z1 = z0 + per < g.nz ? z0 + per : g.nz;
+    if (z0 >= z1)
+        return;
+    const int cr_l = t / TL::Y, cr_y = t % TL::Y; // the row this thread copies out (!TENSOR)
+    const int gx0 = tx * TL::X, gy = ty * TL::Y + cr_y;
+    const int cols = g.ox - gx0 < TL::X ? g.ox - gx0 : TL::X;
+    const bool copier = !TENSOR && t < LZ * TL::Y && gy < g.oy;
+    const int tap0 = (t < ntaps) ? __ldg(my_taps + t) : -1;
+
+    auto issue = [&](int buf, long long z, int nb) {
+        float* dst = s_stage + buf * kStageFloats;
+        const float* lv = in0 + z * g.in_level;
+        if (tap0 >= 0) {
+            const float* src = lv + tap0;
+            float* d = dst + t * kLvlStride;
+#pragma unroll
+            for (int zi = 0; zi < LZ; ++zi)
+                if (zi < nb)
+                    cp_async_f32(d + zi, src + zi * g.in_level);
+        }
+        if (ntaps > kThreads) {
+            for (int r = t + kThreads; r < ntaps; r += kThreads) {
+                const float* src = lv + __ldg(my_taps + r);
+                for (int zi = 0; zi < nb; ++zi)
+                    cp_async_f32(dst + r * kLvlStride + zi, src + zi * g.in_level);
+            }
+        }
+        cp_async_commit();
+    };
+    auto patch = [&](int buf, int nb) { // mifi_bad2nanf on the elements this thread copied itself
+        const float nanv = undef_f();
+        float* dst = s_stage + buf * kStageFloats;
+        for (int r = t; r < ntaps; r += kThreads)
+            for (int zi = 0; zi < nb; ++zi)
+                if (dst[r * kLvlStride + zi] == bad0)
+                    dst[r * kLvlStride + zi] = nanv;
+    };
+    auto send = [&](int buf, long long z, int nb) {
+        const T* src = s_out + (size_t)buf * LZ * kTilePts;
+        if (TENSOR) {
+            if (t == 0) {
+                bulk_store_box(&omap, src, gx0, ty * TL::Y, (int)z);
+                bulk_commit();
+            }
+        } else if (copier && cr_l < nb) {
+            bulk_store_row(out0 + (z + cr_l) * g.out_level + (long long)gy * g.ox + gx0, src + (cr_l * TL::Y + cr_y) * TL::X,
+                           (unsigned)(cols * sizeof(T)));
+            bulk_commit();
+        }
+    };
+
+    issue(0, z0, (int)((z1 - z0) < LZ ? (z1 - z0) : LZ));
+    int buf = 0;
+    long long zprev = z0;
+    int nbprev = 0;
+    for (long long z = z0; z < z1; z += LZ, buf ^= 1) {
+        const int nb = (int)((z1 - z) < LZ ? (z1 - z) : LZ);
+        cp_async_wait_pending<0>();
+        if (fill_in)
+            patch(buf, nb);
+        bulk_wait_read_all(); // this thread's copies out of s_out[buf] (issued two batches ago) are done reading it
+        __syncthreads();      // batch z is staged; everyone has finished (and fenced) the output tile of the previous batch
+        if (z + LZ < z1)
+            issue(buf ^ 1, z + LZ, (int)((z1 - z - LZ) < LZ ? (z1 - z - LZ) : LZ));
+        if (nbprev)
+            send(buf ^ 1, zprev, nbprev);
+        const float* lvl = s_stage + buf * kStageFloats;
+        T* so = s_out + (size_t)buf * LZ * kTilePts + 4 * t; // this thread's 4 x-neighbours: tile positions 4t .. 4t+3 of every level
+        const float nanv = undef_f();
+#pragma unroll
+        for (int q = 0; q < LZ / 4; ++q) {
+            float4 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                v[k] = *reinterpret_cast<const float4*>(lvl + ia[k] + 4 * q); // four levels of the point's one tap
+                if (!hit[k])
+                    v[k] = make_float4(nanv, nanv, nanv, nanv);
+            }
+            // levels past nb hold stale values: written to the tile, never sent
+            store_tile4(so + (4 * q + 0) * kTilePts, conv(v[0].x), conv(v[1].x), conv(v[2].x), conv(v[3].x));
+            store_tile4(so + (4 * q + 1) * kTilePts, conv(v[0].y), conv(v[1].y), conv(v[2].y), conv(v[3].y));
+            store_tile4(so + (4 * q + 2) * kTilePts, conv(v[0].z), conv(v[1].z), conv(v[2].z), conv(v[3].z));
+            store_tile4(so + (4 * q + 3) * kTilePts, conv(v[0].w), conv(v[1].w), conv(v[2].w), conv(v[3].w));
         }
         fence_async_shared();
         zprev = z;
@@ -938,14 +1084,15 @@ EncodeTiledFn tensor_map_encoder()
 }
 
 // 3-D map of the [z][y][x] output for boxes of Tile::X x Tile::Y x lz elements
-bool output_tensor_map(void* d_out, const GatherGeom& g, size_t elem, int lz, CUtensorMap* map)
+bool output_tensor_map(void* d_out, const GatherGeom& g, size_t elem, int lz, CUtensorMap* map, bool quad = false)
 {
     EncodeTiledFn enc = tensor_map_encoder();
     if (!enc)
         return false;
     const cuuint64_t dims[3] = {(cuuint64_t)g.ox, (cuuint64_t)g.oy, (cuuint64_t)g.nz};
     const cuuint64_t strides[2] = {(cuuint64_t)g.ox * elem, (cuuint64_t)g.out_level * elem};
-    const cuuint32_t box[3] = {(cuuint32_t)Tile<false>::X, (cuuint32_t)Tile<false>::Y, (cuuint32_t)lz};
+    const cuuint32_t box[3] = {(cuuint32_t)(quad ? Tile<true>::X : Tile<false>::X), (cuuint32_t)(quad ? Tile<true>::Y : Tile<false>::Y),
+                               (cuuint32_t)lz};
     const cuuint32_t es[3] = {1, 1, 1};
     const CUtensorMapDataType dt = elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16; // moved as bits
     return enc(map, dt, 3, d_out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -994,6 +1141,60 @@ int launch_gather_bilinear_staged(const GatherGeom& g, const TileTable& tt, cons
     if (g.out_level == 0 || g.nz == 0)
         return FB_OK;
     const unsigned tiles = (unsigned)tt.tiles_x * (unsigned)tt.tiles_y;
+    // ---- nearest neighbour, 32-bit output elements: output tile in shared memory, stored by the copy engine ----
+    // FIMEX_B200_NN_BULK: 0 = per-thread 128-bit stores, 1 = 512-byte row copies, 2 = tensor boxes 128 x 8 x 8
+    {
+        const int nn_mode = env_int("FIMEX_B200_NN_BULK", kNnBulkDefault);
+        const bool t32 = !sc.convert_out || sc.out_type == FB_T_FLOAT || sc.out_type == FB_T_INT || sc.out_type == FB_T_UINT;
+        if (tt.nn && nn_mode != 0 && t32 && (g.ox % 4) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15u) == 0 && g.nz < 2147483647LL) {
+            const bool tensor = nn_mode == 2;
+            const int chunks = z_chunks(tiles, g.nz, env_int("FIMEX_B200_BULK_CHUNK", 64));
+            int per = (int)((g.nz + chunks - 1) / chunks);
+            per = (per + kMaxBatch - 1) / kMaxBatch * kMaxBatch; // whole batches per chunk: a tensor box never reaches into the next chunk
+            dim3 grid(tiles, (unsigned)((g.nz + per - 1) / per));
+            CUtensorMap map;
+            std::memset(&map, 0, sizeof(map));
+            FB_REQUIRE(!tensor || output_tensor_map(d_out, g, 4, kMaxBatch, &map, true), "cuTensorMapEncodeTiled failed for the output tensor");
+            cudaError_t e = cudaErrorInvalidValue;
+            const size_t smem = 2 * kStageFloats * sizeof(float) + 2 * (size_t)kMaxBatch * kTilePts * 4;
+            auto go = [&](auto conv) -> cudaError_t {
+                typedef decltype(conv) C;
+                typedef typename C::type T;
+                cudaError_t err;
+                if (tensor) {
+                    auto kernel = k_gather_nn_bulk<true, C>;
+                    if ((err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+                        return err;
+                    kernel<<<grid, kThreads, smem, st>>>(map, g, tt.tiles_x, tt.d_cells, tt.d_ncells, tt.d_meta, d_in, static_cast<T*>(d_out), conv,
+                                                         sc.fill_in ? 1 : 0, sc.bad_in[0], per);
+                } else {
+                    auto kernel = k_gather_nn_bulk<false, C>;
+                    if ((err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+                        return err;
+                    kernel<<<grid, kThreads, smem, st>>>(map, g, tt.tiles_x, tt.d_cells, tt.d_ncells, tt.d_meta, d_in, static_cast<T*>(d_out), conv,
+                                                         sc.fill_in ? 1 : 0, sc.bad_in[0], per);
+                }
+                return cudaGetLastError();
+            };
+            if (!sc.convert_out)
+                e = go(StorePlain());
+            else if (sc.out_type == FB_T_FLOAT)
+                e = go(StoreAs<float>{cast_fill<float>(sc.fill_out)});
+            else if (sc.out_type == FB_T_INT)
+                e = go(StoreAs<int>{cast_fill<int>(sc.fill_out)});
+            else
+                e = go(StoreAs<unsigned int>{cast_fill<unsigned int>(sc.fill_out)});
+            FB_CUDA_CHECK(e);
+            count_launch();
+            if (tt.n_slow > 0) { // the many-tap tiles, through the STG kernel
+                dim3 sgrid((unsigned)tt.n_slow, z_chunks(tt.n_slow, g.nz, 64));
+                FB_REQUIRE(launch_staged_typed<true>(sgrid, g, tt, d_in, d_out, sc, st, tt.d_slow), "staged gather: unsupported output type");
+                count_launch();
+                FB_CUDA_CHECK(cudaGetLastError());
+            }
+            return FB_OK;
+        }
+    }
     // ---- bilinear, 2- and 4-byte output elements: output tiles staged in shared memory, stored by the copy engine ----
     // Opt-in (default 0): measured on config 2, same box (profiles/r02_bulk_store_ab.txt), the bulk-store forms are bit-identical
     // but SLOWER than per-thread STG -- 12.8 ms (tensor boxes, 8 levels) / 14.6 ms (row copies) against 10.9 ms -- although the

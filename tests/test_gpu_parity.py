@@ -1328,3 +1328,26 @@ def test_bicubic_store_paths_are_bit_identical(oracle, monkeypatch, tma):
         assert_bit_equal(gv, wv, f"bicubic TMA={tma}: rotated v")
         pu, pv = ci.interpolateVector(u, v, None)
         assert_bit_equal(pu, oracle.cached_interpolate(2, px, py, inX, inY, outX, outY, u), f"bicubic TMA={tma}: u, no rotation")
+
+
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_nearest_neighbour_bulk_store_forms_are_bit_identical(oracle, monkeypatch, mode):
+    """FIMEX_B200_NN_BULK=1 (cp.async.bulk row copies) / 2 (cp.async.bulk.tensor boxes): the nearest-neighbour gather with its output
+    tile in shared memory -- opt-in (slower on B200, profiles/r02_nn_bulk_ab.txt), same bits, NaN payload included: plain,
+    fill values, int32 output, partial tiles and batches, a many-tap tile"""
+    monkeypatch.setenv("FIMEX_B200_NN_BULK", mode)
+    for (inX, inY, inZ, outX, outY, angle, zoom) in ((60, 50, 19, 200, 152, 17.0, 5.0), (90, 70, 70, 332, 77, -33.0, 6.5), (300, 40, 9, 256, 96, 3.0, 0.6)):
+        px, py = _smooth_positions(inX, inY, outX, outY, angle, zoom, 3)
+        rng = np.random.default_rng(inZ + 2)
+        field = rng.normal(250, 30, (inZ, inY, inX)).astype(np.float32)
+        field[rng.random(field.shape) < 0.02] = np.nan
+        want = oracle.cached_interpolate(0, px, py, inX, inY, outX, outY, field)
+        ci = fb.CachedInterpolation("x", "y", Method.NEAREST_NEIGHBOR, px, py, inX, inY, outX, outY)
+        assert_bit_equal(ci.interpolateValues(field), want, f"NN bulk mode {mode}", nan_payload=True)
+        fill = np.float32(9.96921e+36)
+        got = ci.getDataSlice(np.where(np.isnan(field), fill, field), float(fill))
+        assert_bit_equal(got, np.where(np.isnan(want), fill, want), f"NN bulk mode {mode}: fill values")
+        ints = rng.integers(-100000, 100000, field.shape).astype(np.int32)
+        ints[rng.random(field.shape) < 0.02] = -2147483647
+        want32 = oracle.from_float(oracle.cached_interpolate(0, px, py, inX, inY, outX, outY, oracle.as_float(ints, -2147483647.0)), -2147483647.0, np.int32)
+        assert np.array_equal(ci.getDataSlice(ints, -2147483647.0), want32), f"NN bulk mode {mode}: int32"
