@@ -1193,10 +1193,17 @@ int launch_gather_bicubic_staged(const GatherGeom& g, const BicubicTiles& bt, co
     if (g.out_level == 0 || g.nz == 0)
         return FB_OK;
     const unsigned tiles = (unsigned)bt.tiles_x * (unsigned)bt.tiles_y;
-    // Level chunks: 64 levels like the other gathers (longer chunks are slower here too: CTAs drift apart in z and the set of
-    // DRAM pages being written grows -- 3288-level chunks cost 20 % more time), always a multiple of the 8-level batch so
-    // that only the last chunk has a partial batch; shorter chunks only to fill the SMs of small grids.
-    long long per = 64;
+    // Level chunks: 128 levels where the copy engine stores the output tile (64 with per-thread stores), always a multiple of the 8-level batch so that only the last chunk has a partial batch; shorter
+    // chunks only to fill the SMs of small grids.  (Round 1, per-thread stores: 64-level chunks, because CTAs that own long
+    // level ranges drift apart and the set of DRAM pages being written grows -- 3288-level chunks cost 20 % more time.  With the
+    // output tile stored by the copy engine, same box: fp32 mode 64 / 96 / 128 / 192 levels -> 20.24 / 19.59 / 19.35 / 19.23 ms,
+    // exact 64 / 128 -> 44.42 / 43.76 ms: per-chunk set-up -- group weights, tile initialisation -- outweighs the drift now.)
+    const bool two = d_in1 != nullptr;
+    const size_t elem = (two || !sc.convert_out) ? sizeof(float) : type_size(sc.out_type);
+    const uintptr_t align = reinterpret_cast<uintptr_t>(d_out0) | (two ? reinterpret_cast<uintptr_t>(d_out1) : 0);
+    const int vec_ok = ((g.ox % 4) == 0 && (align & (4 * elem - 1)) == 0) ? 1 : 0;
+    const bool engine_stores = vec_ok && (!sc.convert_out || sc.out_type == FB_T_FLOAT) && bicubic_tma_wanted() && tensor_map_encoder() != nullptr;
+    long long per = engine_stores ? 128 : 64;
     const long long want = 4ll * sm_count();
     while (per > 8 && tiles * ((g.nz + per - 1) / per) < want)
         per -= 8;
@@ -1209,10 +1216,6 @@ int launch_gather_bicubic_staged(const GatherGeom& g, const BicubicTiles& bt, co
         per = (g.nz + gy - 1) / gy;
     }
     dim3 grid(tiles, (unsigned)gy);
-    const bool two = d_in1 != nullptr;
-    const size_t elem = (two || !sc.convert_out) ? sizeof(float) : type_size(sc.out_type);
-    const uintptr_t align = reinterpret_cast<uintptr_t>(d_out0) | (two ? reinterpret_cast<uintptr_t>(d_out1) : 0);
-    const int vec_ok = ((g.ox % 4) == 0 && (align & (4 * elem - 1)) == 0) ? 1 : 0;
     int rc = FB_ERROR;
     const int arith = bicubic_arith();
     if (two) {
